@@ -1,0 +1,33 @@
+#!/bin/sh
+# Build the reference's own assignment solver (vendored lp_solve 5.5.2.5 + lp_transbig_edit)
+# from the sources where they lie under /root/reference into oracle/_ref/ (git-ignored).
+# TEST INFRASTRUCTURE ONLY.  No reference source is copied into the repo: the C function
+# lp_transbig_edit (src/my_lpsolve.cpp:34-122, plain C inside an Rcpp file) is extracted at
+# build time into the ignored output directory.  Include flags follow src/Makevars:1.
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+REF=${BMM_REFERENCE:-/root/reference}
+OUT="$HERE/_ref"
+if [ ! -d "$REF/src" ]; then
+  echo "build_ref: $REF not present; keeping prebuilt $OUT (if any)"; exit 0
+fi
+mkdir -p "$OUT/obj"
+S="$REF/src"
+INC="-I$S/ls_source -I$S/ls_source/bfp -I$S/ls_source/bfp/bfp_LUSOL -I$S/ls_source/bfp/bfp_LUSOL/LUSOL -I$S/ls_source/colamd -I$S/ls_source/shared"
+{
+  echo '#include <stdlib.h>'
+  echo '#include "lp_lib.h"'
+  echo 'void lp_transbig_edit(int, int, double *, double *);'
+  sed -n '34,122p' "$S/my_lpsolve.cpp"
+} > "$OUT/lp_transbig_edit_extracted.c"
+OBJS=""
+for f in "$S"/*.c "$OUT/lp_transbig_edit_extracted.c"; do
+  o="$OUT/obj/$(basename "$f" .c).o"
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then
+    gcc -O2 -fPIC -w $INC -c "$f" -o "$o" &
+  fi
+  OBJS="$OBJS $o"
+done
+wait
+gcc -shared -o "$OUT/liblpsolve_ref.so" $OBJS -lm -ldl
+echo "build_ref: built $OUT/liblpsolve_ref.so"
