@@ -1,0 +1,588 @@
+// Host side of the C ABI declared in include/bmm_capi.h: argument checks, bit-packing and row
+// de-duplication of X, device-resident plans, launches, result download.  No CPU fallback: every
+// compute entry point needs a CUDA device and fails with BMM_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bmm_capi.h"
+#include "assign.cuh"
+#include "kernels.h"
+
+#define BMM_FLAG_PROBE_PROBS 0x100u
+#define BMM_FLAG_PROBE_LOGLIK 0x200u
+
+namespace bmm {
+bool full_rows_fit_smem(int U, int K);
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(BMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n, bool zero = true) {
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        return zero ? cudaMemset(p, 0, n) : cudaSuccess;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct VecHash {
+    size_t operator()(const std::vector<uint32_t> &v) const {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t w : v) { h ^= w; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+
+}  // namespace
+
+struct bmm_plan {
+    int sampler = 0;
+    bmm_args a{};
+    int C = 1, N = 0, P = 0, K = 0, W = 0, U = 0, S = 0, ns = 0;
+    bool relabel = false, replay = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    bmm::FullParams fp{};
+    bmm::CollapsedParams cp{};
+    // data
+    DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG;
+    // state
+    DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status;
+    DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws;
+    // histories
+    DevBuf zhist, theta_out, theta_rel_out, pi_out, alpha_out, perm_out, probs_out, loglik_out, kactive;
+    DevBuf z_orig, z_rel, Qexp;
+    // replay
+    DevBuf ru, rpi, rtheta, ralpha;
+    bool ran = false;
+    ~bmm_plan() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evk0) cudaEventDestroy(evk0);
+        if (evk1) cudaEventDestroy(evk1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int check_args(int sampler, const bmm_args *a, const bmm_init *init) {
+    if (!a) return fail(BMM_ERR_INVALID, "args is NULL");
+    if (!a->X || a->N <= 0 || a->P <= 0) return fail(BMM_ERR_INVALID, "X must be a non-empty N x P matrix");
+    if (a->nsamples < 2) return fail(BMM_ERR_INVALID, "nsamples must be >= 2");
+    if (a->K < 1 || a->K > 255) return fail(BMM_ERR_INVALID, "K / maxK must be in 1..255");
+    if (a->burnin < 0 || a->burnin >= a->nsamples) return fail(BMM_ERR_INVALID, "burnin must be in [0, nsamples)");
+    if (a->relabel) {
+        // the reference's behaviour is undefined otherwise
+        if (a->burnin < 2) return fail(BMM_ERR_INVALID, "relabel needs burnin >= 2 (Q is initialised at sweep burnin-1)");
+        if (a->burnrelabel < 1 || a->burnrelabel > a->burnin)
+            return fail(BMM_ERR_INVALID, "relabel needs 1 <= burnrelabel <= burnin");
+    }
+    if (!(a->beta > 0) || !(a->gamma > 0)) return fail(BMM_ERR_INVALID, "beta and gamma must be > 0");
+    if (a->alpha < 0) return fail(BMM_ERR_INVALID, "alpha must be >= 0 (0 = sample it)");
+    if (a->precision != BMM_FP64 && a->precision != BMM_FP32) return fail(BMM_ERR_INVALID, "precision must be BMM_FP64 or BMM_FP32");
+    if (sampler == BMM_SAMPLER_DP && a->beta != a->gamma)
+        return fail(BMM_ERR_BETA_GAMMA, "Error: sampler currently not implemented for non-symmetric priors on beta and gamma");
+    if (sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING) {
+        if (!init || !init->pi || !init->theta) return fail(BMM_ERR_INVALID, "initialPi / initialTheta required");
+    }
+    if (sampler == BMM_SAMPLER_COLLAPSED && (!init || !init->z)) return fail(BMM_ERR_INVALID, "initialK required");
+    if (a->replay) {
+        const bmm_replay *r = a->replay;
+        if (!r->u || r->u_slots < 1) return fail(BMM_ERR_INVALID, "replay needs u and u_slots");
+        if ((sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING) && (!r->pi || !r->theta || !r->alpha))
+            return fail(BMM_ERR_INVALID, "replay of an uncollapsed sampler needs pi, theta and alpha histories");
+    }
+    return BMM_OK;
+}
+
+// X (N x P int32 cm) -> bit-packed rows [N][W]; rejects non-binary input.
+int pack_rows(const int32_t *X, int N, int P, std::vector<uint32_t> &bits, int &W) {
+    W = (P + 31) / 32;
+    bits.assign((size_t)N * W, 0u);
+    for (int d = 0; d < P; ++d) {
+        const int32_t *col = X + (size_t)N * d;
+        const uint32_t m = 1u << (d & 31);
+        const int w = d >> 5;
+        for (int i = 0; i < N; ++i) {
+            const int32_t v = col[i];
+            if (v == 1) bits[(size_t)i * W + w] |= m;
+            else if (v != 0) return fail(BMM_ERR_NOT_BINARY, "X must contain only 0/1 (the bit-packed path rejects other integers)");
+        }
+    }
+    return BMM_OK;
+}
+
+template <typename T>
+int upload(DevBuf &b, const T *src, size_t n) {
+    CU(b.alloc(n * sizeof(T), false));
+    if (n) CU(cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return BMM_OK;
+}
+
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+int create_full(bmm_plan *pl, const bmm_init *init) {
+    const bmm_args &a = pl->a;
+    const int N = pl->N, P = pl->P, K = pl->K, C = pl->C, ns = pl->ns, S = pl->S;
+    std::vector<uint32_t> bits;
+    int W;
+    TRY(pack_rows(a.X, N, P, bits, W));
+    pl->W = W;
+    // de-duplicate rows (first-occurrence order)
+    std::vector<int> rowid(N), wt;
+    std::vector<uint32_t> rowbits;
+    {
+        std::unordered_map<std::vector<uint32_t>, int, VecHash> seen;
+        std::vector<uint32_t> key(W);
+        for (int i = 0; i < N; ++i) {
+            for (int w = 0; w < W; ++w) key[w] = bits[(size_t)i * W + w];
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                int u = (int)wt.size();
+                seen.emplace(key, u);
+                wt.push_back(1);
+                rowbits.insert(rowbits.end(), key.begin(), key.end());
+                rowid[i] = u;
+            } else {
+                wt[it->second]++;
+                rowid[i] = it->second;
+            }
+        }
+    }
+    const int U = (int)wt.size();
+    pl->U = U;
+    const size_t UK = (size_t)U * K, KP = (size_t)K * P;
+    TRY(upload(pl->rowbits, rowbits.data(), rowbits.size()));
+    TRY(upload(pl->rowid, rowid.data(), rowid.size()));
+    TRY(upload(pl->wt, wt.data(), wt.size()));
+    // initial state
+    TRY(upload(pl->theta_cur, init->theta, (size_t)C * KP));
+    TRY(upload(pl->pi_cur, init->pi, (size_t)C * K));
+    std::vector<double> al(C, a.alpha == 0 ? 1.0 : a.alpha);
+    TRY(upload(pl->alpha_cur, al.data(), al.size()));
+    const bool use_hist = bmm::full_rows_fit_smem(U, K);
+    const bool probes = (a.flags & (BMM_FLAG_PROBE_PROBS | BMM_FLAG_PROBE_LOGLIK)) != 0;
+    (void)probes;
+    if (pl->relabel) {
+        CU(pl->Q.alloc((size_t)C * UK * 8));
+        CU(pl->logQ.alloc((size_t)C * UK * 8));
+        CU(pl->cube.alloc((size_t)C * a.burnrelabel * UK * 8));
+        CU(pl->logp.alloc((size_t)C * a.burnrelabel * UK * 8));
+        CU(pl->sb_perm.alloc((size_t)C * a.burnrelabel * K * 4));
+        CU(pl->sb_cost.alloc((size_t)C * a.burnrelabel * K * K * 8));
+        CU(pl->sb_ws.alloc((size_t)C * a.burnrelabel * bmm::assign_ws_bytes(K)));
+        CU(pl->perm_out.alloc((size_t)C * S * K * 4));
+        CU(pl->theta_rel_out.alloc((size_t)C * KP * S * 8));
+    }
+    if (!use_hist) CU(pl->prob_g.alloc((size_t)C * UK * 8));
+    if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->ll_g.alloc((size_t)C * UK * 8));
+    CU(pl->assign_ws.alloc((size_t)C * bmm::assign_ws_bytes(K)));
+    CU(pl->status.alloc((size_t)C * 4));
+    CU(pl->zhist.alloc((size_t)C * ns * N));
+    CU(pl->theta_out.alloc((size_t)C * KP * S * 8));
+    CU(pl->pi_out.alloc((size_t)C * S * K * 8));
+    CU(pl->alpha_out.alloc((size_t)C * S * 8));
+    if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)C * ns * N * K * 8));
+    if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->loglik_out.alloc((size_t)C * ns * N * K * 8));
+    if (a.replay) {
+        const bmm_replay *r = a.replay;
+        TRY(upload(pl->ru, r->u, (size_t)C * ns * N * r->u_slots));
+        TRY(upload(pl->rpi, r->pi, (size_t)C * ns * K));
+        TRY(upload(pl->rtheta, r->theta, (size_t)C * KP * ns));
+        TRY(upload(pl->ralpha, r->alpha, (size_t)C * ns));
+    }
+    bmm::FullParams &f = pl->fp;
+    f.N = N; f.P = P; f.K = K; f.U = U; f.W = W;
+    f.nsamples = ns; f.burnin = a.burnin; f.relabel = pl->relabel; f.burnrelabel = a.burnrelabel;
+    f.stickbreaking = pl->sampler == BMM_SAMPLER_STICKBREAKING;
+    f.alpha0 = a.alpha; f.beta = a.beta; f.gamma = a.gamma; f.a = a.a; f.b = a.b;
+    f.seed = a.seed; f.chain_offset = a.chain_offset; f.flags = a.flags; f.use_hist = use_hist;
+    f.rowbits = pl->rowbits.as<uint32_t>(); f.rowid = pl->rowid.as<int>(); f.wt = pl->wt.as<int>();
+    f.theta_cur = pl->theta_cur.as<double>(); f.pi_cur = pl->pi_cur.as<double>(); f.alpha_cur = pl->alpha_cur.as<double>();
+    f.Q = pl->Q.as<double>(); f.logQ = pl->logQ.as<double>(); f.cube = pl->cube.as<double>();
+    f.prob_g = pl->prob_g.as<double>(); f.hist_g = nullptr; f.ll_g = pl->ll_g.as<double>();
+    f.assign_ws = pl->assign_ws.as<char>(); f.status = pl->status.as<int>();
+    f.zhist = pl->zhist.as<uint8_t>(); f.theta_out = pl->theta_out.as<double>(); f.theta_rel_out = pl->theta_rel_out.as<double>();
+    f.pi_out = pl->pi_out.as<double>(); f.alpha_out = pl->alpha_out.as<double>(); f.perm_out = pl->perm_out.as<int>();
+    f.probs_out = pl->probs_out.as<double>(); f.loglik_out = pl->loglik_out.as<double>();
+    f.ru = pl->ru.as<double>(); f.ru_slots = a.replay ? a.replay->u_slots : 0;
+    f.rpi = pl->rpi.as<double>(); f.rtheta = pl->rtheta.as<double>(); f.ralpha = pl->ralpha.as<double>();
+    size_t smem = bmm::full_smem_bytes(f, 128);
+    if (smem > 200 * 1024) return fail(BMM_ERR_UNSUPPORTED, "K*P too large for the chain-per-block kernel");
+    return BMM_OK;
+}
+
+int create_collapsed(bmm_plan *pl, const bmm_init *init) {
+    const bmm_args &a = pl->a;
+    const int N = pl->N, P = pl->P, K = pl->K, C = pl->C, ns = pl->ns, S = pl->S;
+    const bool dp = pl->sampler == BMM_SAMPLER_DP;
+    std::vector<uint32_t> bits;
+    int W;
+    TRY(pack_rows(a.X, N, P, bits, W));
+    pl->W = W; pl->U = N;
+    TRY(upload(pl->xbits, bits.data(), bits.size()));
+    std::vector<double> lB(N + 1), lG(N + 1), lBG(N + 1);
+    for (int n = 0; n <= N; ++n) { lB[n] = std::log(a.beta + n); lG[n] = std::log(a.gamma + n); lBG[n] = std::log(a.beta + a.gamma + n); }
+    TRY(upload(pl->logB, lB.data(), lB.size()));
+    TRY(upload(pl->logG, lG.data(), lG.size()));
+    TRY(upload(pl->logBG, lBG.data(), lBG.size()));
+    const size_t P1 = P + 1, NK = (size_t)N * K, KP = (size_t)K * P;
+    std::vector<uint8_t> zc((size_t)C * N, 0xFF);
+    std::vector<int> cnt((size_t)C * K * P1, 0);
+    CU(pl->zhist.alloc((size_t)C * ns * N));
+    if (!dp) {
+        std::vector<uint8_t> row0((size_t)N);
+        for (int c = 0; c < C; ++c) {
+            for (int i = 0; i < N; ++i) {
+                int z = init->z[(size_t)c * N + i];
+                if (z < 1 || z > K) return fail(BMM_ERR_INVALID, "initialK must be in 1..K");
+                zc[(size_t)c * N + i] = (uint8_t)(z - 1);
+                row0[i] = (uint8_t)z;
+                int *cc = &cnt[((size_t)c * K + (z - 1)) * P1];
+                cc[P]++;
+                for (int d = 0; d < P; ++d) cc[d] += (bits[(size_t)i * W + (d >> 5)] >> (d & 31)) & 1;
+            }
+            // z_out.row(0) = initialK (collapsed_gibbs.cpp:46)
+            CU(cudaMemcpy(pl->zhist.as<uint8_t>() + (size_t)c * ns * N, row0.data(), N, cudaMemcpyHostToDevice));
+        }
+    } else {
+        std::vector<int> used((size_t)C * (K + 2), 0);
+        std::vector<uint8_t> fr((size_t)C * K, 1);
+        TRY(upload(pl->dp_used, used.data(), used.size()));
+        TRY(upload(pl->dp_free, fr.data(), fr.size()));
+        if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->kactive.alloc((size_t)C * ns * 4));
+    }
+    TRY(upload(pl->z_cur, zc.data(), zc.size()));
+    TRY(upload(pl->cnt, cnt.data(), cnt.size()));
+    std::vector<double> al(C, a.alpha == 0 ? 1.0 : a.alpha);
+    TRY(upload(pl->alpha_cur, al.data(), al.size()));
+    if (pl->relabel) {
+        CU(pl->Q.alloc((size_t)C * NK * 8));
+        CU(pl->logQ.alloc((size_t)C * NK * 8));
+        CU(pl->probs_sample.alloc((size_t)C * NK * 8));
+        CU(pl->cube.alloc((size_t)C * a.burnrelabel * NK * 8));
+        CU(pl->logp.alloc((size_t)C * a.burnrelabel * NK * 8));
+        CU(pl->sb_perm.alloc((size_t)C * a.burnrelabel * K * 4));
+        CU(pl->sb_cost.alloc((size_t)C * a.burnrelabel * K * K * 8));
+        CU(pl->sb_ws.alloc((size_t)C * a.burnrelabel * bmm::assign_ws_bytes(K)));
+        CU(pl->perm_out.alloc((size_t)C * S * K * 4));
+        CU(pl->theta_rel_out.alloc((size_t)C * KP * S * 8));
+    }
+    CU(pl->assign_ws.alloc((size_t)C * bmm::assign_ws_bytes(K)));
+    CU(pl->status.alloc((size_t)C * 4));
+    CU(pl->theta_out.alloc((size_t)C * KP * S * 8));
+    CU(pl->alpha_out.alloc((size_t)C * S * 8));
+    if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)C * ns * NK * 8));
+    if (a.replay) {
+        const bmm_replay *r = a.replay;
+        TRY(upload(pl->ru, r->u, (size_t)C * ns * N * r->u_slots));
+        if (r->alpha) TRY(upload(pl->ralpha, r->alpha, (size_t)C * ns));
+    }
+    bmm::CollapsedParams &q = pl->cp;
+    q.N = N; q.P = P; q.K = K; q.W = W;
+    q.nsamples = ns; q.burnin = a.burnin; q.relabel = pl->relabel; q.burnrelabel = a.burnrelabel; q.dp = dp;
+    q.alpha0 = a.alpha; q.beta = a.beta; q.gamma = a.gamma; q.a = a.a; q.b = a.b;
+    q.seed = a.seed; q.chain_offset = a.chain_offset; q.flags = a.flags;
+    q.xbits = pl->xbits.as<uint32_t>();
+    q.logB = pl->logB.as<double>(); q.logG = pl->logG.as<double>(); q.logBG = pl->logBG.as<double>();
+    q.z_cur = pl->z_cur.as<uint8_t>(); q.cnt = pl->cnt.as<int>(); q.alpha_cur = pl->alpha_cur.as<double>();
+    q.dp_used = pl->dp_used.as<int>(); q.dp_free = pl->dp_free.as<uint8_t>();
+    q.Q = pl->Q.as<double>(); q.logQ = pl->logQ.as<double>(); q.probs_sample = pl->probs_sample.as<double>();
+    q.cube = pl->cube.as<double>(); q.assign_ws = pl->assign_ws.as<char>(); q.status = pl->status.as<int>();
+    q.zhist = pl->zhist.as<uint8_t>(); q.theta_out = pl->theta_out.as<double>(); q.theta_rel_out = pl->theta_rel_out.as<double>();
+    q.alpha_out = pl->alpha_out.as<double>(); q.perm_out = pl->perm_out.as<int>();
+    q.probs_out = pl->probs_out.as<double>(); q.kactive_out = pl->kactive.as<int>();
+    q.ru = pl->ru.as<double>(); q.ru_slots = a.replay ? a.replay->u_slots : 0; q.ralpha = pl->ralpha.as<double>();
+    if (bmm::collapsed_smem_bytes(q) > 200 * 1024)
+        return fail(BMM_ERR_UNSUPPORTED, "N*P too large for the chain-per-warp collapsed kernel");
+    return BMM_OK;
+}
+
+int run_segment(bmm_plan *pl, int j0, int j1) {
+    if (j1 <= j0) return BMM_OK;
+    if (pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING) {
+        pl->fp.j_begin = j0; pl->fp.j_end = j1;
+        CU(bmm::launch_full(pl->fp, pl->C, 128, pl->stream));
+    } else {
+        pl->cp.j_begin = j0; pl->cp.j_end = j1;
+        CU(bmm::launch_collapsed(pl->cp, pl->C, pl->stream));
+    }
+    return BMM_OK;
+}
+
+int first_status(bmm_plan *pl, std::vector<int> &st) {
+    st.assign(pl->C, 0);
+    CU(cudaMemcpy(st.data(), pl->status.p, (size_t)pl->C * 4, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *bmm_last_error(void) { return g_err.c_str(); }
+const char *bmm_version(void) { return "bmm-mcmc_b200 0.1 (sm_100a)"; }
+uint64_t bmm_launch_count(void) { return bmm::g_launches; }
+
+int bmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init, bmm_plan **plan) {
+    if (!plan) return fail(BMM_ERR_INVALID, "plan is NULL");
+    *plan = nullptr;
+    if (sampler < 0 || sampler > 3) return fail(BMM_ERR_INVALID, "unknown sampler");
+    TRY(check_args(sampler, args, init));
+    if (bmm_device_count() <= args->device) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    CU(cudaSetDevice(args->device));
+    bmm_plan *pl = new bmm_plan();
+    pl->sampler = sampler; pl->a = *args;
+    pl->C = args->n_chains < 1 ? 1 : args->n_chains;
+    pl->N = args->N; pl->P = args->P; pl->K = args->K; pl->ns = args->nsamples; pl->S = args->nsamples - args->burnin;
+    pl->relabel = args->relabel != 0; pl->replay = args->replay != nullptr;
+    int rc = BMM_OK;
+    cudaError_t e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->evk0);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->evk1);
+    if (e != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e));
+    if (!rc) rc = (sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING) ? create_full(pl, init) : create_collapsed(pl, init);
+    if (!rc) {
+        // R-layout allocation histories are produced on the device by the finalize kernel
+        const size_t eb = (args->flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+        cudaError_t e2 = pl->z_orig.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
+        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
+        if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
+    }
+    if (!rc) { cudaError_t e3 = cudaDeviceSynchronize(); if (e3 != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e3)); }
+    if (rc) { delete pl; return rc; }
+    *plan = pl;
+    return BMM_OK;
+}
+
+int bmm_plan_run(bmm_plan *pl) {
+    if (!pl) return fail(BMM_ERR_INVALID, "plan is NULL");
+    CU(cudaSetDevice(pl->a.device));
+    const int ns = pl->ns, burnin = pl->a.burnin;
+    CU(cudaEventRecord(pl->ev0, pl->stream));
+    CU(cudaEventRecord(pl->evk0, pl->stream));
+    if (pl->relabel) {
+        TRY(run_segment(pl, 1, burnin));
+        const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
+        CU(bmm::launch_stephens_batch(pl->C, pl->U, pl->K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
+                                      pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(),
+                                      pl->logQ.as<double>(), pl->sb_perm.as<int>(), pl->sb_cost.as<double>(),
+                                      pl->sb_ws.as<char>(), pl->stream));
+        TRY(run_segment(pl, burnin, ns));
+    } else {
+        TRY(run_segment(pl, 1, ns));
+    }
+    CU(cudaEventRecord(pl->evk1, pl->stream));
+    const int eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+    CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
+                              pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
+                              pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
+    CU(cudaEventRecord(pl->ev1, pl->stream));
+    pl->ran = true;
+    return BMM_OK;
+}
+
+int bmm_plan_sync(bmm_plan *pl) {
+    if (!pl) return fail(BMM_ERR_INVALID, "plan is NULL");
+    CU(cudaStreamSynchronize(pl->stream));
+    return BMM_OK;
+}
+
+int bmm_plan_elapsed_ms(bmm_plan *pl, float *total_ms, float *sampler_kernel_ms) {
+    if (!pl || !pl->ran) return fail(BMM_ERR_INVALID, "plan has not run");
+    CU(cudaEventSynchronize(pl->ev1));
+    if (total_ms) CU(cudaEventElapsedTime(total_ms, pl->ev0, pl->ev1));
+    if (sampler_kernel_ms) CU(cudaEventElapsedTime(sampler_kernel_ms, pl->evk0, pl->evk1));
+    return BMM_OK;
+}
+
+int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
+    if (!pl || !out) return fail(BMM_ERR_INVALID, "plan/out is NULL");
+    if (!pl->ran) return fail(BMM_ERR_INVALID, "plan has not run");
+    CU(cudaSetDevice(pl->a.device));
+    CU(cudaStreamSynchronize(pl->stream));
+    const size_t C = pl->C, S = pl->S, N = pl->N, K = pl->K, P = pl->P, ns = pl->ns;
+    const size_t eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+    auto d2h = [&](void *dst, const DevBuf &src, size_t bytes) -> cudaError_t {
+        if (!dst || !src.p || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, pl->stream);
+    };
+    CU(d2h(out->pi, pl->pi_out, C * S * K * 8));
+    CU(d2h(out->alpha, pl->alpha_out, C * S * 8));
+    if (pl->relabel) {
+        CU(d2h(out->permutations, pl->perm_out, C * S * K * 4));
+        CU(d2h(out->z, pl->z_rel, C * S * N * eb));
+        CU(d2h(out->theta, pl->theta_rel_out, C * K * P * S * 8));
+        CU(d2h(out->z_original, pl->z_orig, C * S * N * eb));
+        CU(d2h(out->theta_original, pl->theta_out, C * K * P * S * 8));
+    } else {
+        CU(d2h(out->z, pl->z_orig, C * S * N * eb));
+        CU(d2h(out->theta, pl->theta_out, C * K * P * S * 8));
+    }
+    CU(d2h(out->probs, pl->probs_out, C * ns * N * K * 8));
+    CU(d2h(out->loglik, pl->loglik_out, C * ns * N * K * 8));
+    if (out->Q_final && pl->relabel) {
+        if (pl->U == pl->N && pl->sampler >= BMM_SAMPLER_COLLAPSED) {
+            CU(d2h(out->Q_final, pl->Q, C * N * K * 8));
+        } else {
+            if (!pl->Qexp.p) CU(pl->Qexp.alloc(C * N * K * 8, false));
+            CU(bmm::launch_expand_rows((int)C, (int)N, pl->U, (int)K, pl->rowid.as<int>(), pl->Q.as<double>(),
+                                       pl->Qexp.as<double>(), pl->stream));
+            CU(d2h(out->Q_final, pl->Qexp, C * N * K * 8));
+        }
+    }
+    CU(d2h(out->status, pl->status, C * 4));
+    CU(cudaStreamSynchronize(pl->stream));
+    std::vector<int> st;
+    TRY(first_status(pl, st));
+    for (size_t c = 0; c < C; ++c)
+        if (st[c]) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "chain %zu stopped with status %d%s", c, st[c],
+                     st[c] == BMM_ERR_NO_FREE_CLUSTER ? " (Error: have no free clusters, need to create one.)" : "");
+            return fail(st[c], buf);
+        }
+    return BMM_OK;
+}
+
+int bmm_plan_destroy(bmm_plan *pl) {
+    if (pl) { cudaSetDevice(pl->a.device); delete pl; }
+    return BMM_OK;
+}
+
+static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm_out *out) {
+    if (!out) return fail(BMM_ERR_INVALID, "out is NULL");
+    if (!args) return fail(BMM_ERR_INVALID, "args is NULL");
+    bmm_args a = *args;
+    if (out->probs) a.flags |= BMM_FLAG_PROBE_PROBS;
+    if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
+    bmm_plan *pl = nullptr;
+    int rc = bmm_plan_create(sampler, &a, init, &pl);
+    if (rc) return rc;
+    rc = bmm_plan_run(pl);
+    if (!rc) rc = bmm_plan_fetch(pl, out);
+    bmm_plan_destroy(pl);
+    return rc;
+}
+
+int bmm_gibbs_full(const bmm_args *args, const bmm_init *init, bmm_out *out) { return run_once(BMM_SAMPLER_FULL, args, init, out); }
+int bmm_gibbs_stickbreaking(const bmm_args *args, const bmm_init *init, bmm_out *out) { return run_once(BMM_SAMPLER_STICKBREAKING, args, init, out); }
+int bmm_gibbs_collapsed(const bmm_args *args, const bmm_init *init, bmm_out *out) { return run_once(BMM_SAMPLER_COLLAPSED, args, init, out); }
+int bmm_gibbs_dp(const bmm_args *args, bmm_out *out) { return run_once(BMM_SAMPLER_DP, args, nullptr, out); }
+
+// ---- helpers --------------------------------------------------------------------------------------
+int bmm_stephens_batch(int32_t N, int32_t K, int32_t M, const double *p, double *q, int32_t *perm_MxK) {
+    if (!p || !q || N < 1 || K < 1 || K > 255 || M < 1) return fail(BMM_ERR_INVALID, "bad stephens_batch arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    const size_t NK = (size_t)N * K;
+    DevBuf cube, logp, Q, logQ, perm, cost, ws;
+    TRY(upload(cube, p, NK * M));
+    CU(logp.alloc(NK * M * 8)); CU(Q.alloc(NK * 8)); CU(logQ.alloc(NK * 8));
+    CU(perm.alloc((size_t)M * K * 4)); CU(cost.alloc((size_t)M * K * K * 8)); CU(ws.alloc((size_t)M * bmm::assign_ws_bytes(K)));
+    CU(bmm::launch_stephens_batch(1, N, K, M, nullptr, cube.as<double>(), logp.as<double>(), Q.as<double>(),
+                                  logQ.as<double>(), perm.as<int>(), cost.as<double>(), ws.as<char>(), 0));
+    CU(cudaMemcpy(q, Q.p, NK * 8, cudaMemcpyDeviceToHost));
+    if (perm_MxK) CU(cudaMemcpy(perm_MxK, perm.p, (size_t)M * K * 4, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+int bmm_stephens_online(int32_t N, int32_t K, const double *q, const double *p, int32_t sample_num,
+                        int32_t *perm, double *q_new, double *cost) {
+    if (!p || !q || !perm || !q_new || N < 1 || K < 1 || K > 255) return fail(BMM_ERR_INVALID, "bad stephens_online arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    const size_t NK = (size_t)N * K;
+    DevBuf Q, logQ, pd, cd, pm, ws;
+    TRY(upload(Q, q, NK)); TRY(upload(pd, p, NK));
+    CU(logQ.alloc(NK * 8)); CU(cd.alloc((size_t)K * K * 8)); CU(pm.alloc((size_t)K * 4)); CU(ws.alloc(bmm::assign_ws_bytes(K)));
+    CU(bmm::launch_stephens_online(N, K, Q.as<double>(), logQ.as<double>(), pd.as<double>(), sample_num,
+                                   cd.as<double>(), pm.as<int>(), ws.as<char>(), 0));
+    CU(cudaMemcpy(q_new, Q.p, NK * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(perm, pm.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
+    if (cost) CU(cudaMemcpy(cost, cd.p, (size_t)K * K * 8, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+int bmm_assign(int32_t K, int32_t batch, const double *cost, int32_t *solution) {
+    if (!cost || !solution || K < 1 || K > 255 || batch < 1) return fail(BMM_ERR_INVALID, "bad assign arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    DevBuf cd, sd, ws;
+    TRY(upload(cd, cost, (size_t)batch * K * K));
+    CU(sd.alloc((size_t)batch * K * K * 4)); CU(ws.alloc((size_t)batch * bmm::assign_ws_bytes(K)));
+    CU(bmm::launch_assign(K, batch, cd.as<double>(), sd.as<int>(), ws.as<char>(), 0));
+    CU(cudaMemcpy(solution, sd.p, (size_t)batch * K * K * 4, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out) {
+    if (!alpha_m || !out || K < 1 || K > 4096) return fail(BMM_ERR_INVALID, "bad rdirichlet arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    DevBuf ad, od;
+    TRY(upload(ad, alpha_m, (size_t)K));
+    CU(od.alloc((size_t)K * 8));
+    CU(bmm::launch_rdirichlet(K, ad.as<double>(), seed, od.as<double>(), 0));
+    CU(cudaMemcpy(out, od.p, (size_t)K * 8, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+// One uncollapsed z-sweep's matrices at a given state: a 2-sample replay run whose "recorded"
+// parameters are the caller's (theta, pi).
+int bmm_full_condprob(const int32_t *X, int32_t N, int32_t P, int32_t K, const double *theta, const double *pi,
+                      int32_t precision, uint32_t flags, double *loglik, double *probs) {
+    if (!X || !theta || !pi) return fail(BMM_ERR_INVALID, "bad condprob arguments");
+    const size_t KP = (size_t)K * P, NK = (size_t)N * K;
+    std::vector<double> rth(KP * 2), rpi((size_t)K * 2), ral(2, 1.0), ru((size_t)2 * N * std::max(K - 1, 1), 0.5);
+    for (size_t e = 0; e < KP; ++e) rth[e] = rth[KP + e] = theta[e];
+    for (int k = 0; k < K; ++k) rpi[2 * (size_t)k] = rpi[2 * (size_t)k + 1] = pi[k];  // 2 x K cm
+    bmm_replay rp{ru.data(), std::max(K - 1, 1), rpi.data(), rth.data(), ral.data()};
+    bmm_args a{};
+    a.X = X; a.N = N; a.P = P; a.nsamples = 2; a.K = K; a.alpha = 1.0; a.beta = 0.5; a.gamma = 0.5; a.a = 1; a.b = 1;
+    a.burnin = 0; a.n_chains = 1; a.precision = precision; a.flags = flags; a.replay = &rp;
+    bmm_init in{pi, theta, nullptr};
+    std::vector<double> pb(probs ? NK * 2 : 0), lb(loglik ? NK * 2 : 0);
+    bmm_out o{};
+    o.probs = probs ? pb.data() : nullptr;
+    o.loglik = loglik ? lb.data() : nullptr;
+    int rc = run_once(BMM_SAMPLER_FULL, &a, &in, &o);
+    if (rc) return rc;
+    if (probs) std::copy(pb.begin() + NK, pb.end(), probs);
+    if (loglik) std::copy(lb.begin() + NK, lb.end(), loglik);
+    return BMM_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

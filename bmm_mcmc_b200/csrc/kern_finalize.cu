@@ -1,0 +1,74 @@
+// History layout conversion.  The sampler kernels append allocations as one byte per draw in
+// [chain][sweep][observation] order (sequential, coalesced).  The reference returns z as an
+// S x N IntegerMatrix, column-major, i.e. sweep fastest (full_gibbs.cpp:56,240-245); this kernel
+// transposes 32x32 tiles through shared memory so both the read and the write are coalesced, and
+// applies the per-sweep relabelling z_rel = perm[z-1]+1 (full_gibbs.cpp:171-174) on the way.
+#include "kernels.h"
+
+namespace bmm {
+namespace {
+
+template <typename OutT>
+__global__ void finalize_z_kernel(int N, int nsamples, int burnin, int K, const uint8_t *__restrict__ zhist,
+                                  const int *__restrict__ perm_out, OutT *__restrict__ z_orig, OutT *__restrict__ z_rel) {
+    __shared__ uint8_t tile[32][33];
+    const int c = blockIdx.z, S = nsamples - burnin;
+    const int i0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const uint8_t *src = zhist + ((size_t)c * nsamples + burnin) * N;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int s = s0 + r, i = i0 + threadIdx.x;
+        tile[r][threadIdx.x] = (s < S && i < N) ? src[(size_t)s * N + i] : 0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, s = s0 + threadIdx.x;
+        if (i < N && s < S) {
+            const int z = tile[threadIdx.x][r];
+            const size_t o = (size_t)c * S * N + (size_t)S * i + s;
+            if (z_orig) z_orig[o] = (OutT)z;
+            if (z_rel) z_rel[o] = (OutT)((z >= 1 && z <= K) ? perm_out[(size_t)c * S * K + s + (size_t)S * (z - 1)] + 1 : 0);
+        }
+    }
+}
+
+__global__ void expand_rows_kernel(int N, int U, int K, const int *__restrict__ rowid, const double *__restrict__ src,
+                                   double *__restrict__ dst) {
+    const int c = blockIdx.y;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)N * K; e += (size_t)gridDim.x * blockDim.x)
+        dst[(size_t)c * N * K + e] = src[(size_t)c * U * K + rowid[e % N] + (size_t)U * (e / N)];
+}
+
+}  // namespace
+
+cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
+                              const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st) {
+    const int S = nsamples - burnin;
+    if (S <= 0 || N <= 0) return cudaSuccess;
+    dim3 block(32, 8);
+    for (int c0 = 0; c0 < n_chains; c0 += 65535) {
+        const int nc = n_chains - c0 < 65535 ? n_chains - c0 : 65535;
+        dim3 grid((N + 31) / 32, (S + 31) / 32, nc);
+        const uint8_t *zh = zhist + (size_t)c0 * nsamples * N;
+        const int *pm = perm_out ? perm_out + (size_t)c0 * S * K : nullptr;
+        const size_t off = (size_t)c0 * S * N;
+        if (elem_bytes == 4)
+            finalize_z_kernel<int32_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+                z_orig ? (int32_t *)z_orig + off : nullptr, z_rel ? (int32_t *)z_rel + off : nullptr);
+        else
+            finalize_z_kernel<uint8_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+                z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
+        g_launches++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
+                               cudaStream_t st) {
+    dim3 grid((unsigned)(((size_t)N * K + 255) / 256), n_chains);
+    if (grid.x > 1024) grid.x = 1024;
+    expand_rows_kernel<<<grid, 256, 0, st>>>(N, U, K, rowid, src, dst);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace bmm

@@ -1,0 +1,109 @@
+// Host-visible parameter blocks and launchers of the sampler kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bmm {
+
+// Counter of kernel launches made by this library (bmm_launch_count()).
+extern unsigned long long g_launches;
+
+// ---- uncollapsed samplers, one chain per thread block (kern_full.cu) --------------------------
+// Data rows are de-duplicated on the host: U unique bit-packed rows, multiplicities wt[U],
+// rowid[N] maps each observation to its row.  Every per-row quantity (probabilities, Stephens Q)
+// is shared by all observations with the same x.
+struct FullParams {
+    int N, P, K, U, W;            // W = 32-bit words per row
+    int nsamples, burnin, relabel, burnrelabel, stickbreaking;
+    int j_begin, j_end;           // sweeps [j_begin, j_end)
+    double alpha0, beta, gamma, a, b;
+    unsigned long long seed;
+    int chain_offset;
+    unsigned flags;
+    int use_hist;                 // 1: (row,label) histogram path; 0: direct count atomics
+    // data, shared by all chains
+    const uint32_t *rowbits;      // [U][W]
+    const int *rowid;             // [N]
+    const int *wt;                // [U]
+    // chain state in global memory (persists between launches)
+    double *theta_cur;            // [c][K*P] cm
+    double *pi_cur;               // [c][K]
+    double *alpha_cur;            // [c]
+    double *Q, *logQ;             // [c][U*K]
+    double *cube;                 // [c][burnrelabel][U*K]
+    double *prob_g;               // [c][U*K] (used when the row table does not fit shared memory)
+    int *hist_g;                  // [c][U*K]
+    double *ll_g;                 // [c][U*K] (loglik probe only)
+    char *assign_ws;              // [c][assign_ws_bytes(K)]
+    int *status;                  // [c]
+    // histories
+    uint8_t *zhist;               // [c][nsamples][N], labels 1..K
+    double *theta_out;            // [c][K*P*S]   original labelling
+    double *theta_rel_out;        // [c][K*P*S]   relabelled
+    double *pi_out;               // [c][S*K cm]
+    double *alpha_out;            // [c][S]
+    int *perm_out;                // [c][S*K cm]
+    double *probs_out;            // [c][nsamples][N*K] or nullptr
+    double *loglik_out;           // [c][nsamples][N*K] or nullptr
+    // replay (nullptr = Philox)
+    const double *ru; int ru_slots;
+    const double *rpi, *rtheta, *ralpha;
+};
+size_t full_smem_bytes(const FullParams &p, int threads);
+cudaError_t launch_full(const FullParams &p, int n_chains, int threads, cudaStream_t st);
+
+// ---- collapsed finite-K and DP samplers, one chain per warp-sized block (kern_collapsed.cu) ---
+struct CollapsedParams {
+    int N, P, K, W;               // K = maxK for dp
+    int nsamples, burnin, relabel, burnrelabel, dp;
+    int j_begin, j_end;
+    double alpha0, beta, gamma, a, b;
+    unsigned long long seed;
+    int chain_offset;
+    unsigned flags;
+    const uint32_t *xbits;        // [N][W]
+    // tables shared by all chains: log(beta+n), log(gamma+n), log(beta+gamma+n), n = 0..N
+    const double *logB, *logG, *logBG;
+    // chain state (global, persists between launches)
+    uint8_t *z_cur;               // [c][N] labels 0..K-1 (0xFF = unseated, dp sweep 1)
+    int *cnt;                     // [c][K*(P+1)]: S_kd at k*(P+1)+d, N_k at k*(P+1)+P
+    double *alpha_cur;            // [c]
+    int *dp_used;                 // [c][K+2]: used[0..K), then nused, Kvar
+    uint8_t *dp_free;             // [c][K] multiplicity of each label in the free heap
+    double *Q, *logQ;             // [c][N*K]
+    double *probs_sample;         // [c][N*K]
+    double *cube;                 // [c][burnrelabel][N*K]
+    char *assign_ws;
+    int *status;
+    // histories
+    uint8_t *zhist;               // [c][nsamples][N] labels 1..K
+    double *theta_out, *theta_rel_out;   // [c][K*P*S]
+    double *alpha_out;            // [c][S]
+    int *perm_out;                // [c][S*K cm]
+    double *probs_out;            // [c][nsamples][N*K] or nullptr
+    int *kactive_out;             // [c][nsamples] or nullptr (dp)
+    const double *ru; int ru_slots;
+    const double *ralpha;
+};
+size_t collapsed_smem_bytes(const CollapsedParams &p);
+cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_t st);
+
+// ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
+cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,
+                                  double *Q, double *logQ, int *perm, double *cost, char *assign_ws,
+                                  cudaStream_t st);
+cudaError_t launch_stephens_online(int U, int K, double *Q, double *logQ, const double *p, int sample_num,
+                                   double *cost, int *perm, char *assign_ws, cudaStream_t st);
+cudaError_t launch_assign(int K, int batch, const double *cost, int *solution, char *ws, cudaStream_t st);
+cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long seed, double *out, cudaStream_t st);
+
+// ---- history layout conversion (kern_finalize.cu) --------------------------------------------
+// zhist [c][nsamples][N] uint8 -> R layout [c][S x N cm]; optional relabelling through perm_out.
+// elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).
+cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
+                              const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st);
+// expand a per-row matrix [c][U*K] to per-observation [c][N*K]
+cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
+                               cudaStream_t st);
+
+}  // namespace bmm
