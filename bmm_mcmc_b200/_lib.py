@@ -53,7 +53,7 @@ EXPORTS = [
     "bmm_gibbs_full", "bmm_gibbs_stickbreaking", "bmm_gibbs_collapsed", "bmm_gibbs_dp", "bmm_stephens_batch",
     "bmm_stephens_online", "bmm_assign", "bmm_rdirichlet", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
     "bmm_plan_sync", "bmm_plan_elapsed_ms", "bmm_plan_fetch", "bmm_plan_destroy", "bmm_dist_unique_id",
-    "bmm_dist_init", "bmm_dist_finalize", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_version",
+    "bmm_dist_init", "bmm_dist_finalize", "bmm_plan_kernel_ms", "bmm_host_alloc", "bmm_host_free", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_version",
 ]
 
 _lib = None
@@ -81,6 +81,9 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.bmm_plan_fetch.argtypes = [C.c_void_p, C.POINTER(Out)]
         L.bmm_plan_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.bmm_plan_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.bmm_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        L.bmm_host_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from .rcompat import RRng
 
-__all__ = ["gibbs_full", "gibbs_collapsed", "gibbs_dp", "gibbs_stickbreaking"]
+__all__ = ["gibbs_full", "gibbs_collapsed", "gibbs_dp", "gibbs_stickbreaking", "Plan"]
 
 
 def _r_round(x):
@@ -40,31 +40,61 @@ def _p(arr, typ):
     return arr.ctypes.data_as(C.POINTER(typ)) if arr is not None else None
 
 
-def _chain_cm(C_, shape, dtype):
+class _Pinned:
+    """numpy arrays over cudaHostAlloc'ed memory (freed when the owner array is collected)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.lib().bmm_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().bmm_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def _empty(shape, dtype, pinned):
+    if not pinned:
+        return np.zeros(shape, dtype=dtype)
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    owner = _Pinned(max(n, 1))
+    buf = (C.c_char * max(n, 1)).from_address(owner.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _KEEP[id(buf)] = owner
+    import weakref
+    weakref.finalize(buf, _KEEP.pop, id(buf), None)
+    return arr
+
+
+_KEEP = {}
+
+
+def _chain_cm(C_, shape, dtype, pinned=False):
     """Array of shape (C_, *shape) whose per-chain blocks are column-major (R layout)."""
     rev = tuple(reversed(shape))
-    base = np.zeros((C_,) + rev, dtype=dtype)
+    base = _empty((C_,) + rev, dtype, pinned)
     axes = (0,) + tuple(range(len(shape), 0, -1))
     return base.transpose(axes)
 
 
-def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
-         chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
-         compact_z=False, stable_softmax=False, probes=(), chain_offset=0):
-    L = _lib.lib()
+def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
+                chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
+                compact_z=False, stable_softmax=False, chain_offset=0):
+    """ctypes bmm_args / bmm_init for one call; returns (args, init, keepalive)."""
     N, P = X.shape
-    S = nsamples - burnin
-    Cn = int(chains)
     args = _lib.Args()
     args.X = _p(X, C.c_int32)
     args.N, args.P, args.nsamples, args.K = N, P, int(nsamples), int(K)
     args.alpha, args.beta, args.gamma, args.a, args.b = float(alpha), float(beta), float(gamma), float(a), float(b)
     args.burnin, args.relabel, args.burnrelabel, args.debug = int(burnin), int(bool(relabel)), int(burnrelabel), int(bool(debug))
-    args.n_chains, args.chain_offset, args.seed = Cn, int(chain_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
+    args.n_chains, args.chain_offset, args.seed = int(chains), int(chain_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
     args.precision = {"fp64": _lib.BMM_FP64, "fp32": _lib.BMM_FP32}[precision]
     args.device = int(device)
     args.flags = (_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0)
-    keep = []
+    keep = [X, init_pi, init_theta, init_z]
     if replay is not None:
         rp = _lib.Replay()
         u = np.ascontiguousarray(replay["u"], dtype=np.float64)
@@ -84,46 +114,128 @@ def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, bur
         init.theta = _p(init_theta, C.c_double)
     if init_z is not None:
         init.z = _p(init_z, C.c_int32)
+    return args, init, keep
+
+
+def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned):
+    """Caller-side output buffers in the reference's returned-list layout; returns (dict, bmm_out, status)."""
+    S = nsamples - burnin
     zt = np.uint8 if compact_z else np.int32
     res = {}
     out = _lib.Out()
-    has_pi = sampler in (_lib.SAMPLER_FULL, _lib.SAMPLER_STICKBREAKING)
-    if has_pi:
-        res["pi"] = _chain_cm(Cn, (S, K), np.float64)
+    if sampler in (_lib.SAMPLER_FULL, _lib.SAMPLER_STICKBREAKING):
+        res["pi"] = _chain_cm(Cn, (S, K), np.float64, pinned)
         out.pi = _p(res["pi"], C.c_double)
-    res["alpha"] = _chain_cm(Cn, (S, 1), np.float64)
+    res["alpha"] = _chain_cm(Cn, (S, 1), np.float64, pinned)
     out.alpha = _p(res["alpha"], C.c_double)
-    res["permutations"] = _chain_cm(Cn, (S, K), np.int32)
+    res["permutations"] = _chain_cm(Cn, (S, K), np.int32, pinned)
     out.permutations = _p(res["permutations"], C.c_int32)
-    res["z"] = _chain_cm(Cn, (S, N), zt)
+    res["z"] = _chain_cm(Cn, (S, N), zt, pinned)
     out.z = C.cast(res["z"].ctypes.data, C.POINTER(C.c_int32))
-    res["theta"] = _chain_cm(Cn, (K, P, S), np.float64)
+    res["theta"] = _chain_cm(Cn, (K, P, S), np.float64, pinned)
     out.theta = _p(res["theta"], C.c_double)
     if relabel:
-        res["z_original"] = _chain_cm(Cn, (S, N), zt)
+        res["z_original"] = _chain_cm(Cn, (S, N), zt, pinned)
         out.z_original = C.cast(res["z_original"].ctypes.data, C.POINTER(C.c_int32))
-        res["theta_original"] = _chain_cm(Cn, (K, P, S), np.float64)
+        res["theta_original"] = _chain_cm(Cn, (K, P, S), np.float64, pinned)
         out.theta_original = _p(res["theta_original"], C.c_double)
-    extra = {}
     if "probs" in probes:
-        extra["probs"] = np.zeros((Cn, nsamples, K, N)).transpose(0, 1, 3, 2)  # [c][j] blocks of N x K cm
-        out.probs = C.cast(extra["probs"].ctypes.data, C.POINTER(C.c_double))
+        res["probs"] = np.zeros((Cn, nsamples, K, N)).transpose(0, 1, 3, 2)  # [c][j] blocks of N x K cm
+        out.probs = C.cast(res["probs"].ctypes.data, C.POINTER(C.c_double))
     if "loglik" in probes:
-        extra["loglik"] = np.zeros((Cn, nsamples, K, N)).transpose(0, 1, 3, 2)
-        out.loglik = C.cast(extra["loglik"].ctypes.data, C.POINTER(C.c_double))
+        res["loglik"] = np.zeros((Cn, nsamples, K, N)).transpose(0, 1, 3, 2)
+        out.loglik = C.cast(res["loglik"].ctypes.data, C.POINTER(C.c_double))
     if "Q_final" in probes and relabel:
-        extra["Q_final"] = _chain_cm(Cn, (N, K), np.float64)
-        out.Q_final = _p(extra["Q_final"], C.c_double)
+        res["Q_final"] = _chain_cm(Cn, (N, K), np.float64)
+        out.Q_final = _p(res["Q_final"], C.c_double)
     status = np.zeros(Cn, dtype=np.int32)
     out.status = _p(status, C.c_int32)
-    fn = {_lib.SAMPLER_FULL: L.bmm_gibbs_full, _lib.SAMPLER_STICKBREAKING: L.bmm_gibbs_stickbreaking,
-          _lib.SAMPLER_COLLAPSED: L.bmm_gibbs_collapsed}.get(sampler)
+    return res, out, status
+
+
+def out_nbytes(res):
+    return int(sum(v.nbytes for v in res.values()))
+
+
+class Plan:
+    """Device-resident run (bmm_plan_*): upload once, `run()` any number of times, `fetch()` the lists.
+
+    The one-shot `gibbs_*` functions are create + run + fetch + destroy of exactly this."""
+
+    def __init__(self, sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
+                 chains=1, seed=0, device=0, precision="fp64", init_pi=None, init_theta=None, init_z=None,
+                 compact_z=False, chain_offset=0, probes=()):
+        self.L = _lib.lib()
+        self.X = _as_X(X)
+        self.meta = dict(sampler=sampler, Cn=int(chains), N=self.X.shape[0], P=self.X.shape[1], K=int(K),
+                         nsamples=int(nsamples), burnin=int(burnin), relabel=bool(relabel), compact_z=compact_z,
+                         probes=probes)
+        args, init, self._keep = _build_args(sampler, self.X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel,
+                                             burnrelabel, False, chains, seed, device, precision, init_pi, init_theta,
+                                             init_z, None, compact_z, False, chain_offset)
+        if "probs" in probes:
+            args.flags |= 0x100
+        if "loglik" in probes:
+            args.flags |= 0x200
+        self.h = C.c_void_p()
+        _lib.check(self.L.bmm_plan_create(sampler, C.byref(args), C.byref(init), C.byref(self.h)))
+
+    def run(self):
+        _lib.check(self.L.bmm_plan_run(self.h))
+
+    def sync(self):
+        _lib.check(self.L.bmm_plan_sync(self.h))
+
+    def elapsed_ms(self):
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self.L.bmm_plan_elapsed_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def kernel_ms(self):
+        ms = (C.c_float * 4)()
+        _lib.check(self.L.bmm_plan_kernel_ms(self.h, ms))
+        return list(ms)
+
+    def alloc_out(self, pinned=False):
+        m = self.meta
+        return _alloc_out(m["sampler"], m["Cn"], m["N"], m["P"], m["K"], m["nsamples"], m["burnin"], m["relabel"],
+                          m["compact_z"], m["probes"], pinned)
+
+    def fetch(self, bufs=None, pinned=False):
+        res, out, status = bufs if bufs is not None else self.alloc_out(pinned)
+        _lib.check(self.L.bmm_plan_fetch(self.h, C.byref(out)))
+        return res
+
+    def close(self):
+        if self.h:
+            self.L.bmm_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
+         chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
+         compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
+    L = _lib.lib()
+    N, P = X.shape
+    Cn = int(chains)
+    args, init, keep = _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
+                                   debug, chains, seed, device, precision, init_pi, init_theta, init_z, replay,
+                                   compact_z, stable_softmax, chain_offset)
+    res, out, status = out_bufs if out_bufs is not None else _alloc_out(
+        sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned)
     if sampler == _lib.SAMPLER_DP:
         rc = L.bmm_gibbs_dp(C.byref(args), C.byref(out))
     else:
+        fn = {_lib.SAMPLER_FULL: L.bmm_gibbs_full, _lib.SAMPLER_STICKBREAKING: L.bmm_gibbs_stickbreaking,
+              _lib.SAMPLER_COLLAPSED: L.bmm_gibbs_collapsed}[sampler]
         rc = fn(C.byref(args), C.byref(init), C.byref(out))
     _lib.check(rc)
-    res.update(extra)
     if Cn == 1 and chains == 1:
         res = {k: v[0] for k, v in res.items()}
     return res
@@ -142,7 +254,7 @@ def _defaults(nsamples, burnin, burnrelabel, alpha, clamp=True):
 def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None, relabel=False,
                burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                initial_pi=None, initial_theta=None, replay=None, compact_z=False, stable_softmax=False,
-               probes=(), chain_offset=0, _sampler=None):
+               probes=(), chain_offset=0, pinned=False, out_bufs=None, _sampler=None):
     """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32)."""
     X = _as_X(data)
     N, P = X.shape
@@ -162,7 +274,8 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
     sampler = _lib.SAMPLER_FULL if _sampler is None else _sampler
     return _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug, chains, seed,
                 device, precision, init_pi=np.ascontiguousarray(initial_pi), init_theta=np.ascontiguousarray(initial_theta),
-                replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset)
+                replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset,
+                pinned=pinned, out_bufs=out_bufs)
 
 
 def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None,
@@ -176,7 +289,7 @@ def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a
 
 def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None, relabel=False,
                     burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
-                    initial_K=None, replay=None, compact_z=False, probes=(), chain_offset=0):
+                    initial_K=None, replay=None, compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
     """Collapsed Gibbs sampler for a finite mixture (R/utils.R:37-47 -> collapsed_gibbs.cpp:24)."""
     X = _as_X(data)
     N, P = X.shape
@@ -187,15 +300,15 @@ def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1
     initial_K = np.ascontiguousarray(np.asarray(initial_K, dtype=np.int32).reshape(chains, N))
     return _run(_lib.SAMPLER_COLLAPSED, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_z=initial_K, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs)
 
 
 def gibbs_dp(data, nsamples, alpha=None, a=1, b=1, beta=0.5, gamma=0.5, burnin=None, relabel=False,
              burnrelabel=50, maxK=30, debug=False, *, chains=1, seed=0, device=0, precision="fp64", replay=None,
-             compact_z=False, probes=(), chain_offset=0):
+             compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
     """Collapsed Gibbs sampler for the DP (CRP) infinite mixture (R/utils.R:23-30 -> collapsed_gibbs_dp.cpp:27)."""
     X = _as_X(data)
     burnin, burnrelabel, alpha = _defaults(nsamples, burnin, burnrelabel, alpha)
     return _run(_lib.SAMPLER_DP, X, nsamples, maxK, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs)

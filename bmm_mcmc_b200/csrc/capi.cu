@@ -67,6 +67,7 @@ struct bmm_plan {
     bool relabel = false, replay = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bmm::FullParams fp{};
     bmm::CollapsedParams cp{};
     // data
@@ -85,6 +86,7 @@ struct bmm_plan {
         if (ev1) cudaEventDestroy(ev1);
         if (evk0) cudaEventDestroy(evk0);
         if (evk1) cudaEventDestroy(evk1);
+        for (auto &e : evs) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -375,6 +377,7 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
     if (e == cudaSuccess) e = cudaEventCreate(&pl->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->evk0);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->evk1);
+    for (auto &ev : pl->evs) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e));
     if (!rc) rc = (sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING) ? create_full(pl, init) : create_collapsed(pl, init);
     if (!rc) {
@@ -396,22 +399,29 @@ int bmm_plan_run(bmm_plan *pl) {
     const int ns = pl->ns, burnin = pl->a.burnin;
     CU(cudaEventRecord(pl->ev0, pl->stream));
     CU(cudaEventRecord(pl->evk0, pl->stream));
+    CU(cudaEventRecord(pl->evs[0], pl->stream));
     if (pl->relabel) {
         TRY(run_segment(pl, 1, burnin));
+        CU(cudaEventRecord(pl->evs[1], pl->stream));
         const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
         CU(bmm::launch_stephens_batch(pl->C, pl->U, pl->K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
                                       pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(),
                                       pl->logQ.as<double>(), pl->sb_perm.as<int>(), pl->sb_cost.as<double>(),
                                       pl->sb_ws.as<char>(), pl->stream));
+        CU(cudaEventRecord(pl->evs[2], pl->stream));
         TRY(run_segment(pl, burnin, ns));
     } else {
+        CU(cudaEventRecord(pl->evs[1], pl->stream));
+        CU(cudaEventRecord(pl->evs[2], pl->stream));
         TRY(run_segment(pl, 1, ns));
     }
+    CU(cudaEventRecord(pl->evs[3], pl->stream));
     CU(cudaEventRecord(pl->evk1, pl->stream));
     const int eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
     CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
                               pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
                               pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
+    CU(cudaEventRecord(pl->evs[4], pl->stream));
     CU(cudaEventRecord(pl->ev1, pl->stream));
     pl->ran = true;
     return BMM_OK;
@@ -428,6 +438,26 @@ int bmm_plan_elapsed_ms(bmm_plan *pl, float *total_ms, float *sampler_kernel_ms)
     CU(cudaEventSynchronize(pl->ev1));
     if (total_ms) CU(cudaEventElapsedTime(total_ms, pl->ev0, pl->ev1));
     if (sampler_kernel_ms) CU(cudaEventElapsedTime(sampler_kernel_ms, pl->evk0, pl->evk1));
+    return BMM_OK;
+}
+
+int bmm_plan_kernel_ms(bmm_plan *pl, float ms_out[4]) {
+    if (!pl || !pl->ran || !ms_out) return fail(BMM_ERR_INVALID, "plan has not run");
+    CU(cudaEventSynchronize(pl->evs[4]));
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms_out[i], pl->evs[i], pl->evs[i + 1]));
+    return BMM_OK;
+}
+
+int bmm_host_alloc(uint64_t bytes, void **ptr_out) {
+    if (!ptr_out) return fail(BMM_ERR_INVALID, "ptr_out is NULL");
+    *ptr_out = nullptr;
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device");
+    CU(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return BMM_OK;
+}
+
+int bmm_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
     return BMM_OK;
 }
 

@@ -145,6 +145,10 @@ int bmm_plan_run(bmm_plan *plan);
 int bmm_plan_sync(bmm_plan *plan);
 /* Device time of the last bmm_plan_run in ms (CUDA events on the launching stream). */
 int bmm_plan_elapsed_ms(bmm_plan *plan, float *total_ms, float *sampler_kernel_ms);
+/* Device time of each launch group of the last run, in ms: [0] sampler sweeps 1..burnin-1,
+ * [1] Stephens batch, [2] sampler sweeps burnin..nsamples-1 (all sweeps when !relabel),
+ * [3] history layout conversion.  CUDA events on the launching stream. */
+int bmm_plan_kernel_ms(bmm_plan *plan, float ms_out[4]);
 /* Copy the results into caller (host) buffers. */
 int bmm_plan_fetch(bmm_plan *plan, bmm_out *out);
 int bmm_plan_destroy(bmm_plan *plan);
@@ -155,6 +159,9 @@ int bmm_dist_init(int32_t rank, int32_t world, const uint8_t id[128], int32_t de
 int bmm_dist_finalize(void);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
+/* Page-locked host memory for output buffers (cudaHostAlloc): D2H into it runs at PCIe speed.    */
+int bmm_host_alloc(uint64_t bytes, void **ptr_out);
+int bmm_host_free(void *ptr);
 const char *bmm_last_error(void);
 int bmm_device_count(void);
 uint64_t bmm_launch_count(void);   /* kernels launched by this library so far */
