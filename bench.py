@@ -27,10 +27,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DATASET, K = "K3_N1000_P5", 3
-CHAINS_PER_GPU = 1024
-NSAMPLES, BURNIN, BURNRELABEL = 1000, 100, 50
 METRIC = "allocation updates/sec (N*chains*sweeps/s)"
+
+# Chain-parallel workloads (independent chains, split across GPUs with no collective).
+# "c2" is BASELINE.json configs[1] and the default; the others are the remaining chain configs.
+WORKLOADS = {
+    "c2": dict(sampler="full", dataset="K3_N1000_P5", K=3, chains=1024, nsamples=1000, burnin=100, burnrelabel=50,
+               relabel=True, label="C2: gibbs_full K3_N1000_P5 (N=1000,P=5) K=3"),
+    "collapsed": dict(sampler="collapsed", dataset="K3_N1000_P5", K=3, chains=1024, nsamples=300, burnin=30,
+                      burnrelabel=10, relabel=False, label="gibbs_collapsed K3_N1000_P5 (N=1000,P=5) K=3 (north_star 100x target)"),
+    "c1": dict(sampler="collapsed", dataset="K2_N100_P5", K=2, chains=1, nsamples=10000, burnin=1000,
+               burnrelabel=50, relabel=False, label="C1: gibbs_collapsed K2_N100_P5 (N=100,P=5) K=2, 1 chain, 10k iters"),
+    "c3": dict(sampler="dp", dataset="K2_N1000_P5", K=64, chains=4096, nsamples=300, burnin=30, burnrelabel=10,
+               relabel=False, label="C3: gibbs_dp K2_N1000_P5 (N=1000,P=5) maxK=64"),
+}
+WL = WORKLOADS["c2"]
+DATASET, K = WL["dataset"], WL["K"]
+CHAINS_PER_GPU = WL["chains"]
+NSAMPLES, BURNIN, BURNRELABEL = WL["nsamples"], WL["burnin"], WL["burnrelabel"]
+
+
+def select_workload(name):
+    global WL, DATASET, K, CHAINS_PER_GPU, NSAMPLES, BURNIN, BURNRELABEL
+    WL = WORKLOADS[name]
+    DATASET, K = WL["dataset"], WL["K"]
+    CHAINS_PER_GPU = WL["chains"]
+    NSAMPLES, BURNIN, BURNRELABEL = WL["nsamples"], WL["burnin"], WL["burnrelabel"]
 
 
 def peaks():
@@ -104,17 +126,35 @@ def cpu_chain(args):
     seed, nsamples, burnin, br = args
     from oracle import pyoracle as O
     import bmm_mcmc_b200 as B
+    from bmm_mcmc_b200.rcompat import RRng
     X = B.load_dataset(DATASET)
-    ip, th = init_states(1, X.shape[1], 1000 + seed)
-    t0 = time.perf_counter()
-    O.gibbs_full(X, ip[0], th[0].T, nsamples, K, burnin=burnin, relabel=True, burnrelabel=br, seed=seed,
-                 use_ref=O.has_ref(), probes=False)
-    return X.shape[0] * (nsamples - 1), time.perf_counter() - t0
+    N, P = X.shape
+    kw = dict(burnin=burnin, relabel=WL["relabel"], burnrelabel=br, seed=seed, use_ref=O.has_ref(), probes=False)
+    if WL["sampler"] == "full":
+        ip, th = init_states(1, P, 1000 + seed)
+        t0 = time.perf_counter()
+        O.gibbs_full(X, ip[0], th[0].T, nsamples, K, **kw)
+    elif WL["sampler"] == "collapsed":
+        iz = RRng(1000 + seed).sample_int(K, N)
+        t0 = time.perf_counter()
+        O.gibbs_collapsed(X, iz, nsamples, K, **kw)
+    else:
+        t0 = time.perf_counter()
+        O.gibbs_dp(X, nsamples, maxK=K, **kw)
+    return N * (nsamples - 1), time.perf_counter() - t0
+
+
+def cpu_sample_shape():
+    """Sweeps of one CPU sample chain: the workload's own, capped so one chain stays within seconds
+    (the collapsed reference is O(N^2 P) per sweep; per-update cost does not depend on the sweep count)."""
+    ns = NSAMPLES if WL["sampler"] == "full" else min(NSAMPLES, 120)
+    burnin = min(BURNIN, max(2, ns // 10))
+    return ns, burnin, min(BURNRELABEL, burnin)
 
 
 def cpu_baseline_single(budget_s=12.0):
     """Oracle on one host core, bounded sample of the same workload."""
-    ns, burnin, br = NSAMPLES, BURNIN, BURNRELABEL
+    ns, burnin, br = cpu_sample_shape()
     upd, sec, chains = 0, 0.0, 0
     while sec < budget_s and chains < 16:
         u, s = cpu_chain((chains, ns, burnin, br))
@@ -122,8 +162,8 @@ def cpu_baseline_single(budget_s=12.0):
     from oracle import pyoracle as O
     return {"value": upd / sec, "unit": "allocation updates/s", "cores": 1,
             "kind": "port", "assignment": "reference lp_solve" if O.has_ref() else "Hungarian port",
-            "sample": "%d chain(s) x %d sweeps of gibbs_full(%s, K=%d, relabel, burnrelabel=%d), %.1f s"
-                      % (chains, ns - 1, DATASET, K, br, sec)}
+            "sample": "%d chain(s) x %d sweeps of %s, relabel=%s burnrelabel=%d, %.1f s"
+                      % (chains, ns - 1, WL["label"], WL["relabel"], br, sec)}
 
 
 def run_reference(a):
@@ -133,7 +173,8 @@ def run_reference(a):
         return 0
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    ns, burnin, br = NSAMPLES, BURNIN, BURNRELABEL
+    select_workload(a.workload)
+    ns, burnin, br = cpu_sample_shape()
     from oracle import pyoracle as O
     O.lib()
     ctx = mp.get_context("fork")
@@ -150,9 +191,9 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "allocation updates/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / max(a.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "bundled K3_N1000_P5 (regenerated from set.seed(17))",
-        "config": {"workload": "C2: gibbs_full K3_N1000_P5 K=3, relabel=TRUE burnrelabel=50; CPU sample: %d chains x %d sweeps per step"
-                               % (cores, ns - 1)},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "bundled %s (regenerated from set.seed(17))" % DATASET,
+        "config": {"workload": "%s, relabel=%s burnrelabel=%d; CPU sample: %d chains x %d sweeps per step"
+                               % (WL["label"], WL["relabel"], br, cores, ns - 1)},
         "cpu_baseline": {"value": val, "unit": "allocation updates/s", "cores": cores,
                          "kind": "port", "assignment": "reference lp_solve" if O.has_ref() else "Hungarian port",
                          "sample": "one chain per core, %d cores x %d sweeps per step (reference is single-threaded; "
@@ -170,13 +211,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
-    ap.add_argument("--nsamples", type=int, default=NSAMPLES)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=None)
+    ap.add_argument("--nsamples", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
     a.warmup = max(a.warmup, 3)
+    select_workload(a.workload)
+    a.chains = a.chains or CHAINS_PER_GPU
+    a.nsamples = a.nsamples or NSAMPLES
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,18 +242,30 @@ def main():
     C_, ns = a.chains, a.nsamples
     burnin = BURNIN if ns > 2 * BURNIN else max(2, ns // 10)
     br = min(BURNRELABEL, burnin)
+    relabel = WL["relabel"]
     S = ns - burnin
-    ip, th = init_states(C_, P, 1 + rank)
-    kw = dict(alpha=0.0, beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=True, burnrelabel=br)
+    smp = WL["sampler"]
+    sid = {"full": _lib.SAMPLER_FULL, "collapsed": _lib.SAMPLER_COLLAPSED, "dp": _lib.SAMPLER_DP}[smp]
+    kw = dict(alpha=0.0, beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=relabel, burnrelabel=br)
     updates_per_step = N * C_ * (ns - 1)
+    init_kw, h2d = {}, X.nbytes
+    if smp == "full":
+        ip, th = init_states(C_, P, 1 + rank)
+        init_kw = dict(init_pi=ip, init_theta=th)
+        h2d += ip.nbytes + th.nbytes
+    elif smp == "collapsed":
+        from bmm_mcmc_b200.rcompat import RRng
+        iz = np.ascontiguousarray(np.random.default_rng(1 + rank).integers(1, K + 1, (C_, N)), dtype=np.int32)
+        iz[0] = RRng(1 + rank).sample_int(K, N)   # chain 0 exactly as R/utils.R:42 draws it
+        init_kw = dict(init_z=iz)
+        h2d += iz.nbytes
 
     def barrier():
         if dist:
             dist.barrier()
 
     # ---- device-resident arm (value) --------------------------------------------------------
-    plan = api.Plan(_lib.SAMPLER_FULL, X, ns, K, chains=C_, seed=2026, device=local, init_pi=ip, init_theta=th,
-                    chain_offset=rank * C_, **kw)
+    plan = api.Plan(sid, X, ns, K, chains=C_, seed=2026, device=local, chain_offset=rank * C_, **init_kw, **kw)
     for _ in range(a.warmup):
         plan.run(); plan.sync()
     clocks = ClockSampler(local)
@@ -228,14 +285,17 @@ def main():
     plan.close()
 
     # ---- end-to-end arm (e2e): the public call with host buffers, every step ------------------
-    bufs = api._alloc_out(_lib.SAMPLER_FULL, C_, N, P, K, ns, burnin, True, False, (), True)  # pinned
+    bufs = api._alloc_out(sid, C_, N, P, K, ns, burnin, relabel, False, (), True)  # pinned
     d2h = api.out_nbytes(bufs[0])
-    h2d = X.nbytes + ip.nbytes + th.nbytes
+    common = dict(chains=C_, seed=2026, device=local, chain_offset=rank * C_, out_bufs=bufs, alpha=None,
+                  burnin=burnin, relabel=relabel, burnrelabel=br)
 
     def e2e_step():
-        return B.gibbs_full(X, ns, K, chains=C_, seed=2026, device=local, initial_pi=ip,
-                            initial_theta=th.transpose(0, 2, 1), chain_offset=rank * C_, out_bufs=bufs,
-                            alpha=None, burnin=burnin, relabel=True, burnrelabel=br)
+        if smp == "full":
+            return B.gibbs_full(X, ns, K, initial_pi=ip, initial_theta=th.transpose(0, 2, 1), **common)
+        if smp == "collapsed":
+            return B.gibbs_collapsed(X, ns, K, initial_K=iz, **common)
+        return B.gibbs_dp(X, ns, maxK=K, **common)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -262,28 +322,30 @@ def main():
     # dominant kernel: full_chain_kernel over sweeps burnin..nsamples-1 (kern[2]).  Algorithmic HBM
     # bytes per allocation update: 1 B appended to the allocation history; per sweep and chain
     # theta, theta_rel (K*P*8 each), pi (K*8), alpha (8), permutations (K*4).
-    sweeps2 = ns - burnin
-    bytes_launch = C_ * sweeps2 * (N * 1 + 2 * K * P * 8 + K * 8 + 8 + K * 4)
+    sweeps2 = (ns - burnin) if relabel else (ns - 1)
+    per_sweep_hist = (2 if relabel else 1) * K * P * 8 + K * 8 + 8 + (K * 4 if relabel else 0)
+    bytes_launch = C_ * (sweeps2 * N * 1 + S * per_sweep_hist)
     dur_s = kern[2] / a.steps / 1e3
+    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_kernel", "dp": "dp_kernel"}[smp]
     achieved = bytes_launch / dur_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
-                "kernel": "full_chain_kernel (sweeps %d..%d, %d chains)" % (burnin, ns - 1, C_),
+                "kernel": "%s (sweeps %d..%d, %d chains)" % (kname, burnin if relabel else 1, ns - 1, C_),
                 "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[2] / max(kern.sum(), 1e-9)),
                 "note": "C1-C3 are on-chip (issue/latency) bound by construction: chain state lives in shared "
                         "memory and only the 1 B/update history reaches HBM (SURVEY 8d); see extra.kernels_ms"}
     line = {
         "metric": METRIC, "value": value, "unit": "allocation updates/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tm[0] / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "bundled K3_N1000_P5 regenerated from set.seed(17) (bit-identical to data/K3_N1000_P5.RData)",
-        "config": {"workload": "C2: gibbs_full K3_N1000_P5 (N=1000,P=5) K=3, %d chains/GPU, nsamples=%d burnin=%d, "
-                               "relabel=TRUE burnrelabel=%d" % (C_, ns, burnin, br),
+        "vs_baseline": None, "dtype": "f64", "data": "bundled %s regenerated from set.seed(17) (bit-identical to data/%s.RData)" % (DATASET, DATASET),
+        "config": {"workload": "%s, %d chains/GPU, nsamples=%d burnin=%d, relabel=%s burnrelabel=%d"
+                               % (WL["label"], C_, ns, burnin, relabel, br),
                    "chains_per_gpu": C_, "nsamples": ns, "parallelism": "chains split across GPUs, no collective",
                    "l2": "per-step histories (%.1f GB written) exceed the 126 MB L2; no explicit flush" % (d2h / 1e9 + C_ * ns * N / 1e9)},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "allocation updates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tm[2] / a.steps,
-                "api": "bmm_mcmc_b200.gibbs_full -> bmm_gibbs_full (C ABI), pinned host output buffers"},
+                "api": "bmm_mcmc_b200.gibbs_%s -> bmm_gibbs_%s (C ABI), pinned host output buffers" % (smp, smp)},
         "gpu_launches": launches,
         "roofline": roofline,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbmm_b200.so")
 
 BMM_FP64, BMM_FP32 = 0, 1
-FLAG_STABLE_SOFTMAX, FLAG_COMPACT_Z = 1, 2
+FLAG_STABLE_SOFTMAX, FLAG_COMPACT_Z, FLAG_NO_Z_HISTORY, FLAG_GRID_PATH = 1, 2, 4, 8
 SAMPLER_FULL, SAMPLER_STICKBREAKING, SAMPLER_COLLAPSED, SAMPLER_DP = 0, 1, 2, 3
 
 ERRORS = {
@@ -34,6 +34,7 @@ class Args(C.Structure):
         ("burnin", C.c_int32), ("relabel", C.c_int32), ("burnrelabel", C.c_int32), ("debug", C.c_int32),
         ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("seed", C.c_uint64), ("precision", C.c_int32),
         ("device", C.c_int32), ("flags", C.c_uint32), ("replay", C.POINTER(Replay)),
+        ("n_global", C.c_int64), ("row_offset", C.c_int64),
     ]
 
 

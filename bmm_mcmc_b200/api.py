@@ -82,7 +82,8 @@ def _chain_cm(C_, shape, dtype, pinned=False):
 
 def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
-                compact_z=False, stable_softmax=False, chain_offset=0):
+                compact_z=False, stable_softmax=False, chain_offset=0, grid_path=False, no_z_history=False,
+                n_global=0, row_offset=0):
     """ctypes bmm_args / bmm_init for one call; returns (args, init, keepalive)."""
     N, P = X.shape
     args = _lib.Args()
@@ -93,7 +94,9 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     args.n_chains, args.chain_offset, args.seed = int(chains), int(chain_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
     args.precision = {"fp64": _lib.BMM_FP64, "fp32": _lib.BMM_FP32}[precision]
     args.device = int(device)
-    args.flags = (_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0)
+    args.flags = ((_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0) |
+                  (_lib.FLAG_GRID_PATH if grid_path else 0) | (_lib.FLAG_NO_Z_HISTORY if no_z_history else 0))
+    args.n_global, args.row_offset = int(n_global), int(row_offset)
     keep = [X, init_pi, init_theta, init_z]
     if replay is not None:
         rp = _lib.Replay()
@@ -117,7 +120,7 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     return args, init, keep
 
 
-def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned):
+def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=False):
     """Caller-side output buffers in the reference's returned-list layout; returns (dict, bmm_out, status)."""
     S = nsamples - burnin
     zt = np.uint8 if compact_z else np.int32
@@ -130,8 +133,9 @@ def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probe
     out.alpha = _p(res["alpha"], C.c_double)
     res["permutations"] = _chain_cm(Cn, (S, K), np.int32, pinned)
     out.permutations = _p(res["permutations"], C.c_int32)
-    res["z"] = _chain_cm(Cn, (S, N), zt, pinned)
-    out.z = C.cast(res["z"].ctypes.data, C.POINTER(C.c_int32))
+    if not no_z:
+        res["z"] = _chain_cm(Cn, (S, N), zt, pinned)
+        out.z = C.cast(res["z"].ctypes.data, C.POINTER(C.c_int32))
     res["theta"] = _chain_cm(Cn, (K, P, S), np.float64, pinned)
     out.theta = _p(res["theta"], C.c_double)
     if relabel:
@@ -164,15 +168,17 @@ class Plan:
 
     def __init__(self, sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                  chains=1, seed=0, device=0, precision="fp64", init_pi=None, init_theta=None, init_z=None,
-                 compact_z=False, chain_offset=0, probes=()):
+                 compact_z=False, chain_offset=0, probes=(), stable_softmax=False, grid_path=False,
+                 no_z_history=False, n_global=0, row_offset=0):
         self.L = _lib.lib()
         self.X = _as_X(X)
         self.meta = dict(sampler=sampler, Cn=int(chains), N=self.X.shape[0], P=self.X.shape[1], K=int(K),
                          nsamples=int(nsamples), burnin=int(burnin), relabel=bool(relabel), compact_z=compact_z,
-                         probes=probes)
+                         probes=probes, no_z=bool(no_z_history))
         args, init, self._keep = _build_args(sampler, self.X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel,
                                              burnrelabel, False, chains, seed, device, precision, init_pi, init_theta,
-                                             init_z, None, compact_z, False, chain_offset)
+                                             init_z, None, compact_z, stable_softmax, chain_offset, grid_path,
+                                             no_z_history, n_global, row_offset)
         if "probs" in probes:
             args.flags |= 0x100
         if "loglik" in probes:
@@ -199,7 +205,7 @@ class Plan:
     def alloc_out(self, pinned=False):
         m = self.meta
         return _alloc_out(m["sampler"], m["Cn"], m["N"], m["P"], m["K"], m["nsamples"], m["burnin"], m["relabel"],
-                          m["compact_z"], m["probes"], pinned)
+                          m["compact_z"], m["probes"], pinned, no_z=m["no_z"])
 
     def fetch(self, bufs=None, pinned=False):
         res, out, status = bufs if bufs is not None else self.alloc_out(pinned)
@@ -220,15 +226,17 @@ class Plan:
 
 def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
          chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
-         compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
+         compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
+         grid_path=False, no_z_history=False, n_global=0, row_offset=0):
     L = _lib.lib()
     N, P = X.shape
     Cn = int(chains)
     args, init, keep = _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                                    debug, chains, seed, device, precision, init_pi, init_theta, init_z, replay,
-                                   compact_z, stable_softmax, chain_offset)
+                                   compact_z, stable_softmax, chain_offset, grid_path, no_z_history, n_global,
+                                   row_offset)
     res, out, status = out_bufs if out_bufs is not None else _alloc_out(
-        sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned)
+        sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=no_z_history)
     if sampler == _lib.SAMPLER_DP:
         rc = L.bmm_gibbs_dp(C.byref(args), C.byref(out))
     else:
@@ -254,7 +262,8 @@ def _defaults(nsamples, burnin, burnrelabel, alpha, clamp=True):
 def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None, relabel=False,
                burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                initial_pi=None, initial_theta=None, replay=None, compact_z=False, stable_softmax=False,
-               probes=(), chain_offset=0, pinned=False, out_bufs=None, _sampler=None):
+               probes=(), chain_offset=0, pinned=False, out_bufs=None, grid_path=False, no_z_history=False,
+               n_global=0, row_offset=0, _sampler=None):
     """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32)."""
     X = _as_X(data)
     N, P = X.shape
@@ -275,7 +284,8 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
     return _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug, chains, seed,
                 device, precision, init_pi=np.ascontiguousarray(initial_pi), init_theta=np.ascontiguousarray(initial_theta),
                 replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset,
-                pinned=pinned, out_bufs=out_bufs)
+                pinned=pinned, out_bufs=out_bufs, grid_path=grid_path, no_z_history=no_z_history, n_global=n_global,
+                row_offset=row_offset)
 
 
 def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None,

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -12,6 +13,7 @@
 #include "../../include/bmm_capi.h"
 #include "assign.cuh"
 #include "kernels.h"
+#include "dist.h"
 
 #define BMM_FLAG_PROBE_PROBS 0x100u
 #define BMM_FLAG_PROBE_LOGLIK 0x200u
@@ -70,6 +72,11 @@ struct bmm_plan {
     cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bmm::FullParams fp{};
     bmm::CollapsedParams cp{};
+    bmm::BigParams bp{};
+    bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
+    int sm_count = 148;
+    std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
+    DevBuf w1, w0, lpi, gsc, counts;
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG;
     // state
@@ -87,6 +94,7 @@ struct bmm_plan {
         if (evk0) cudaEventDestroy(evk0);
         if (evk1) cudaEventDestroy(evk1);
         for (auto &e : evs) if (e) cudaEventDestroy(e);
+        for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -240,6 +248,89 @@ int create_full(bmm_plan *pl, const bmm_init *init) {
     return BMM_OK;
 }
 
+// One chain over the whole GPU (and N-sharded over the ranks of bmm_dist_init): kern_big.cu.
+int create_big(bmm_plan *pl, const bmm_init *init) {
+    const bmm_args &a = pl->a;
+    const int N = pl->N, P = pl->P, K = pl->K, ns = pl->ns, S = pl->S;
+    if (pl->C != 1) return fail(BMM_ERR_UNSUPPORTED, "the grid path runs one chain (n_chains <= 1)");
+    if (pl->relabel) return fail(BMM_ERR_UNSUPPORTED, "relabel is not available on the grid path yet");
+    if (a.replay && K > bmm::big_replay_max_k()) return fail(BMM_ERR_UNSUPPORTED, "grid-path replay needs K <= 64");
+    const long long n_global = a.n_global > 0 ? a.n_global : N;
+    if (a.row_offset < 0 || a.row_offset + N > n_global) return fail(BMM_ERR_INVALID, "row_offset + N exceeds n_global");
+    std::vector<uint32_t> bits;
+    int W;
+    TRY(pack_rows(a.X, N, P, bits, W));
+    pl->W = W; pl->U = N;
+    TRY(upload(pl->xbits, bits.data(), bits.size()));
+    const size_t KP = (size_t)K * P;
+    TRY(upload(pl->theta_cur, init->theta, KP));
+    TRY(upload(pl->pi_cur, init->pi, (size_t)K));
+    std::vector<double> al(1, a.alpha == 0 ? 1.0 : a.alpha);
+    TRY(upload(pl->alpha_cur, al.data(), 1));
+    CU(pl->w1.alloc(KP * 8)); CU(pl->w0.alloc(KP * 8)); CU(pl->lpi.alloc((size_t)K * 8)); CU(pl->gsc.alloc((size_t)K * 8));
+    CU(pl->counts.alloc(2 * (K + KP) * 4));
+    CU(pl->status.alloc(4));
+    const bool keep = !(a.flags & BMM_FLAG_NO_Z_HISTORY);
+    CU(pl->zhist.alloc(keep ? (size_t)ns * N : (size_t)N));
+    CU(pl->theta_out.alloc(KP * S * 8));
+    CU(pl->pi_out.alloc((size_t)S * K * 8));
+    CU(pl->alpha_out.alloc((size_t)S * 8));
+    if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)ns * N * K * 8));
+    if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->loglik_out.alloc((size_t)ns * N * K * 8));
+    if (a.replay) {
+        const bmm_replay *r = a.replay;
+        TRY(upload(pl->ru, r->u, (size_t)ns * N * r->u_slots));
+        TRY(upload(pl->rpi, r->pi, (size_t)ns * K));
+        TRY(upload(pl->rtheta, r->theta, KP * ns));
+        TRY(upload(pl->ralpha, r->alpha, (size_t)ns));
+    }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, a.device));
+    pl->sm_count = prop.multiProcessorCount;
+    bmm::BigParams &b = pl->bp;
+    b.N_global = n_global; b.row_offset = a.row_offset; b.N_local = N; b.P = P; b.K = K; b.W = W;
+    b.nsamples = ns; b.burnin = a.burnin; b.stickbreaking = pl->sampler == BMM_SAMPLER_STICKBREAKING;
+    b.precision = a.precision; b.tables_in_smem = bmm::big_tables_fit_smem(K, P, a.precision); b.keep_history = keep;
+    b.alpha0 = a.alpha; b.beta = a.beta; b.gamma = a.gamma; b.a = a.a; b.b = a.b;
+    b.seed = a.seed; b.chain_offset = a.chain_offset; b.flags = a.flags;
+    b.xbits = pl->xbits.as<uint32_t>();
+    b.w1 = pl->w1.as<double>(); b.w0 = pl->w0.as<double>(); b.lpi = pl->lpi.as<double>();
+    b.theta_cur = pl->theta_cur.as<double>(); b.pi_cur = pl->pi_cur.as<double>(); b.alpha_cur = pl->alpha_cur.as<double>();
+    b.gsc = pl->gsc.as<double>(); b.counts = pl->counts.as<int>(); b.status = pl->status.as<int>();
+    b.zhist = pl->zhist.as<uint8_t>();
+    b.theta_out = pl->theta_out.as<double>(); b.pi_out = pl->pi_out.as<double>(); b.alpha_out = pl->alpha_out.as<double>();
+    b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
+    b.ru = pl->ru.as<double>(); b.ru_slots = a.replay ? a.replay->u_slots : 0;
+    b.rpi = pl->rpi.as<double>(); b.rtheta = pl->rtheta.as<double>(); b.ralpha = pl->ralpha.as<double>();
+    return BMM_OK;
+}
+
+// All sweeps of the grid path on the plan's stream.
+int run_big(bmm_plan *pl) {
+    const bmm::BigParams &b = pl->bp;
+    const int ns = pl->ns;
+    const size_t ncnt = (size_t)b.K + (size_t)b.K * b.P;
+    const bool sharded = b.N_global > b.N_local;
+    if (sharded && bmm::dist_world() < 2) return fail(BMM_ERR_NCCL, "N-sharded run needs bmm_dist_init with world > 1");
+    while (pl->sweep_ev.size() < (size_t)2 * ns) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        pl->sweep_ev.push_back(e);
+    }
+    CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
+    CU(bmm::launch_big_init(b, pl->stream));
+    for (int j = 1; j < ns; ++j) {
+        if (b.ru) CU(bmm::launch_big_replay_load(b, j, pl->stream));
+        CU(cudaEventRecord(pl->sweep_ev[2 * j], pl->stream));
+        CU(bmm::launch_big_sweep(b, j, pl->sm_count, pl->stream));
+        CU(cudaEventRecord(pl->sweep_ev[2 * j + 1], pl->stream));
+        if (sharded && bmm::dist_allreduce_i32(pl->counts.as<int>() + (size_t)(j & 1) * ncnt, ncnt, pl->stream))
+            return fail(BMM_ERR_NCCL, bmm::dist_error());
+        CU(bmm::launch_big_params(b, j, pl->stream));
+    }
+    return BMM_OK;
+}
+
 int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     const bmm_args &a = pl->a;
     const int N = pl->N, P = pl->P, K = pl->K, C = pl->C, ns = pl->ns, S = pl->S;
@@ -326,11 +417,22 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     return BMM_OK;
 }
 
+// Threads per chain block of the uncollapsed chain-per-block kernel: 128 registers/thread cap the SM
+// at 512 resident threads, so smaller blocks keep more chains resident (one wave for 1024 chains at
+// 64 threads; measured on C2: 32 threads 9.5 ms, 64: 9.9 ms, 128: 14.4 ms per 300 sweeps).  BMM_FULL_THREADS overrides (tuning).
+int full_threads(int n_chains) {
+    if (const char *e = getenv("BMM_FULL_THREADS")) {
+        int t = atoi(e);
+        if (t == 32 || t == 64 || t == 128) return t;
+    }
+    return n_chains >= 1024 ? 32 : (n_chains >= 512 ? 64 : 128);
+}
+
 int run_segment(bmm_plan *pl, int j0, int j1) {
     if (j1 <= j0) return BMM_OK;
     if (pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING) {
         pl->fp.j_begin = j0; pl->fp.j_end = j1;
-        CU(bmm::launch_full(pl->fp, pl->C, 128, pl->stream));
+        CU(bmm::launch_full(pl->fp, pl->C, full_threads(pl->C), pl->stream));
     } else {
         pl->cp.j_begin = j0; pl->cp.j_end = j1;
         CU(bmm::launch_collapsed(pl->cp, pl->C, pl->stream));
@@ -379,11 +481,16 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
     if (e == cudaSuccess) e = cudaEventCreate(&pl->evk1);
     for (auto &ev : pl->evs) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e));
-    if (!rc) rc = (sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING) ? create_full(pl, init) : create_collapsed(pl, init);
+    const bool uncollapsed = sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING;
+    if (uncollapsed)
+        pl->grid_path = (args->flags & BMM_FLAG_GRID_PATH) || args->n_global > args->N ||
+                        (pl->C == 1 && (args->N >= 32768 || (size_t)args->K * args->P > 4096));
+    if (!rc) rc = pl->grid_path ? create_big(pl, init) : (uncollapsed ? create_full(pl, init) : create_collapsed(pl, init));
     if (!rc) {
         // R-layout allocation histories are produced on the device by the finalize kernel
         const size_t eb = (args->flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
-        cudaError_t e2 = pl->z_orig.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
+        const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
+        cudaError_t e2 = no_z ? cudaSuccess : pl->z_orig.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
         if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
         if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
     }
@@ -400,7 +507,11 @@ int bmm_plan_run(bmm_plan *pl) {
     CU(cudaEventRecord(pl->ev0, pl->stream));
     CU(cudaEventRecord(pl->evk0, pl->stream));
     CU(cudaEventRecord(pl->evs[0], pl->stream));
-    if (pl->relabel) {
+    if (pl->grid_path) {
+        TRY(run_big(pl));
+        CU(cudaEventRecord(pl->evs[1], pl->stream));
+        CU(cudaEventRecord(pl->evs[2], pl->stream));
+    } else if (pl->relabel) {
         TRY(run_segment(pl, 1, burnin));
         CU(cudaEventRecord(pl->evs[1], pl->stream));
         const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
@@ -418,9 +529,10 @@ int bmm_plan_run(bmm_plan *pl) {
     CU(cudaEventRecord(pl->evs[3], pl->stream));
     CU(cudaEventRecord(pl->evk1, pl->stream));
     const int eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
-    CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
-                              pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
-                              pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
+    if (pl->z_orig.p)
+        CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
+                                  pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
+                                  pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
     CU(cudaEventRecord(pl->evs[4], pl->stream));
     CU(cudaEventRecord(pl->ev1, pl->stream));
     pl->ran = true;
@@ -445,6 +557,17 @@ int bmm_plan_kernel_ms(bmm_plan *pl, float ms_out[4]) {
     if (!pl || !pl->ran || !ms_out) return fail(BMM_ERR_INVALID, "plan has not run");
     CU(cudaEventSynchronize(pl->evs[4]));
     for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms_out[i], pl->evs[i], pl->evs[i + 1]));
+    if (pl->grid_path) {
+        // [0] sum of the sweep kernels, [1] everything else in the sweep loop (parameter kernels,
+        // all-reduce), [2] 0, [3] history layout conversion
+        float sweeps = 0.f, total = ms_out[0];
+        for (int j = 1; j < pl->ns; ++j) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, pl->sweep_ev[2 * j], pl->sweep_ev[2 * j + 1]));
+            sweeps += t;
+        }
+        ms_out[0] = sweeps; ms_out[1] = total - sweeps; ms_out[2] = 0.f;
+    }
     return BMM_OK;
 }
 

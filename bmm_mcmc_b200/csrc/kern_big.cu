@@ -1,0 +1,344 @@
+// Uncollapsed samplers for ONE chain over many observations (BASELINE configs C4 / C5): the z-sweep is
+// data-parallel over observations, so the whole GPU (and, N-sharded, several GPUs) works on one
+// sweep.  Replaces, per sweep,
+//   z-sweep               /root/reference/src/full_gibbs.cpp:87-157, stickbreaking.cpp:70-140
+//   sufficient statistics full_gibbs.cpp:182-200, stickbreaking.cpp:164-186
+//   pi / sticks / theta / alpha draws  full_gibbs.cpp:10-27,202-230, stickbreaking.cpp:187-235, utils.cpp:6-14
+//
+// Launch sequence per sweep j (all on one stream):
+//   big_sweep_kernel   grid-wide: one observation per thread; bit-packed row -> K conditional
+//                      probabilities -> categorical draw -> 1-byte allocation; counts c_k, V_kd as
+//                      shared-memory histograms flushed once per block with global atomics.
+//   [all-reduce]       N-sharded runs only: int32 counts summed over ranks (dist.cu).
+//   big_param_kernel   theta_kd ~ Beta, gamma / stick draws, one thread per parameter (Philox keyed by
+//                      parameter index, so every rank draws identical values: no broadcast).
+//   big_finish_kernel  one block: pi (normalise / stick-breaking), alpha (Escobar-West), log tables for
+//                      the next sweep, history rows, zeroing of the next sweep's count buffer.
+//
+// The per-observation Philox counter is the GLOBAL observation index, and the reduced quantities are
+// integers, so the chain is bit-identical for any number of GPUs and identical to the
+// chain-per-block kernel (kern_full.cu) for the same seed.
+//
+// Template parameter R is the type of the probability arithmetic: double follows the reference's
+// operation order exactly (d-ordered log-likelihood sum, exp(log pi + loglh), running normaliser);
+// float is the CUDA-core fast path (BMM_FP32).  The tensor-core path lives in kern_big_tc.cu.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace bmm {
+namespace {
+
+constexpr int BIG_THREADS = 256;
+constexpr int REPLAY_MAXK = 64;
+
+template <typename R> __device__ __forceinline__ R exp_r(R x);
+template <> __device__ __forceinline__ double exp_r<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ float exp_r<float>(float x) { return __expf(x); }
+
+template <typename R>
+struct BigSmem {
+    R *w1, *w0, *lpi;
+    int *cnt;
+};
+
+template <typename R>
+__host__ __device__ inline size_t big_layout(int K, int P, bool tables_in_smem, char *base, BigSmem<R> *s) {
+    const size_t KP = (size_t)K * P;
+    size_t off = 0;
+    R *w1 = nullptr, *w0 = nullptr, *lpi = nullptr;
+    int *cnt = nullptr;
+    if (tables_in_smem) {
+        w1 = (R *)(base + off); off += KP * sizeof(R);
+        w0 = (R *)(base + off); off += KP * sizeof(R);
+        lpi = (R *)(base + off); off += (size_t)K * sizeof(R);
+        off = (off + 7) & ~(size_t)7;
+        cnt = (int *)(base + off); off += (K + KP) * sizeof(int);
+    }
+    if (s) { s->w1 = w1; s->w0 = w0; s->lpi = lpi; s->cnt = cnt; }
+    return (off + 15) & ~(size_t)15;
+}
+
+// loglh_k(x) = sum_d x_d log theta_kd + (1 - x_d) log(1 - theta_kd), summed in d order (full_gibbs.cpp:92-103)
+template <typename R>
+__device__ __forceinline__ R row_loglik(const uint32_t *__restrict__ xb, int P, int K, int k, const R *w1, const R *w0) {
+    R ll = 0;
+    for (int d0 = 0; d0 < P; d0 += 32) {
+        const uint32_t word = xb[d0 >> 5];
+        const int dn = min(32, P - d0);
+        for (int b = 0; b < dn; ++b) {
+            const int d = d0 + b;
+            ll += ((word >> b) & 1u) ? w1[k + K * d] : w0[k + K * d];
+        }
+    }
+    return ll;
+}
+
+template <typename R, bool REPLAY>
+__global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams p, const int j) {
+    extern __shared__ __align__(16) char smem_raw[];
+    BigSmem<R> s;
+    big_layout<R>(p.K, p.P, p.tables_in_smem, smem_raw, &s);
+    const int K = p.K, P = p.P, W = p.W, KP = K * P, tid = threadIdx.x;
+    int *gcnt = p.counts + (size_t)(j & 1) * (K + KP);
+    const R *w1, *w0, *lpi;
+    if (p.tables_in_smem) {
+        for (int t = tid; t < KP; t += blockDim.x) { s.w1[t] = (R)p.w1[t]; s.w0[t] = (R)p.w0[t]; }
+        for (int t = tid; t < K; t += blockDim.x) s.lpi[t] = (R)p.lpi[t];
+        for (int t = tid; t < K + KP; t += blockDim.x) s.cnt[t] = 0;
+        __syncthreads();
+        w1 = s.w1; w0 = s.w0; lpi = s.lpi;
+    } else {
+        w1 = (const R *)p.w1; w0 = (const R *)p.w0; lpi = (const R *)p.lpi;  // R == double on this path
+    }
+    int *cnt = p.tables_in_smem ? s.cnt : gcnt;
+    const bool stable = (p.flags & 1u) != 0;  // BMM_FLAG_STABLE_SOFTMAX
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
+    const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+    uint8_t *zrow = p.zhist ? p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local : nullptr;
+
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < p.N_local; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t *xb = p.xbits + (size_t)i * W;
+        const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
+        R mx = 0;
+        if (stable) {
+            mx = -INFINITY;
+            for (int k = 0; k < K; ++k) mx = max(mx, lpi[k] + row_loglik<R>(xb, P, K, k, w1, w0));
+        }
+        R cum = 0;
+        for (int k = 0; k < K; ++k) cum += exp_r<R>(lpi[k] + row_loglik<R>(xb, P, K, k, w1, w0) - mx);
+        if (!(cum > 0) || !isfinite(cum)) *p.status = -9;  // BMM_ERR_PROB
+        int z;
+        if (REPLAY) {
+            double pr[REPLAY_MAXK];
+            for (int k = 0; k < K; ++k) pr[k] = (double)(exp_r<R>(lpi[k] + row_loglik<R>(xb, P, K, k, w1, w0) - mx) / cum);
+            z = rmultinom1_replay(K, [&](int k) { return pr[k]; },
+                                  p.ru + ((size_t)j * p.N_local + i) * p.ru_slots);
+        } else {
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
+            const double u = (gi & 1) ? u53(rnd.z, rnd.w) : u53(rnd.x, rnd.y);
+            R c2 = 0;
+            z = K - 1;
+            for (int k = 0; k < K - 1; ++k) {
+                c2 += exp_r<R>(lpi[k] + row_loglik<R>(xb, P, K, k, w1, w0) - mx) / cum;
+                if (u < (double)c2) { z = k; break; }
+            }
+        }
+        if (p.probs_out || p.loglik_out) {
+            for (int k = 0; k < K; ++k) {
+                const R ll = row_loglik<R>(xb, P, K, k, w1, w0);
+                if (p.loglik_out) p.loglik_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * k] = (double)ll;
+                if (p.probs_out) p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * k] = (double)(exp_r<R>(lpi[k] + ll - mx) / cum);
+            }
+        }
+        if (zrow) zrow[i] = (uint8_t)(z + 1);
+        atomicAdd(&cnt[z], 1);
+        for (int d0 = 0; d0 < P; d0 += 32) {
+            uint32_t word = xb[d0 >> 5];
+            if (P - d0 < 32) word &= (1u << (P - d0)) - 1u;
+            while (word) {
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                atomicAdd(&cnt[K + z + K * (d0 + b)], 1);
+            }
+        }
+    }
+    if (p.tables_in_smem) {
+        __syncthreads();
+        for (int t = tid; t < K + KP; t += blockDim.x) {
+            const int v = s.cnt[t];
+            if (v) atomicAdd(&gcnt[t], v);
+        }
+    }
+}
+
+// One thread per parameter: gamma / stick draws for t < K, theta draws for t >= K.
+__global__ void big_param_kernel(const BigParams p, const int j) {
+    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples;
+    const int *cnt = p.counts + (size_t)(j & 1) * (K + KP);
+    const uint32_t chain = (uint32_t)p.chain_offset;
+    const double alpha_prev = *p.alpha_cur;
+    const bool replay = p.rtheta != nullptr;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + KP; t += gridDim.x * blockDim.x) {
+        if (t < K) {
+            if (replay) continue;
+            if (!p.stickbreaking) {  // Dirichlet via K Gamma(alpha/K + c_k, 1) (full_gibbs.cpp:202-210)
+                Stream st(p.seed, chain, (uint32_t)j, ST_PI, (uint32_t)t);
+                p.gsc[t] = st.gamma(alpha_prev / K + cnt[t]);
+            } else {                 // v_k ~ Beta(1 + c_k, alpha + sum_{l>k} c_l) (stickbreaking.cpp:187-193)
+                long long later = 0;
+                for (int l = t + 1; l < K; ++l) later += cnt[l];
+                Stream st(p.seed, chain, (uint32_t)j, ST_STICK, (uint32_t)t);
+                p.gsc[t] = st.beta(1.0 + cnt[t], alpha_prev + (double)later);
+            }
+        } else {                     // theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) (full_gibbs.cpp:213-225)
+            const int e = t - K, k = e % K, d = e / K;
+            double th;
+            if (replay) th = p.rtheta[(size_t)KP * j + e];
+            else {
+                Stream st(p.seed, chain, (uint32_t)j, ST_THETA, (uint32_t)(k * P + d));
+                th = st.beta(p.beta + cnt[K + e], p.gamma + cnt[k] - cnt[K + e]);
+            }
+            p.theta_cur[e] = th;
+            p.w1[e] = log(th);
+            p.w0[e] = log(1 - th);
+            if (p.theta_out && j >= p.burnin) p.theta_out[(size_t)KP * (j - p.burnin) + e] = th;
+        }
+    }
+    (void)ns;
+}
+
+// One block: pi, alpha, log pi, history rows; zero the next sweep's count buffer.
+__global__ void big_finish_kernel(const BigParams p, const int j) {
+    __shared__ double red[32];
+    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = ns - p.burnin, tid = threadIdx.x;
+    const bool replay = p.rtheta != nullptr;
+    const double alpha_prev = *p.alpha_cur;
+    int *next = p.counts + (size_t)((j + 1) & 1) * (K + KP);
+    for (int t = tid; t < K + KP; t += blockDim.x) next[t] = 0;
+    if (replay) {
+        for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.rpi[j + (size_t)ns * k];
+        __syncthreads();
+        if (tid == 0) *p.alpha_cur = p.ralpha[j];
+    } else if (!p.stickbreaking) {
+        double part = 0.0;
+        for (int k = tid; k < K; k += blockDim.x) part += p.gsc[k];
+        part = warp_sum_xor(part, 32);
+        if ((tid & 31) == 0) red[tid >> 5] = part;
+        __syncthreads();
+        double sum = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+        for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.gsc[k] / sum;
+        if (tid == 0 && p.alpha0 == 0.0) {
+            Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, 0u);
+            *p.alpha_cur = update_alpha_dev(st, alpha_prev, p.a, p.b, (int)p.N_global, K);
+        }
+    } else if (tid == 0) {           // stick-breaking weights (stickbreaking.cpp:195-214)
+        p.gsc[K - 1] = 1.0;
+        int K_viable = 0;
+        double cumprod = 1.0;
+        for (int k = 0; k < K; ++k) {
+            const double pk = (k == 0) ? p.gsc[0] : cumprod * p.gsc[k];
+            p.pi_cur[k] = pk;
+            if (pk > 0.01) K_viable++;
+            cumprod *= (1 - p.gsc[k]);
+        }
+        if (p.alpha0 == 0.0) {
+            Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, 0u);
+            *p.alpha_cur = update_alpha_dev(st, alpha_prev, p.a, p.b, (int)p.N_global, K_viable);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += blockDim.x) {
+        const double pk = p.pi_cur[k];
+        p.lpi[k] = log(pk);
+        if (p.pi_out && j >= p.burnin) p.pi_out[(j - p.burnin) + (size_t)S * k] = pk;
+    }
+    if (tid == 0 && p.alpha_out && j >= p.burnin) p.alpha_out[j - p.burnin] = *p.alpha_cur;
+    (void)P;
+}
+
+// Log tables of the initial state (sweep 1 reads theta_0, pi_0); iteration 0 of the histories.
+__global__ void big_init_kernel(const BigParams p) {
+    const int K = p.K, P = p.P, KP = K * P, S = p.nsamples - p.burnin;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + KP; t += gridDim.x * blockDim.x) {
+        if (t < K) {
+            const double pk = p.pi_cur[t];
+            p.lpi[t] = log(pk);
+            if (p.burnin == 0 && p.pi_out) p.pi_out[(size_t)S * t] = pk;
+        } else {
+            const int e = t - K;
+            const double th = p.theta_cur[e];
+            p.w1[e] = log(th);
+            p.w0[e] = log(1 - th);
+            if (p.burnin == 0 && p.theta_out) p.theta_out[e] = th;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.burnin == 0 && p.alpha_out) p.alpha_out[0] = *p.alpha_cur;
+    (void)P;
+}
+
+// replay: state of sweep j-1 comes from the recorded run
+__global__ void big_replay_load_kernel(const BigParams p, const int j) {
+    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + KP; t += gridDim.x * blockDim.x) {
+        if (t < K) {
+            const double pk = p.rpi[(j - 1) + (size_t)ns * t];
+            p.pi_cur[t] = pk;
+            p.lpi[t] = log(pk);
+        } else {
+            const int e = t - K;
+            const double th = p.rtheta[(size_t)KP * (j - 1) + e];
+            p.theta_cur[e] = th;
+            p.w1[e] = log(th);
+            p.w0[e] = log(1 - th);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.alpha_cur = p.ralpha[j - 1];
+    (void)P;
+}
+
+template <typename R>
+cudaError_t launch_sweep_t(const BigParams &p, int j, int grid, cudaStream_t st) {
+    BigSmem<R> *none = nullptr;
+    const size_t smem = big_layout<R>(p.K, p.P, p.tables_in_smem, nullptr, none);
+    cudaError_t e;
+    if (p.ru) {
+        e = cudaFuncSetAttribute(big_sweep_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        big_sweep_kernel<R, true><<<grid, BIG_THREADS, smem, st>>>(p, j);
+    } else {
+        e = cudaFuncSetAttribute(big_sweep_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        big_sweep_kernel<R, false><<<grid, BIG_THREADS, smem, st>>>(p, j);
+    }
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool big_tables_fit_smem(int K, int P, int precision) {
+    const size_t KP = (size_t)K * P, r = precision == 1 ? 4 : 8;
+    return (2 * KP + K) * r + (K + KP) * 4 + 64 <= 96 * 1024;
+}
+
+int big_replay_max_k() { return REPLAY_MAXK; }
+
+cudaError_t launch_big_init(const BigParams &p, cudaStream_t st) {
+    const int n = p.K + p.K * p.P;
+    big_init_kernel<<<min(296, (n + 255) / 256), 256, 0, st>>>(p);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st) {
+    const int n = p.K + p.K * p.P;
+    big_replay_load_kernel<<<min(296, (n + 255) / 256), 256, 0, st>>>(p, j);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st) {
+    long long blocks = ((long long)p.N_local + BIG_THREADS - 1) / BIG_THREADS;
+    const int cap = sm_count * 8;
+    const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+    if (p.precision == 1) {
+        // float tables are the double tables converted on load (tables_in_smem) -- the global-table
+        // variant reads the double tables through R = double.
+        if (p.tables_in_smem) return launch_sweep_t<float>(p, j, grid, st);
+    }
+    return launch_sweep_t<double>(p, j, grid, st);
+}
+
+cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st) {
+    const int n = p.K + p.K * p.P;
+    big_param_kernel<<<min(1184, (n + 127) / 128), 128, 0, st>>>(p, j);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    big_finish_kernel<<<1, 256, 0, st>>>(p, j);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace bmm

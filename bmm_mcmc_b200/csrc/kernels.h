@@ -88,6 +88,35 @@ struct CollapsedParams {
 size_t collapsed_smem_bytes(const CollapsedParams &p);
 cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_t st);
 
+// ---- uncollapsed samplers, one chain over the whole GPU / N-sharded over GPUs (kern_big.cu) ----
+struct BigParams {
+    long long N_global, row_offset;   // this rank holds observations [row_offset, row_offset + N_local)
+    int N_local, P, K, W;
+    int nsamples, burnin, stickbreaking, precision;
+    int tables_in_smem;               // K*P log tables + count histogram fit shared memory
+    int keep_history;                 // zhist holds every sweep ([nsamples][N_local]) or only the current one
+    double alpha0, beta, gamma, a, b;
+    unsigned long long seed;
+    int chain_offset;
+    unsigned flags;
+    const uint32_t *xbits;            // [N_local][W]
+    double *w1, *w0, *lpi;            // log theta [K*P] (k + K*d), log(1-theta), log pi [K]
+    double *theta_cur, *pi_cur, *alpha_cur, *gsc;
+    int *counts;                      // 2 x (K + K*P): c_k then V_kd (k + K*d); sweep j uses buffer j & 1
+    int *status;
+    uint8_t *zhist;
+    double *theta_out, *pi_out, *alpha_out;   // [K*P*S], [S*K cm], [S]
+    double *probs_out, *loglik_out;   // [nsamples][N_local*K cm] or nullptr
+    const double *ru; int ru_slots;   // replay
+    const double *rpi, *rtheta, *ralpha;
+};
+bool big_tables_fit_smem(int K, int P, int precision);
+int big_replay_max_k();
+cudaError_t launch_big_init(const BigParams &p, cudaStream_t st);
+cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st);
+cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st);
+cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st);
+
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,
                                   double *Q, double *logQ, int *perm, double *cost, char *assign_ws,

@@ -44,6 +44,11 @@ extern "C" {
                                         full_gibbs.cpp:106 underflows to NaN at large P)          */
 #define BMM_FLAG_COMPACT_Z 2u        /* out->z / z_original are uint8 buffers (cast pointer), not
                                         int32: 1 B per allocation over PCIe; K must be <= 255     */
+#define BMM_FLAG_NO_Z_HISTORY 4u     /* keep only the current allocations on the device; out->z is
+                                        not written (large-N runs: S x N would not fit anywhere)   */
+#define BMM_FLAG_GRID_PATH 8u        /* force the one-chain-over-the-whole-GPU kernels (default:
+                                        chosen when n_chains <= 1 and N >= 32768, or when K*P is
+                                        too large for the chain-per-block kernel)                  */
 
 /* Replay mode: the z draws consume these uniforms instead of Philox, and the parameter draws
  * (pi, theta, alpha) are taken from the recorded histories, so allocations and counts can be
@@ -78,6 +83,11 @@ typedef struct bmm_args {
     int32_t device;      /* CUDA device ordinal                                                    */
     uint32_t flags;      /* BMM_FLAG_*                                                             */
     const bmm_replay *replay; /* NULL = Philox                                                     */
+    /* N-sharded single chain (full / stick-breaking, n_chains <= 1): X holds this rank's rows
+     * [row_offset, row_offset + N) of an n_global-row data set; counts are all-reduced over the
+     * ranks of bmm_dist_init each sweep.  0 = not sharded (n_global = N).                         */
+    int64_t n_global;
+    int64_t row_offset;
 } bmm_args;
 
 /* Initial state, drawn by the R wrappers before entering C++ (R/utils.R:42,68-74,98-103). */

@@ -272,3 +272,69 @@ def test_dp_requires_symmetric_prior(datasets):
     with pytest.raises(_lib.BmmError) as e:
         B.gibbs_dp(datasets["K2_N100_P5"], 20, beta=0.5, gamma=0.7)
     assert e.value.code == -4
+
+
+# ---- grid path: one chain over the whole GPU (kern_big.cu) ----------------------------------------
+@pytest.mark.parametrize("sampler", ["full", "stickbreaking"])
+def test_grid_path_replay(oracle, datasets, sampler):
+    """The grid-wide kernels consume the oracle's uniforms / parameter draws: z, counts bit-exact."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    N, P = X.shape
+    K, ns, burnin = (3, 40, 10) if sampler == "full" else (8, 30, 10)
+    ip, th = _init_full(K, P, 5)
+    of = oracle.gibbs_full if sampler == "full" else oracle.gibbs_stickbreaking
+    gf = B.gibbs_full if sampler == "full" else B.gibbs_stickbreaking
+    r = of(X, ip, th, ns, K, burnin=burnin, seed=11)
+    g = gf(X, ns, K, burnin=burnin, initial_pi=ip, initial_theta=th, replay=_replay_of(r),
+           probes=("probs", "loglik"), grid_path=True)
+    t = r.tail()
+    _close(g["loglik"][1:], r["loglik"][1:])
+    _close(g["probs"][1:], r["probs"][1:], atol=1e-300)
+    assert np.array_equal(g["z"], t["z"])
+    _close(g["theta"], t["theta"], rtol=0)
+    _close(g["pi"], t["pi"], rtol=0)
+    _close(g["alpha"], t["alpha"], rtol=0)
+
+
+@pytest.mark.parametrize("sampler,K", [("full", 3), ("stickbreaking", 6)])
+def test_grid_path_equals_chain_path(datasets, sampler, K):
+    """Same seed => the grid-wide kernels and the chain-per-block kernel produce the same chain, bit for bit
+    (global-index Philox counters, same operation order)."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    gf = B.gibbs_full if sampler == "full" else B.gibbs_stickbreaking
+    a = gf(X, 60, K, seed=42)
+    b = gf(X, 60, K, seed=42, grid_path=True)
+    for k in ("z", "theta", "pi", "alpha"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_grid_path_fp32_close(oracle, datasets):
+    """BMM_FP32 probability arithmetic: conditional probabilities within 1e-4 relative of the fp64 oracle."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    N, P = X.shape
+    K, ns = 3, 12
+    ip, th = _init_full(K, P, 5)
+    r = oracle.gibbs_full(X, ip, th, ns, K, burnin=2, seed=11)
+    g = B.gibbs_full(X, ns, K, burnin=2, initial_pi=ip, initial_theta=th, replay=_replay_of(r), probes=("probs",),
+                     grid_path=True, precision="fp32")
+    _close(g["probs"][1:], r["probs"][1:], rtol=1e-4, atol=1e-30)
+
+
+def test_grid_path_large_synthetic():
+    """Full-size property checks (no oracle at this size): counts consistent with z, pi sums to 1."""
+    _need_gpu()
+    rng = np.random.default_rng(3)
+    N, P, K = 200_000, 64, 32
+    th_true = rng.uniform(0.1, 0.9, (K, P))
+    zt = rng.integers(0, K, N)
+    X = (rng.random((N, P)) < th_true[zt]).astype(np.int32)
+    g = B.gibbs_stickbreaking(X, 12, K, alpha=1.0, burnin=1, seed=9)
+    assert g["z"].shape == (11, N) and g["z"].min() >= 1 and g["z"].max() <= K
+    assert np.allclose(g["pi"].sum(1), 1.0) and np.isfinite(g["theta"]).all()
+    h = B.gibbs_stickbreaking(X, 12, K, alpha=1.0, burnin=1, seed=9, precision="fp32")
+    assert h["z"].shape == (11, N)
+    # first sweep uses identical parameters: fp32 and fp64 allocations agree except at ulp-close draws
+    assert (g["z"][0] != h["z"][0]).mean() < 1e-3
