@@ -205,17 +205,230 @@ def run_reference(a):
     return 0
 
 
+# ---- grid workloads: one uncollapsed chain over many observations, N-sharded across GPUs ----------
+GRID_WORKLOADS = {
+    # BASELINE.json configs[3]: strong scaling, total N fixed, counts all-reduced every sweep
+    "c4": dict(sampler="stickbreaking", N=10_000_000, P=64, K=32, nsamples=101, burnin=11, alpha=1.0,
+               precision="fp32", cpu_N=60_000, cpu_ns=6,
+               label="C4: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1"),
+    "c4small": dict(sampler="stickbreaking", N=1_000_000, P=64, K=32, nsamples=21, burnin=3, alpha=1.0,
+                    precision="fp32", cpu_N=20_000, cpu_ns=4,
+                    label="C4 shape at N=1e6 (smoke size)"),
+}
+
+
+def synth_rows(lo, hi, P, K_true, seed=17, chunk=500_000):
+    """Rows [lo, hi) of the synthetic data set: pi* uniform, theta* ~ U(0.1, 0.9),
+    x_id ~ Bernoulli(theta*[z*_i, d]); generated chunk by chunk so any shard sees the same rows."""
+    from bmm_mcmc_b200 import PackedX
+    th = np.random.default_rng([seed, 0]).uniform(0.1, 0.9, (K_true, P)).astype(np.float32)
+    W = (P + 31) // 32
+    out = np.zeros((hi - lo, W), dtype=np.uint32)
+    c0 = lo // chunk
+    while c0 * chunk < hi:
+        a0, a1 = c0 * chunk, (c0 + 1) * chunk
+        rng = np.random.default_rng([seed, 1 + c0])
+        z = rng.integers(0, K_true, chunk)
+        x = rng.random((chunk, P), dtype=np.float32) < th[z]
+        s0, s1 = max(a0, lo), min(a1, hi)
+        out[s0 - lo:s1 - lo] = PackedX.pack(x[s0 - a0:s1 - a0]).bits
+        c0 += 1
+    return PackedX(out, P)
+
+
+def grid_init(K, P):
+    from bmm_mcmc_b200.rcompat import RRng
+    rng = RRng(1)
+    ip = np.exp(rng.runif(K)); ip /= ip.sum()                  # R/utils.R:98-100
+    th = rng.runif(K * P).reshape(P, K)                        # matrix(runif(K*P), nrow=K), column-major
+    return np.ascontiguousarray(ip[None]), np.ascontiguousarray(th[None])
+
+
+def grid_cpu_baseline(w):
+    from oracle import pyoracle as O
+    N, ns, K, P = w["cpu_N"], w["cpu_ns"], w["K"], w["P"]
+    X = synth_rows(0, N, P, K)
+    Xi = ((X.bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(N, -1)[:, :P].astype(np.int32)
+    ip, th = grid_init(K, P)
+    f = O.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else O.gibbs_full
+    t0 = time.perf_counter()
+    f(Xi, ip[0], th[0].T, ns, K, alpha=w["alpha"], burnin=1, seed=3, probes=False)
+    sec = time.perf_counter() - t0
+    return {"value": N * (ns - 1) / sec, "unit": "allocation updates/s", "cores": 1, "kind": "port",
+            "sample": "%s reduced to N=%d, %d sweeps (the reference's N x K x nsamples double cube cannot hold N=%g; "
+                      "per-update cost of the uncollapsed sampler does not depend on N), %.1f s"
+                      % (w["label"], N, ns - 1, w["N"], sec)}, sec
+
+
+def run_grid_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    import multiprocessing as mp
+    w = GRID_WORKLOADS[a.workload]
+    cores = os.cpu_count() or 1
+    from oracle import pyoracle as O
+    O.lib()
+    ctx = mp.get_context("fork")
+    tot_u, tot_s = 0, 0.0
+    with ctx.Pool(cores) as pool:
+        for step in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            pool.map(grid_cpu_baseline, [w] * cores)
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                tot_u += cores * w["cpu_N"] * (w["cpu_ns"] - 1); tot_s += dt
+    val = tot_u / tot_s
+    sample = "one independent reduced chain per core: %d cores x N=%d x %d sweeps per step" % (cores, w["cpu_N"], w["cpu_ns"] - 1)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "allocation updates/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / max(a.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seed 17)",
+        "config": {"workload": w["label"] + "; CPU sample: " + sample},
+        "cpu_baseline": {"value": val, "unit": "allocation updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "allocation updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+    return 0
+
+
+def run_grid(a):
+    w = dict(GRID_WORKLOADS[a.workload])
+    if a.nsamples:
+        w["nsamples"] = a.nsamples
+    if a.n:
+        w["N"] = a.n
+    if a.precision:
+        w["precision"] = a.precision
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import bmm_mcmc_b200 as B
+    from bmm_mcmc_b200 import _lib, api, dist as bdist
+    L = _lib.lib()
+    assert L.bmm_device_count() > local, "no CUDA device: the product path has no CPU fallback"
+    bdist.init(rank, world, local)
+    N, P, K, ns, burnin = w["N"], w["P"], w["K"], w["nsamples"], w["burnin"]
+    lo, hi = bdist.shard_rows(N, world, rank)
+    X = synth_rows(lo, hi, P, K)
+    ip, th = grid_init(K, P)
+    sid = _lib.SAMPLER_STICKBREAKING if w["sampler"] == "stickbreaking" else _lib.SAMPLER_FULL
+    shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
+    kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=False, burnrelabel=0)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    plan = api.Plan(sid, X, ns, K, chains=1, seed=2026, device=local, init_pi=ip, init_theta=th,
+                    precision=w["precision"], compact_z=True, grid_path=True, **shard, **kw)
+    for _ in range(a.warmup):
+        plan.run(); plan.sync()
+    clocks = ClockSampler(local)
+    barrier(); plan.sync()
+    clocks.start()
+    l0 = L.bmm_launch_count()
+    t0 = time.perf_counter()
+    dev_ms, kern = 0.0, np.zeros(4)
+    for _ in range(a.steps):
+        plan.run(); plan.sync()
+        dev_ms += plan.elapsed_ms()[0]
+        kern += np.array(plan.kernel_ms())
+    plan.sync(); barrier()
+    wall_s = time.perf_counter() - t0
+    launches = int(L.bmm_launch_count() - l0)
+    clk = clocks.stop()
+    plan.close()
+
+    # e2e: the public call with host buffers (bit-packed rows in, uint8 allocation history out)
+    bufs = api._alloc_out(sid, 1, hi - lo, P, K, ns, burnin, False, True, (), True)
+    d2h = api.out_nbytes(bufs[0])
+    h2d = X.nbytes + ip.nbytes + th.nbytes
+    fn = B.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else B.gibbs_full
+
+    def e2e_step():
+        return fn(X, ns, K, alpha=w["alpha"], burnin=burnin, seed=2026, device=local, initial_pi=ip,
+                  initial_theta=th.transpose(0, 2, 1), precision=w["precision"], compact_z=True, grid_path=True,
+                  out_bufs=bufs, **shard)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert 1 <= int(r["z"][-1].max()) <= K
+
+    tm = np.array([dev_ms / 1e3, wall_s, e2e_s])
+    if dist:
+        import torch
+        t = torch.tensor(tm, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tm = t.cpu().numpy()
+    total_updates = N * (ns - 1) * a.steps
+    pk, pk_src = peaks()
+    n_local = hi - lo
+    bytes_per_update = (P + 7) // 8 + 1
+    dur_s = kern[0] / a.steps / (ns - 1) / 1e3
+    achieved = n_local * bytes_per_update / dur_s / 1e9
+    line = {
+        "metric": METRIC, "value": total_updates / tm[0], "unit": "allocation updates/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tm[0] / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["precision"] == "fp32" else "f64",
+        "data": "synthetic (seed 17): pi* uniform, theta* ~ U(0.1,0.9), bit-packed rows",
+        "config": {"workload": "%s, nsamples=%d (one step = %d sweeps), relabel=FALSE" % (w["label"], ns, ns - 1),
+                   "N": N, "rows_per_gpu": n_local,
+                   "parallelism": "rows block-partitioned over GPUs; int32 counts all-reduced (NCCL) every sweep"
+                                  if world > 1 else "single GPU",
+                   "l2": "per-sweep input (%.0f MB of packed rows + allocations) vs 126 MB L2; sweeps alternate "
+                         "history rows" % (n_local * bytes_per_update / 1e6)},
+        "clocks": clk,
+        "e2e": {"value": total_updates / tm[2], "unit": "allocation updates/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tm[2] / a.steps,
+                "api": "bmm_mcmc_b200.gibbs_%s(PackedX, ...) -> bmm_gibbs_%s (C ABI), pinned host output buffers"
+                       % (w["sampler"], w["sampler"])},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                     "kernel": "big_sweep_kernel (%d rows, %d B/update)" % (n_local, bytes_per_update),
+                     "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))},
+        "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,
+                  "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "params_and_allreduce": kern[1] / a.steps,
+                                 "finalize_layout": kern[3] / a.steps}},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu:
+        line["cpu_baseline"] = grid_cpu_baseline(w)[0]
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    bdist.finalize()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(GRID_WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="grid workloads: override N")
+    ap.add_argument("--precision", default=None, choices=["fp32", "fp64"])
     ap.add_argument("--chains", type=int, default=None)
     ap.add_argument("--nsamples", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    if a.workload in GRID_WORKLOADS:
+        if a.impl == "reference":
+            return run_grid_reference(a)
+        a.warmup = max(a.warmup, 3)
+        return run_grid(a)
     if a.impl == "reference":
         return run_reference(a)
     a.warmup = max(a.warmup, 3)

@@ -10,13 +10,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbmm_b200.so")
 
 BMM_FP64, BMM_FP32 = 0, 1
-FLAG_STABLE_SOFTMAX, FLAG_COMPACT_Z, FLAG_NO_Z_HISTORY, FLAG_GRID_PATH = 1, 2, 4, 8
+FLAG_STABLE_SOFTMAX, FLAG_COMPACT_Z, FLAG_NO_Z_HISTORY, FLAG_GRID_PATH, FLAG_X_PACKED, FLAG_NO_TENSOR = 1, 2, 4, 8, 16, 32
 SAMPLER_FULL, SAMPLER_STICKBREAKING, SAMPLER_COLLAPSED, SAMPLER_DP = 0, 1, 2, 3
 
 ERRORS = {
     -1: "BMM_ERR_INVALID", -2: "BMM_ERR_CUDA", -3: "BMM_ERR_NOT_BINARY", -4: "BMM_ERR_BETA_GAMMA",
     -5: "BMM_ERR_NO_FREE_CLUSTER", -6: "BMM_ERR_DP_STATE", -7: "BMM_ERR_NCCL", -8: "BMM_ERR_UNSUPPORTED",
-    -9: "BMM_ERR_PROB",
+    -9: "BMM_ERR_PROB", -10: "BMM_ERR_TIMEOUT",
 }
 
 _dbl_p = C.POINTER(C.c_double)
@@ -46,7 +46,7 @@ class Out(C.Structure):
     _fields_ = [
         ("pi", _dbl_p), ("alpha", _dbl_p), ("permutations", _i32_p), ("z", _i32_p), ("theta", _dbl_p),
         ("z_original", _i32_p), ("theta_original", _dbl_p), ("probs", _dbl_p), ("loglik", _dbl_p),
-        ("Q_final", _dbl_p), ("status", _i32_p),
+        ("Q_final", _dbl_p), ("status", _i32_p), ("counts", _i32_p),
     ]
 
 

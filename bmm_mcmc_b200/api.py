@@ -17,14 +17,40 @@ import numpy as np
 from . import _lib
 from .rcompat import RRng
 
-__all__ = ["gibbs_full", "gibbs_collapsed", "gibbs_dp", "gibbs_stickbreaking", "Plan"]
+__all__ = ["gibbs_full", "gibbs_collapsed", "gibbs_dp", "gibbs_stickbreaking", "Plan", "PackedX"]
 
 
 def _r_round(x):
     return int(round(x))  # R's round() and Python's are both half-to-even
 
 
+class PackedX:
+    """Bit-packed observations for the grid path (BMM_FLAG_X_PACKED): uint32 [N][ceil(P/32)], bit d%32
+    of word d//32 of row i is x_id.  `PackedX.pack(X)` packs a 0/1 matrix."""
+
+    def __init__(self, bits, P):
+        self.bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        assert self.bits.ndim == 2 and self.bits.shape[1] == (P + 31) // 32
+        self.shape = (self.bits.shape[0], int(P))
+        self.nbytes = self.bits.nbytes
+        self.ctypes = self.bits.ctypes
+
+    @classmethod
+    def pack(cls, X):
+        X = np.asarray(X)
+        N, P = X.shape
+        W = (P + 31) // 32
+        b = np.zeros((N, W * 32), dtype=np.uint8)
+        b[:, :P] = X != 0
+        return cls(np.packbits(b, axis=1, bitorder="little").view("<u4").reshape(N, W), P)
+
+    def rows(self, lo, hi):
+        return PackedX(self.bits[lo:hi], self.shape[1])
+
+
 def _as_X(data):
+    if isinstance(data, PackedX):
+        return data
     X = np.asarray(data)
     if X.ndim != 2:
         raise ValueError("data must be a 2-d matrix (observations x binary variables)")
@@ -83,7 +109,7 @@ def _chain_cm(C_, shape, dtype, pinned=False):
 def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
                 compact_z=False, stable_softmax=False, chain_offset=0, grid_path=False, no_z_history=False,
-                n_global=0, row_offset=0):
+                n_global=0, row_offset=0, no_tensor=False):
     """ctypes bmm_args / bmm_init for one call; returns (args, init, keepalive)."""
     N, P = X.shape
     args = _lib.Args()
@@ -95,7 +121,10 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     args.precision = {"fp64": _lib.BMM_FP64, "fp32": _lib.BMM_FP32}[precision]
     args.device = int(device)
     args.flags = ((_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0) |
-                  (_lib.FLAG_GRID_PATH if grid_path else 0) | (_lib.FLAG_NO_Z_HISTORY if no_z_history else 0))
+                  (_lib.FLAG_GRID_PATH if grid_path else 0) | (_lib.FLAG_NO_Z_HISTORY if no_z_history else 0) |
+                  (_lib.FLAG_NO_TENSOR if no_tensor else 0))
+    if isinstance(X, PackedX):
+        args.flags |= _lib.FLAG_X_PACKED
     args.n_global, args.row_offset = int(n_global), int(row_offset)
     keep = [X, init_pi, init_theta, init_z]
     if replay is not None:
@@ -152,6 +181,9 @@ def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probe
     if "Q_final" in probes and relabel:
         res["Q_final"] = _chain_cm(Cn, (N, K), np.float64)
         out.Q_final = _p(res["Q_final"], C.c_double)
+    if "counts" in probes:
+        res["counts"] = np.zeros((Cn, nsamples, K + K * P), dtype=np.int32)
+        out.counts = _p(res["counts"], C.c_int32)
     status = np.zeros(Cn, dtype=np.int32)
     out.status = _p(status, C.c_int32)
     return res, out, status
@@ -169,7 +201,7 @@ class Plan:
     def __init__(self, sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                  chains=1, seed=0, device=0, precision="fp64", init_pi=None, init_theta=None, init_z=None,
                  compact_z=False, chain_offset=0, probes=(), stable_softmax=False, grid_path=False,
-                 no_z_history=False, n_global=0, row_offset=0):
+                 no_z_history=False, n_global=0, row_offset=0, no_tensor=False):
         self.L = _lib.lib()
         self.X = _as_X(X)
         self.meta = dict(sampler=sampler, Cn=int(chains), N=self.X.shape[0], P=self.X.shape[1], K=int(K),
@@ -178,11 +210,13 @@ class Plan:
         args, init, self._keep = _build_args(sampler, self.X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel,
                                              burnrelabel, False, chains, seed, device, precision, init_pi, init_theta,
                                              init_z, None, compact_z, stable_softmax, chain_offset, grid_path,
-                                             no_z_history, n_global, row_offset)
+                                             no_z_history, n_global, row_offset, no_tensor)
         if "probs" in probes:
             args.flags |= 0x100
         if "loglik" in probes:
             args.flags |= 0x200
+        if "counts" in probes:
+            args.flags |= 0x400
         self.h = C.c_void_p()
         _lib.check(self.L.bmm_plan_create(sampler, C.byref(args), C.byref(init), C.byref(self.h)))
 
@@ -227,14 +261,14 @@ class Plan:
 def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
          chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
          compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
-         grid_path=False, no_z_history=False, n_global=0, row_offset=0):
+         grid_path=False, no_z_history=False, n_global=0, row_offset=0, no_tensor=False):
     L = _lib.lib()
     N, P = X.shape
     Cn = int(chains)
     args, init, keep = _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                                    debug, chains, seed, device, precision, init_pi, init_theta, init_z, replay,
                                    compact_z, stable_softmax, chain_offset, grid_path, no_z_history, n_global,
-                                   row_offset)
+                                   row_offset, no_tensor)
     res, out, status = out_bufs if out_bufs is not None else _alloc_out(
         sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=no_z_history)
     if sampler == _lib.SAMPLER_DP:
@@ -263,7 +297,7 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                initial_pi=None, initial_theta=None, replay=None, compact_z=False, stable_softmax=False,
                probes=(), chain_offset=0, pinned=False, out_bufs=None, grid_path=False, no_z_history=False,
-               n_global=0, row_offset=0, _sampler=None):
+               n_global=0, row_offset=0, no_tensor=False, _sampler=None):
     """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32)."""
     X = _as_X(data)
     N, P = X.shape
@@ -285,7 +319,7 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                 device, precision, init_pi=np.ascontiguousarray(initial_pi), init_theta=np.ascontiguousarray(initial_theta),
                 replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset,
                 pinned=pinned, out_bufs=out_bufs, grid_path=grid_path, no_z_history=no_z_history, n_global=n_global,
-                row_offset=row_offset)
+                row_offset=row_offset, no_tensor=no_tensor)
 
 
 def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None,

@@ -17,6 +17,7 @@
 
 #define BMM_FLAG_PROBE_PROBS 0x100u
 #define BMM_FLAG_PROBE_LOGLIK 0x200u
+#define BMM_FLAG_PROBE_COUNTS 0x400u
 
 namespace bmm {
 bool full_rows_fit_smem(int U, int K);
@@ -76,7 +77,7 @@ struct bmm_plan {
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
-    DevBuf w1, w0, lpi, gsc, counts;
+    DevBuf w1, w0, lpi, gsc, counts, counts_out;
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG;
     // state
@@ -257,11 +258,15 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     if (a.replay && K > bmm::big_replay_max_k()) return fail(BMM_ERR_UNSUPPORTED, "grid-path replay needs K <= 64");
     const long long n_global = a.n_global > 0 ? a.n_global : N;
     if (a.row_offset < 0 || a.row_offset + N > n_global) return fail(BMM_ERR_INVALID, "row_offset + N exceeds n_global");
-    std::vector<uint32_t> bits;
-    int W;
-    TRY(pack_rows(a.X, N, P, bits, W));
+    int W = (P + 31) / 32;
+    if (a.flags & BMM_FLAG_X_PACKED) {
+        TRY(upload(pl->xbits, (const uint32_t *)a.X, (size_t)N * W));
+    } else {
+        std::vector<uint32_t> bits;
+        TRY(pack_rows(a.X, N, P, bits, W));
+        TRY(upload(pl->xbits, bits.data(), bits.size()));
+    }
     pl->W = W; pl->U = N;
-    TRY(upload(pl->xbits, bits.data(), bits.size()));
     const size_t KP = (size_t)K * P;
     TRY(upload(pl->theta_cur, init->theta, KP));
     TRY(upload(pl->pi_cur, init->pi, (size_t)K));
@@ -277,6 +282,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     CU(pl->alpha_out.alloc((size_t)S * 8));
     if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)ns * N * K * 8));
     if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->loglik_out.alloc((size_t)ns * N * K * 8));
+    if (a.flags & BMM_FLAG_PROBE_COUNTS) CU(pl->counts_out.alloc((size_t)ns * (K + KP) * 4));
     if (a.replay) {
         const bmm_replay *r = a.replay;
         TRY(upload(pl->ru, r->u, (size_t)ns * N * r->u_slots));
@@ -300,6 +306,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.zhist = pl->zhist.as<uint8_t>();
     b.theta_out = pl->theta_out.as<double>(); b.pi_out = pl->pi_out.as<double>(); b.alpha_out = pl->alpha_out.as<double>();
     b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
+    b.counts_out = pl->counts_out.as<int>();
     b.ru = pl->ru.as<double>(); b.ru_slots = a.replay ? a.replay->u_slots : 0;
     b.rpi = pl->rpi.as<double>(); b.rtheta = pl->rtheta.as<double>(); b.ralpha = pl->ralpha.as<double>();
     return BMM_OK;
@@ -483,7 +490,7 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
     if (e != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e));
     const bool uncollapsed = sampler == BMM_SAMPLER_FULL || sampler == BMM_SAMPLER_STICKBREAKING;
     if (uncollapsed)
-        pl->grid_path = (args->flags & BMM_FLAG_GRID_PATH) || args->n_global > args->N ||
+        pl->grid_path = (args->flags & (BMM_FLAG_GRID_PATH | BMM_FLAG_X_PACKED)) || args->n_global > args->N ||
                         (pl->C == 1 && (args->N >= 32768 || (size_t)args->K * args->P > 4096));
     if (!rc) rc = pl->grid_path ? create_big(pl, init) : (uncollapsed ? create_full(pl, init) : create_collapsed(pl, init));
     if (!rc) {
@@ -619,6 +626,7 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
             CU(d2h(out->Q_final, pl->Qexp, C * N * K * 8));
         }
     }
+    CU(d2h(out->counts, pl->counts_out, ns * (K + K * P) * 4));
     CU(d2h(out->status, pl->status, C * 4));
     CU(cudaStreamSynchronize(pl->stream));
     std::vector<int> st;
@@ -644,6 +652,7 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     bmm_args a = *args;
     if (out->probs) a.flags |= BMM_FLAG_PROBE_PROBS;
     if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
+    if (out->counts) a.flags |= BMM_FLAG_PROBE_COUNTS;
     bmm_plan *pl = nullptr;
     int rc = bmm_plan_create(sampler, &a, init, &pl);
     if (rc) return rc;

@@ -22,6 +22,8 @@
 // Template parameter R is the type of the probability arithmetic: double follows the reference's
 // operation order exactly (d-ordered log-likelihood sum, exp(log pi + loglh), running normaliser);
 // float is the CUDA-core fast path (BMM_FP32).  The tensor-core path lives in kern_big_tc.cu.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "common.cuh"
 
@@ -195,6 +197,10 @@ __global__ void big_finish_kernel(const BigParams p, const int j) {
     const double alpha_prev = *p.alpha_cur;
     int *next = p.counts + (size_t)((j + 1) & 1) * (K + KP);
     for (int t = tid; t < K + KP; t += blockDim.x) next[t] = 0;
+    if (p.counts_out) {
+        const int *cur = p.counts + (size_t)(j & 1) * (K + KP);
+        for (int t = tid; t < K + KP; t += blockDim.x) p.counts_out[(size_t)j * (K + KP) + t] = cur[t];
+    }
     if (replay) {
         for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.rpi[j + (size_t)ns * k];
         __syncthreads();
@@ -319,6 +325,8 @@ cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st) {
 }
 
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st) {
+    static const bool no_tc = getenv("BMM_NO_TC") != nullptr;  // A/B switch: CUDA-core float path
+    if (!no_tc && !(p.flags & 32u /* BMM_FLAG_NO_TENSOR */) && big_tc_supported(p)) return launch_big_sweep_tc(p, j, sm_count, st);
     long long blocks = ((long long)p.N_local + BIG_THREADS - 1) / BIG_THREADS;
     const int cap = sm_count * 8;
     const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));

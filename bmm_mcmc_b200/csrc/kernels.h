@@ -107,6 +107,7 @@ struct BigParams {
     uint8_t *zhist;
     double *theta_out, *pi_out, *alpha_out;   // [K*P*S], [S*K cm], [S]
     double *probs_out, *loglik_out;   // [nsamples][N_local*K cm] or nullptr
+    int *counts_out;                  // [nsamples][K + K*P] probe or nullptr
     const double *ru; int ru_slots;   // replay
     const double *rpi, *rtheta, *ralpha;
 };
@@ -116,6 +117,9 @@ cudaError_t launch_big_init(const BigParams &p, cudaStream_t st);
 cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st);
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st);
 cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st);
+// tcgen05 sweep (kern_big_tc.cu): log-likelihood and sufficient statistics as tensor-core contractions
+bool big_tc_supported(const BigParams &p);
+cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStream_t st);
 
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,

@@ -35,6 +35,7 @@ extern "C" {
 #define BMM_ERR_NCCL (-7)
 #define BMM_ERR_UNSUPPORTED (-8)     /* shape outside what the kernels cover                       */
 #define BMM_ERR_PROB (-9)            /* non-finite conditional probabilities (reference: NA draw)  */
+#define BMM_ERR_TIMEOUT (-10)        /* a device-side barrier never completed (kernel bug guard)   */
 
 #define BMM_FP64 0
 #define BMM_FP32 1
@@ -46,6 +47,11 @@ extern "C" {
                                         int32: 1 B per allocation over PCIe; K must be <= 255     */
 #define BMM_FLAG_NO_Z_HISTORY 4u     /* keep only the current allocations on the device; out->z is
                                         not written (large-N runs: S x N would not fit anywhere)   */
+#define BMM_FLAG_X_PACKED 16u         /* args->X points at bit-packed rows instead of an IntegerMatrix:
+                                        uint32 [N][ceil(P/32)], bit d%32 of word d/32 = x_id (grid
+                                        path only; 8 B per row at P = 64 instead of 256 B)         */
+#define BMM_FLAG_NO_TENSOR 32u        /* grid path, BMM_FP32: use the CUDA-core float kernel instead of
+                                        the tcgen05 contraction (A/B testing)                      */
 #define BMM_FLAG_GRID_PATH 8u        /* force the one-chain-over-the-whole-GPU kernels (default:
                                         chosen when n_chains <= 1 and N >= 32768, or when K*P is
                                         too large for the chain-per-block kernel)                  */
@@ -112,6 +118,8 @@ typedef struct bmm_out {
     double *loglik;          /* [chain][nsamples][N x K cm] Bernoulli log-likelihood (full / SB)   */
     double *Q_final;         /* [chain][N x K cm] running Stephens Q after the last sweep          */
     int32_t *status;         /* [chain] 0 or a BMM_ERR_* raised inside that chain                  */
+    int32_t *counts;         /* grid path probe: [nsamples][K + K*P] sufficient statistics of every
+                                sweep, c_k then V_kd (k + K*d) (full_gibbs.cpp:182-200)             */
 } bmm_out;
 
 /* ---- samplers: replace the four sampler .Call symbols ---------------------------------------- */

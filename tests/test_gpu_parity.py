@@ -338,3 +338,50 @@ def test_grid_path_large_synthetic():
     assert h["z"].shape == (11, N)
     # first sweep uses identical parameters: fp32 and fp64 allocations agree except at ulp-close draws
     assert (g["z"][0] != h["z"][0]).mean() < 1e-3
+
+
+# ---- tcgen05 sweep of the grid path (kern_big_tc.cu) ----------------------------------------------
+def _host_counts(z, X, K):
+    """[S][K + K*P]: c_k then V_kd (k + K*d) from an S x N allocation history."""
+    S, P = z.shape[0], X.shape[1]
+    out = np.zeros((S, K + K * P), dtype=np.int64)
+    for s in range(S):
+        oh = (z[s][:, None] == np.arange(1, K + 1)[None, :]).astype(np.int64)   # N x K
+        out[s, :K] = oh.sum(0)
+        out[s, K:] = (oh.T @ X).T.reshape(-1)                                   # (P, K) -> d-major
+    return out
+
+
+def test_grid_tensor_path_small(oracle, datasets):
+    """tcgen05 log-likelihood contraction vs the fp64 oracle (1e-4 relative on the conditional
+    probabilities) and tcgen05 sufficient statistics vs counts recomputed from the returned z (exact)."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    N, P = X.shape
+    K, ns = 3, 7
+    ip, th = _init_full(K, P, 5)
+    r = oracle.gibbs_full(X, ip, th, 2, K, burnin=0, seed=11)
+    g = B.gibbs_full(X, ns, K, burnin=1, initial_pi=ip, initial_theta=th, seed=3, probes=("probs", "counts"),
+                     grid_path=True, precision="fp32")
+    _close(g["probs"][1], r["probs"][1], rtol=1e-4, atol=1e-30)
+    assert np.array_equal(g["counts"][1:], _host_counts(g["z"], X, K))
+    h = B.gibbs_full(X, ns, K, burnin=1, initial_pi=ip, initial_theta=th, seed=3, grid_path=True)   # fp64, same Philox
+    assert (g["z"][0] != h["z"][0]).mean() < 2e-3
+
+
+def test_grid_tensor_path_c4_shape():
+    """C4 shape (P=64, K=32) with a ragged last tile: tensor-core path vs the CUDA-core float kernel."""
+    _need_gpu()
+    rng = np.random.default_rng(5)
+    N, P, K = 50_000 + 37, 64, 32
+    th_true = rng.uniform(0.1, 0.9, (K, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, K, N)]).astype(np.int32)
+    kw = dict(alpha=1.0, burnin=1, seed=9, precision="fp32", probes=("probs", "counts"))
+    g = B.gibbs_stickbreaking(X, 5, K, **kw)
+    c = B.gibbs_stickbreaking(X, 5, K, no_tensor=True, **kw)
+    assert np.array_equal(g["counts"][1:], _host_counts(g["z"], X, K))
+    assert np.array_equal(c["counts"][1:], _host_counts(c["z"], X, K))
+    big = c["probs"][1] > 1e-12
+    _close(g["probs"][1][big], c["probs"][1][big], rtol=2e-4)
+    assert (g["z"][0] != c["z"][0]).mean() < 2e-3
+    assert np.allclose(g["pi"].sum(1), 1.0) and np.isfinite(g["theta"]).all()
