@@ -1,0 +1,72 @@
+"""Multi-GPU checks (need >= 2 CUDA devices; run with `gpurun --gpus 2`):
+N-sharded grid path == unsharded chain, bit for bit; chain split across ranks == single-rank run."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        from bmm_mcmc_b200 import _lib
+        return _lib.lib().bmm_device_count()
+    except Exception:
+        return 0
+
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.environ["BMM_ROOT"])
+import torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+import bmm_mcmc_b200 as B
+from bmm_mcmc_b200 import dist as bdist
+bdist.init(rank, world, rank)
+rng = np.random.default_rng(3)
+N, P, K = 40_001, 64, 16
+th = rng.uniform(0.1, 0.9, (K, P))
+X = (rng.random((N, P)) < th[rng.integers(0, K, N)]).astype(np.int32)
+lo, hi = bdist.shard_rows(N, world, rank)
+out = {}
+for prec in ("fp64", "fp32"):
+    g = B.gibbs_stickbreaking(X[lo:hi], 8, K, alpha=1.0, burnin=1, seed=5, device=rank, precision=prec,
+                              grid_path=True, n_global=N, row_offset=lo, probes=("counts",))
+    out[prec] = g
+np.savez(os.path.join(os.environ["BMM_OUT"], "rank%d.npz" % rank), lo=lo, hi=hi,
+         **{p + "_" + k: v for p, g in out.items() for k, v in g.items()})
+bdist.finalize()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_n_sharded_equals_unsharded(tmp_path):
+    import bmm_mcmc_b200 as B
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, BMM_ROOT=ROOT, BMM_OUT=str(tmp_path))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                    "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], check=True, env=env,
+                   timeout=300)
+    r = [np.load(tmp_path / ("rank%d.npz" % i)) for i in range(2)]
+    rng = np.random.default_rng(3)
+    N, P, K = 40_001, 64, 16
+    th = rng.uniform(0.1, 0.9, (K, P))
+    X = (rng.random((N, P)) < th[rng.integers(0, K, N)]).astype(np.int32)
+    for prec in ("fp64", "fp32"):
+        g = B.gibbs_stickbreaking(X, 8, K, alpha=1.0, burnin=1, seed=5, precision=prec, grid_path=True, probes=("counts",))
+        z = np.concatenate([r[0][prec + "_z"], r[1][prec + "_z"]], axis=1)
+        assert np.array_equal(z, g["z"]), prec
+        for k in ("theta", "pi", "alpha", "counts"):
+            assert np.array_equal(r[0][prec + "_" + k], g[k]) and np.array_equal(r[1][prec + "_" + k], g[k]), (prec, k)
