@@ -77,7 +77,7 @@ struct bmm_plan {
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
-    DevBuf w1, w0, lpi, gsc, counts, counts_out;
+    DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG;
     // state
@@ -307,6 +307,12 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.theta_out = pl->theta_out.as<double>(); b.pi_out = pl->pi_out.as<double>(); b.alpha_out = pl->alpha_out.as<double>();
     b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
     b.counts_out = pl->counts_out.as<int>();
+    if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && P % 64 == 0 && (K > 32 || P > 112)) {
+        CU(pl->lp_table.alloc(bmm::big_lp_table_bytes(P)));
+        CU(pl->lp_bias.alloc(128 * 8));
+        if (!pl->zhist.p) return fail(BMM_ERR_INVALID, "internal: allocation buffer missing");
+    }
+    b.lp_table = pl->lp_table.p; b.lp_bias = pl->lp_bias.as<double>();
     b.ru = pl->ru.as<double>(); b.ru_slots = a.replay ? a.replay->u_slots : 0;
     b.rpi = pl->rpi.as<double>(); b.rtheta = pl->rtheta.as<double>(); b.ralpha = pl->ralpha.as<double>();
     return BMM_OK;

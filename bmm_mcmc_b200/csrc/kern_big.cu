@@ -326,7 +326,10 @@ cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st) {
 
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     static const bool no_tc = getenv("BMM_NO_TC") != nullptr;  // A/B switch: CUDA-core float path
-    if (!no_tc && !(p.flags & 32u /* BMM_FLAG_NO_TENSOR */) && big_tc_supported(p)) return launch_big_sweep_tc(p, j, sm_count, st);
+    if (!no_tc && !(p.flags & 32u /* BMM_FLAG_NO_TENSOR */)) {
+        if (big_tc_supported(p)) return launch_big_sweep_tc(p, j, sm_count, st);
+        if (big_lp_supported(p)) return launch_big_sweep_lp(p, j, sm_count, st);
+    }
     long long blocks = ((long long)p.N_local + BIG_THREADS - 1) / BIG_THREADS;
     const int cap = sm_count * 8;
     const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));

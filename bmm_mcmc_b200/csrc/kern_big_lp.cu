@@ -1,0 +1,391 @@
+// Large-P / large-K tensor-core path of the grid sampler (BASELINE config C5: N = 1e6, P = 4096,
+// K = 128).  Same algebra as kern_big_tc.cu -- loglh = X D^T + b on tcgen05 with D split into three
+// bf16 terms, sufficient statistics as [X]^T onehot(z) -- but P no longer fits one shared-memory tile,
+// so the contraction runs as a pipelined k-loop and the statistics as a second kernel:
+//
+//   lp_table_kernel    per sweep: D (log2 units) split hi|mid|lo, written to global memory already in
+//                      the shared-memory operand image ([64-feature step][16-B chunk][3*128 rows][16 B]),
+//                      so a stage is one contiguous 48 KB block.
+//   lp_sweep_kernel    persistent, one 128-observation tile at a time per CTA, 2-stage mbarrier pipeline:
+//                        warps 0-3  expand 64 bits per observation and step into the bf16 A stage, later
+//                                   run the epilogue (one observation per thread = one TMEM lane);
+//                        warp 4     one thread streams the B stage with cp.async.bulk (mbarrier tx count);
+//                        warp 5     one thread issues 8 tcgen05.mma (M128 N192 K16) per step into a
+//                                   128 x 384 fp32 accumulator and commits stage-empty / accumulator-full.
+//                      Epilogue: three passes over TMEM (max, sum, inverse-CDF walk) because 128 logits
+//                      do not fit the register file; 1-byte allocation to HBM.
+//   lp_counts_kernel   V_kd = [X]^T onehot(z): CTA (feature group of 256, observation split), the
+//                      MN-major operand layout of kern_big_tc.cu, two 128 x 128 accumulators in TMEM,
+//                      exact integer counts flushed with atomics; c_k as a shared-memory histogram.
+//
+// Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186) at sizes
+// where the reference itself cannot run (its unstabilised exp underflows at P = 4096, full_gibbs.cpp:106).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace bmm {
+namespace {
+
+constexpr int LP_KC = 128;                  // clusters, padded
+constexpr int LP_NCOL = 3 * LP_KC;          // accumulator columns: hi | mid | lo
+constexpr int LP_DK = 64;                   // features per pipeline step
+constexpr int LP_A_STAGE = 8 * 2048;        // [8 chunks][128 rows][16 B]
+constexpr int LP_B_STAGE = 8 * LP_NCOL * 16;  // [8 chunks][384 rows][16 B]
+constexpr int LP_STAGE = LP_A_STAGE + LP_B_STAGE;
+constexpr int LP_THREADS = 192;
+constexpr double LOG2E_D = 1.4426950408889634;
+
+// ---- per-sweep tables -----------------------------------------------------------------------------
+// The conditional probabilities only depend on differences between clusters, so both D_kd and b_k
+// are centred over k (exact in double) before they are rounded: the fp32 accumulator then carries a
+// zero-mean random walk of magnitude ~sqrt(P) instead of a drift of magnitude ~P, which is what keeps
+// the probabilities within 1e-4 of fp64 at P = 4096.
+__global__ void lp_table_kernel(const BigParams p) {
+    const int K = p.K, P = p.P;
+    unsigned char *img = (unsigned char *)p.lp_table;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P; d += gridDim.x * blockDim.x) {
+        const double *w1 = p.w1 + (size_t)K * d, *w0 = p.w0 + (size_t)K * d;
+        double mean = 0.0;
+        for (int k = 0; k < K; ++k) mean += w1[k] - w0[k];
+        mean /= K;
+        unsigned char *col = img + (size_t)(d >> 3) * LP_NCOL * 16 + (d & 7) * 2;
+        for (int k = 0; k < LP_KC; ++k) {
+            const double D = k < K ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
+            const __nv_bfloat16 hi = __double2bfloat16(D);
+            const double r1 = D - (double)__bfloat162float(hi);
+            const __nv_bfloat16 mid = __double2bfloat16(r1);
+            const __nv_bfloat16 lo = __double2bfloat16(r1 - (double)__bfloat162float(mid));
+            *(__nv_bfloat16 *)(col + (0 * LP_KC + k) * 16) = hi;
+            *(__nv_bfloat16 *)(col + (1 * LP_KC + k) * 16) = mid;
+            *(__nv_bfloat16 *)(col + (2 * LP_KC + k) * 16) = lo;
+        }
+    }
+}
+
+// b_k = log2(e) * (log pi_k + sum_d log(1 - theta_kd)) in double; centred and rounded by the sweep kernel
+__global__ void lp_bias_kernel(const BigParams p) {
+    __shared__ double red[4];
+    const int k = blockIdx.x, K = p.K, P = p.P;
+    double s = 0.0;
+    if (k < K) for (int d = threadIdx.x; d < P; d += blockDim.x) s += p.w0[k + (size_t)K * d];
+    s = warp_sum_xor(s, 32);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) p.lp_bias[k] = k < K ? (p.lpi[k] + red[0] + red[1] + red[2] + red[3]) * LOG2E_D : 0.0;
+}
+
+// ---- the sweep ------------------------------------------------------------------------------------
+struct LpSmem {
+    static constexpr int BIAS_OFF = LP_STAGE * 2;
+    static constexpr int BAR_OFF = BIAS_OFF + LP_KC * 4;
+    static constexpr int TOTAL = BAR_OFF + 8 * 8 + 16;
+};
+
+// logits of 32 clusters [c0, c0+32) of this thread's observation: hi + mid + lo + bias
+__device__ __forceinline__ void lp_logits32(uint32_t acc, uint32_t lane_sel, int c0, const float *bias, float (&l)[32]) {
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+        uint32_t v[32];
+        tmem_ld32(acc + lane_sel + (uint32_t)(part * LP_KC + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) l[q] = part == 0 ? __uint_as_float(v[q]) + bias[c0 + q] : l[q] + __uint_as_float(v[q]);
+    }
+}
+
+__global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams p, const int j) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = p.K, W = p.W;
+    const int nsteps = p.P / LP_DK;
+    float *bias = (float *)(smem + LpSmem::BIAS_OFF);
+    uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[2], empty[2], accfull, accempty
+    uint32_t *tmem_slot = (uint32_t *)(bars + 6);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+    const uint32_t accfull = smem_u32(&bars[4]), accempty = smem_u32(&bars[5]);
+
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 160) {
+        mbar_init(full0, 129); mbar_init(full0 + 8, 129);      // 128 row threads + the bulk-copy thread
+        mbar_init(empty0, 1); mbar_init(empty0 + 8, 1);        // tcgen05.commit
+        mbar_init(accfull, 1); mbar_init(accempty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        double mean = 0.0;
+        for (int k = 0; k < K; ++k) mean += p.lp_bias[k];
+        mean /= K;
+        for (int k = tid; k < LP_KC; k += LP_THREADS) bias[k] = k < K ? (float)(p.lp_bias[k] - mean) : -INFINITY;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t acc = *tmem_slot;
+    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    bool ok = true;
+    long long g = 0;       // pipeline step counter of this CTA (all roles advance it identically)
+    int tile_it = 0;
+
+    if (warp < 4) {
+        // ================= A producers, then epilogue =================
+        const int t = tid;
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
+        const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+        uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
+            const long long i = tile * 128 + t;
+            const bool valid = i < p.N_local;
+            const uint32_t *xb = p.xbits + (size_t)(valid ? i : 0) * W;
+            uint2 nxt = valid ? *(const uint2 *)xb : make_uint2(0u, 0u);
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const uint2 cur = nxt;
+                if (c + 1 < nsteps && valid) nxt = *(const uint2 *)(xb + 2 * (c + 1));
+                uint4 ex[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint32_t byte = (ch < 4 ? cur.x : cur.y) >> ((ch & 3) * 8);
+                    ex[ch] = make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
+                }
+                const int s = (int)(g & 1);
+                const long long n = g >> 1;
+                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+                if (!ok) break;
+                unsigned char *A = smem + s * LP_STAGE;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) *(uint4 *)(A + ch * 2048 + t * 16) = ex[ch];
+                fence_async_smem();
+                mbar_arrive(full0 + 8 * s);
+            }
+            if (!ok) break;
+            // ---- epilogue: this thread's observation = TMEM lane t ----
+            const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
+            const float u = ((float)(((gi & 1) ? rnd.z : rnd.x) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+            ok = mbar_wait(accfull, (uint32_t)(tile_it & 1));
+            if (!ok) break;
+            tc_fence_after();
+            float l[32];
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < LP_KC; c0 += 32) {
+                lp_logits32(acc, lane_sel, c0, bias, l);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) mx = fmaxf(mx, l[q]);
+            }
+            float sum = 0.f;
+            for (int c0 = 0; c0 < LP_KC; c0 += 32) {
+                lp_logits32(acc, lane_sel, c0, bias, l);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) sum += ex2_ftz(l[q] - mx);
+            }
+            if (!(sum > 0.f) || !isfinite(sum)) *p.status = -9;  // BMM_ERR_PROB
+            const float target = u * sum, inv = 1.f / sum;
+            float run = 0.f;
+            int z = 0;
+            for (int c0 = 0; c0 < LP_KC; c0 += 32) {
+                lp_logits32(acc, lane_sel, c0, bias, l);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float e = ex2_ftz(l[q] - mx);
+                    run += e;
+                    z += (run <= target) ? 1 : 0;
+                    if (p.probs_out && valid && c0 + q < K)
+                        p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * (c0 + q)] = (double)(e * inv);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(accempty);             // the accumulator may be overwritten by the next tile
+            z = min(z, K - 1);
+            if (valid) zrow[i] = (uint8_t)(z + 1);
+        }
+    } else if (warp == 4) {
+      if (tid == 128) {
+        // ================= B stage streamer =================
+        const unsigned char *img = (const unsigned char *)p.lp_table;
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x)
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const int s = (int)(g & 1);
+                const long long n = g >> 1;
+                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+                if (!ok) break;
+                const uint32_t dst = smem_u32(smem + s * LP_STAGE + LP_A_STAGE);
+                mbar_arrive_expect_tx(full0 + 8 * s, LP_B_STAGE);
+                bulk_g2s(dst, img + (size_t)c * LP_B_STAGE, LP_B_STAGE, full0 + 8 * s);
+            }
+      }
+      __syncwarp();
+    } else {
+      if (tid == 160) {
+        // ================= MMA issuer =================
+        constexpr uint32_t IDESC = umma_idesc(128, LP_NCOL / 2, 0, 0);
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
+            if (tile_it > 0) ok = mbar_wait(accempty, (uint32_t)((tile_it - 1) & 1));
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const int s = (int)(g & 1);
+                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g >> 1) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        umma_bf16(acc + (uint32_t)(h * (LP_NCOL / 2)), umma_desc(a0 + kk * 2 * 2048, 2048, 128),
+                                  umma_desc(b0 + kk * 2 * (LP_NCOL * 16) + h * (LP_NCOL / 2) * 16, LP_NCOL * 16, 128),
+                                  IDESC, (c | kk) ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);
+                if (c == nsteps - 1) umma_commit(accfull);
+            }
+        }
+      }
+      __syncwarp();
+    }
+    if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(acc), "r"(512) : "memory");
+    }
+}
+
+// ---- sufficient statistics ------------------------------------------------------------------------
+constexpr int LC_DG = 256;                          // features per CTA
+constexpr int LC_A_HALF = 16 * 2048;                // [16 chunks][128 obs][16 B] = 128 features
+constexpr int LC_B2 = (LP_KC / 8) * 2048;           // one-hot [16 chunks][128 obs][16 B]
+constexpr int LC_SMEM = 2 * LC_A_HALF + LC_B2 + 64;
+
+__global__ void __launch_bounds__(128, 2) lp_counts_kernel(const BigParams p, const int j, const int nsplit) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int hist[LP_KC];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int K = p.K, P = p.P, W = p.W;
+    const int dg = blockIdx.x / nsplit, sp = blockIdx.x % nsplit;
+    unsigned char *A = smem, *B2 = smem + 2 * LC_A_HALF;
+    uint64_t *bar = (uint64_t *)(smem + 2 * LC_A_HALF + LC_B2);
+    const uint32_t bar_a = smem_u32(bar);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (t == 32) { mbar_init(bar_a, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    hist[t] = 0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t acc = tmem_slot, lane_sel = (uint32_t)(warp * 32) << 16;
+    constexpr uint32_t IDESC = umma_idesc(128, LP_KC, 1, 1);
+    const uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
+    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    const int w0 = dg * (LC_DG / 32);                // first 32-bit word of this feature group
+    bool ok = true;
+    int it = 0;
+    for (long long tile = sp; tile < ntiles && ok; tile += nsplit, ++it) {
+        const long long i = tile * 128 + t;
+        const bool valid = i < p.N_local;
+        uint32_t xw[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) xw[w] = (valid && w0 + w < W) ? p.xbits[(size_t)i * W + w0 + w] : 0u;
+        const int z = valid ? (int)zrow[i] - 1 : -1;
+        if (it > 0) ok = mbar_wait(bar_a, (uint32_t)((it - 1) & 1));
+        if (!ok) break;
+#pragma unroll
+        for (int ch = 0; ch < 32; ++ch) {
+            const uint32_t byte = xw[ch >> 2] >> ((ch & 3) * 8);
+            *(uint4 *)(A + (ch >> 4) * LC_A_HALF + (ch & 15) * 2048 + t * 16) =
+                make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
+        }
+        {
+            const uint32_t h = z >= 0 ? ((z & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+            const int wsel = (z & 7) >> 1, csel = z >> 3;
+            const uint4 hot = make_uint4(wsel == 0 ? h : 0u, wsel == 1 ? h : 0u, wsel == 2 ? h : 0u, wsel == 3 ? h : 0u);
+#pragma unroll
+            for (int cc = 0; cc < LP_KC / 8; ++cc)
+                *(uint4 *)(B2 + cc * 2048 + t * 16) = (csel == cc) ? hot : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (dg == 0 && z >= 0) atomicAdd(&hist[z], 1);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(A), b0 = smem_u32(B2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(acc + (uint32_t)(h * LP_KC), umma_desc(a0 + h * LC_A_HALF + kk * 256, 128, 2048),
+                              umma_desc(b0 + kk * 256, 128, 2048), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar_a);
+        }
+    }
+    if (ok && it > 0) ok = mbar_wait(bar_a, (uint32_t)((it - 1) & 1));
+    if (!ok) *p.status = -10;
+    int *gcnt = p.counts + (size_t)(j & 1) * (K + (size_t)K * P);
+    if (ok && it > 0) {
+        tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+            const int d = dg * LC_DG + h * 128 + t;
+            for (int c0 = 0; c0 < LP_KC; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(acc + lane_sel + (uint32_t)(h * LP_KC + c0), v);
+                tmem_ld_wait();
+                if (d < P) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = c0 + q, n = (int)(__uint_as_float(v[q]) + 0.5f);
+                        if (k < K && n) atomicAdd(&gcnt[K + k + (size_t)K * d], n);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (dg == 0 && t < K && hist[t]) atomicAdd(&gcnt[t], hist[t]);
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(acc), "r"(256) : "memory");
+    }
+}
+
+}  // namespace
+
+// float path, K <= 128 clusters, P a multiple of 64 (packed rows then are 8-byte aligned per step)
+bool big_lp_supported(const BigParams &p) {
+    return p.precision == 1 && p.K <= LP_KC && p.P % LP_DK == 0 && p.P >= LP_DK && p.ru == nullptr &&
+           p.loglik_out == nullptr && p.lp_table != nullptr;
+}
+
+size_t big_lp_table_bytes(int P) { return (size_t)P / 8 * LP_NCOL * 16; }
+
+cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LpSmem::TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lp_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    lp_table_kernel<<<(p.P + 63) / 64, 64, 0, st>>>(p);
+    lp_bias_kernel<<<LP_KC, 128, 0, st>>>(p);
+    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    const int ctas = (int)(ntiles < sm_count ? ntiles : sm_count);
+    lp_sweep_kernel<<<ctas, LP_THREADS, LpSmem::TOTAL, st>>>(p, j);
+    const int ndg = (p.P + LC_DG - 1) / LC_DG;
+    int nsplit = (2 * sm_count + ndg - 1) / ndg;
+    if (nsplit > ntiles) nsplit = (int)ntiles;
+    if (nsplit < 1) nsplit = 1;
+    lp_counts_kernel<<<ndg * nsplit, 128, LC_SMEM, st>>>(p, j, nsplit);
+    g_launches += 4;
+    return cudaGetLastError();
+}
+
+}  // namespace bmm

@@ -108,6 +108,8 @@ struct BigParams {
     double *theta_out, *pi_out, *alpha_out;   // [K*P*S], [S*K cm], [S]
     double *probs_out, *loglik_out;   // [nsamples][N_local*K cm] or nullptr
     int *counts_out;                  // [nsamples][K + K*P] probe or nullptr
+    void *lp_table;                   // large-P tensor path: split weight table in operand-image order
+    double *lp_bias;                  // [128] uncentred b_k
     const double *ru; int ru_slots;   // replay
     const double *rpi, *rtheta, *ralpha;
 };
@@ -120,6 +122,10 @@ cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st);
 // tcgen05 sweep (kern_big_tc.cu): log-likelihood and sufficient statistics as tensor-core contractions
 bool big_tc_supported(const BigParams &p);
 cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStream_t st);
+// large-P / large-K tcgen05 path (kern_big_lp.cu): pipelined k-loop contraction + counts kernel
+bool big_lp_supported(const BigParams &p);
+size_t big_lp_table_bytes(int P);
+cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st);
 
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,

@@ -385,3 +385,24 @@ def test_grid_tensor_path_c4_shape():
     _close(g["probs"][1][big], c["probs"][1][big], rtol=2e-4)
     assert (g["z"][0] != c["z"][0]).mean() < 2e-3
     assert np.allclose(g["pi"].sum(1), 1.0) and np.isfinite(g["theta"]).all()
+
+
+def test_grid_large_p_tensor_path():
+    """Large-P / large-K tcgen05 path (kern_big_lp.cu) vs the CUDA-core fp64 grid kernel with the
+    stabilised softmax (the reference's own exp underflows at this P): probabilities within 1e-4,
+    counts exact, allocations equal except at ulp-close draws."""
+    _need_gpu()
+    rng = np.random.default_rng(11)
+    N, P, K = 3000 + 77, 512, 100
+    th_true = rng.uniform(0.2, 0.8, (K, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, K, N)]).astype(np.int32)
+    ip = np.full(K, 1.0 / K)
+    th0 = rng.uniform(0.3, 0.7, (K, P))
+    kw = dict(alpha=1.0, burnin=1, seed=4, initial_pi=ip, initial_theta=th0, probes=("probs", "counts"), grid_path=True)
+    g = B.gibbs_full(X, 4, K, precision="fp32", **kw)
+    c = B.gibbs_full(X, 4, K, precision="fp64", stable_softmax=True, **kw)
+    assert np.array_equal(g["counts"][1:], _host_counts(g["z"], X, K))
+    big = c["probs"][1] > 1e-9
+    _close(g["probs"][1][big], c["probs"][1][big], rtol=1e-4)
+    assert (g["z"][0] != c["z"][0]).mean() < 5e-3
+    assert np.allclose(g["pi"].sum(1), 1.0) and np.isfinite(g["theta"]).all()
