@@ -211,17 +211,26 @@ GRID_WORKLOADS = {
     "c4": dict(sampler="stickbreaking", N=10_000_000, P=64, K=32, nsamples=101, burnin=11, alpha=1.0,
                precision="fp32", cpu_N=60_000, cpu_ns=6,
                label="C4: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1"),
+    # BASELINE.json configs[4] (relabelling on the grid path is not built yet: relabel=FALSE here)
+    "c5": dict(sampler="full", N=1_000_000, P=4096, K=128, nsamples=21, burnin=3, alpha=1.0,
+               precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
+               label="C5: gibbs_full synthetic N=1e6 P=4096 K=128 (large-P tcgen05 contraction)"),
+    "c5small": dict(sampler="full", N=100_000, P=4096, K=128, nsamples=9, burnin=2, alpha=1.0,
+                    precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
+                    label="C5 shape at N=1e5 (smoke size)"),
     "c4small": dict(sampler="stickbreaking", N=1_000_000, P=64, K=32, nsamples=21, burnin=3, alpha=1.0,
                     precision="fp32", cpu_N=20_000, cpu_ns=4,
                     label="C4 shape at N=1e6 (smoke size)"),
 }
 
 
-def synth_rows(lo, hi, P, K_true, seed=17, chunk=500_000):
+def synth_rows(lo, hi, P, K_true, seed=17, chunk=None):
     """Rows [lo, hi) of the synthetic data set: pi* uniform, theta* ~ U(0.1, 0.9),
     x_id ~ Bernoulli(theta*[z*_i, d]); generated chunk by chunk so any shard sees the same rows."""
     from bmm_mcmc_b200 import PackedX
+    chunk = chunk or (500_000 if P <= 64 else 16_384)
     th = np.random.default_rng([seed, 0]).uniform(0.1, 0.9, (K_true, P)).astype(np.float32)
+    thq = np.clip(np.round(th * 256.0), 1, 255).astype(np.uint8)      # large P: 8-bit thresholds, 1 B of randomness per bit
     W = (P + 31) // 32
     out = np.zeros((hi - lo, W), dtype=np.uint32)
     c0 = lo // chunk
@@ -229,7 +238,10 @@ def synth_rows(lo, hi, P, K_true, seed=17, chunk=500_000):
         a0, a1 = c0 * chunk, (c0 + 1) * chunk
         rng = np.random.default_rng([seed, 1 + c0])
         z = rng.integers(0, K_true, chunk)
-        x = rng.random((chunk, P), dtype=np.float32) < th[z]
+        if P <= 64:
+            x = rng.random((chunk, P), dtype=np.float32) < th[z]
+        else:
+            x = rng.integers(0, 256, (chunk, P), dtype=np.uint8) < thq[z]
         s0, s1 = max(a0, lo), min(a1, hi)
         out[s0 - lo:s1 - lo] = PackedX.pack(x[s0 - a0:s1 - a0]).bits
         c0 += 1
@@ -252,7 +264,7 @@ def grid_cpu_baseline(w):
     ip, th = grid_init(K, P)
     f = O.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else O.gibbs_full
     t0 = time.perf_counter()
-    f(Xi, ip[0], th[0].T, ns, K, alpha=w["alpha"], burnin=1, seed=3, probes=False)
+    f(Xi, ip[0], th[0].T, ns, K, alpha=w["alpha"], burnin=1, seed=3, probes=False, **({"stabilise": True} if w.get("stabilise") else {}))
     sec = time.perf_counter() - t0
     return {"value": N * (ns - 1) / sec, "unit": "allocation updates/s", "cores": 1, "kind": "port",
             "sample": "%s reduced to N=%d, %d sweeps (the reference's N x K x nsamples double cube cannot hold N=%g; "
@@ -316,6 +328,7 @@ def run_grid(a):
     X = synth_rows(lo, hi, P, K)
     ip, th = grid_init(K, P)
     sid = _lib.SAMPLER_STICKBREAKING if w["sampler"] == "stickbreaking" else _lib.SAMPLER_FULL
+    kname = "big_sweep_tc_kernel" if (K <= 32 and P <= 112) else "lp_table+lp_sweep+lp_counts kernels"
     shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
     kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=False, burnrelabel=0)
 
@@ -374,6 +387,18 @@ def run_grid(a):
     bytes_per_update = (P + 7) // 8 + 1
     dur_s = kern[0] / a.steps / (ns - 1) / 1e3
     achieved = n_local * bytes_per_update / dur_s / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+            "kernel": "%s (%d rows, %d B/update)" % (kname, n_local, bytes_per_update),
+            "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))}
+    if 2 * K * P / bytes_per_update > 1e3 * pk["bf16_tflops_sustained"] / pk["hbm_gbs"]:
+        # arithmetic intensity above the ridge (C5: 2044 flop/B vs 216): the tensor pipe bounds it
+        flops = 2.0 * K * P * n_local          # algorithmic: one K x P contraction per update
+        tf = flops / dur_s / 1e12
+        roof.update(bound="tensor", achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=tf / pk["bf16_tflops_sustained"],
+                    kernel="%s (%d rows, %d algorithmic flop/update; issued flops are 4x: 3-term bf16 split + counts GEMM)"
+                           % (kname, n_local, 2 * K * P))
     line = {
         "metric": METRIC, "value": total_updates / tm[0], "unit": "allocation updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tm[0] / a.steps, "higher_is_better": True,
@@ -391,10 +416,7 @@ def run_grid(a):
                 "api": "bmm_mcmc_b200.gibbs_%s(PackedX, ...) -> bmm_gibbs_%s (C ABI), pinned host output buffers"
                        % (w["sampler"], w["sampler"])},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
-                     "kernel": "big_sweep_kernel (%d rows, %d B/update)" % (n_local, bytes_per_update),
-                     "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))},
+        "roofline": roof,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,
                   "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "params_and_allreduce": kern[1] / a.steps,
                                  "finalize_layout": kern[3] / a.steps}},

@@ -79,7 +79,7 @@ struct bmm_plan {
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
     // data
-    DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG;
+    DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
     // state
     DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status;
     DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws;
@@ -353,8 +353,12 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     TRY(pack_rows(a.X, N, P, bits, W));
     pl->W = W; pl->U = N;
     TRY(upload(pl->xbits, bits.data(), bits.size()));
-    std::vector<double> lB(N + 1), lG(N + 1), lBG(N + 1);
-    for (int n = 0; n <= N; ++n) { lB[n] = std::log(a.beta + n); lG[n] = std::log(a.gamma + n); lBG[n] = std::log(a.beta + a.gamma + n); }
+    std::vector<double> lB(N + 1), lG(N + 1), lBG(N + 1), lN(N + 1);
+    for (int n = 0; n <= N; ++n) {
+        lB[n] = std::log(a.beta + n); lG[n] = std::log(a.gamma + n); lBG[n] = std::log(a.beta + a.gamma + n);
+        lN[n] = std::log((double)n);
+    }
+    TRY(upload(pl->logN, lN.data(), lN.size()));
     TRY(upload(pl->logB, lB.data(), lB.size()));
     TRY(upload(pl->logG, lG.data(), lG.size()));
     TRY(upload(pl->logBG, lBG.data(), lBG.size()));
@@ -417,6 +421,7 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     q.seed = a.seed; q.chain_offset = a.chain_offset; q.flags = a.flags;
     q.xbits = pl->xbits.as<uint32_t>();
     q.logB = pl->logB.as<double>(); q.logG = pl->logG.as<double>(); q.logBG = pl->logBG.as<double>();
+    q.logN = pl->logN.as<double>();
     q.z_cur = pl->z_cur.as<uint8_t>(); q.cnt = pl->cnt.as<int>(); q.alpha_cur = pl->alpha_cur.as<double>();
     q.dp_used = pl->dp_used.as<int>(); q.dp_free = pl->dp_free.as<uint8_t>();
     q.Q = pl->Q.as<double>(); q.logQ = pl->logQ.as<double>(); q.probs_sample = pl->probs_sample.as<double>();

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
                 if (pos < Kvar) {
                     label = s.used[pos];
                     const int Nk = s.cnt[label * P1 + P];
-                    const double LHS = log((double)Nk) - left_denom;   // (:145)
+                    const double LHS = __ldg(&p.logN[Nk]) - left_denom;   // log N_k (:145)
                     const double denom = __ldg(&p.logBG[Nk]);
                     double logLH = 0.0;
                     for (int d = 0; d < P; ++d) {
@@ -350,40 +350,62 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
                         if (p.probs_out) p.probs_out[((size_t)c * ns + j) * NK + i + (size_t)N * lab[sl]] = pn[sl];
                     }
             }
-            // RcppArmadillo::sample(choices, 1, false, probs_norm): renormalise, walk in descending order
-            double tot2 = 0.0;
+            unsigned best = 0xffffffffu;  // (rank << 8) | pos of the first entry of the walk with rT <= mass
+            if (replay) {
+                // RcppArmadillo::sample(choices, 1, false, probs_norm): renormalise, walk in descending
+                // order (collapsed_gibbs_dp.cpp:207) -- reproduced exactly so a recorded uniform picks the
+                // same label as in the reference
+                double tot2 = 0.0;
 #pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl) tot2 += pn[sl];
-            tot2 = warp_sum_all(tot2);
-            double q[SLOTS], mass[SLOTS];
-            int rank[SLOTS];
+                for (int sl = 0; sl < SLOTS; ++sl) tot2 += pn[sl];
+                tot2 = warp_sum_all(tot2);
+                double q[SLOTS], mass[SLOTS];
+                int rank[SLOTS];
 #pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl) { q[sl] = pn[sl] / tot2; mass[sl] = 0.0; rank[sl] = 0; }
-            for (int src = 0; src < n_ent; ++src) {
-                double qs = 0.0;
+                for (int sl = 0; sl < SLOTS; ++sl) { q[sl] = pn[sl] / tot2; mass[sl] = 0.0; rank[sl] = 0; }
+                for (int src = 0; src < n_ent; ++src) {
+                    double qs = 0.0;
 #pragma unroll
-                for (int sl = 0; sl < SLOTS; ++sl) { double t = __shfl_sync(0xffffffffu, q[sl], src & 31); if ((src >> 5) == sl) qs = t; }
+                    for (int sl = 0; sl < SLOTS; ++sl) { double t = __shfl_sync(0xffffffffu, q[sl], src & 31); if ((src >> 5) == sl) qs = t; }
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) {
+                        const int pos = lane + 32 * sl;
+                        const bool before = (qs > q[sl]) || (qs == q[sl] && src < pos);   // stable descending
+                        if (before) rank[sl]++;
+                        if (before || src == pos) mass[sl] += qs;
+                    }
+                }
+                const double rT = p.ru[(((size_t)c * ns + j) * N + i) * p.ru_slots];
 #pragma unroll
                 for (int sl = 0; sl < SLOTS; ++sl) {
                     const int pos = lane + 32 * sl;
-                    const bool before = (qs > q[sl]) || (qs == q[sl] && src < pos);   // stable descending
-                    if (before) rank[sl]++;
-                    if (before || src == pos) mass[sl] += qs;
+                    if (pos < n_ent && (rank[sl] == n_ent - 1 || rT <= mass[sl])) best = min(best, ((unsigned)rank[sl] << 8) | (unsigned)pos);
                 }
-            }
-            double rT;
-            if (replay) rT = p.ru[(((size_t)c * ns + j) * N + i) * p.ru_slots];
-            else {
-                const int src = (i & 63) >> 1;
-                const uint32_t w0 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.z : rnd.x, src);
-                const uint32_t w1 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.w : rnd.y, src);
-                rT = u53(w0, w1);
-            }
-            unsigned best = 0xffffffffu;  // (rank << 8) | pos of the first sorted entry with rT <= mass
+            } else {
+                // Philox: the same categorical law by inverse CDF over the used-list order (the order of the
+                // walk does not change the distribution of the draw), one warp scan instead of a sort
+                const int usrc = (i & 63) >> 1;
+                const uint32_t w0 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.z : rnd.x, usrc);
+                const uint32_t w1 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.w : rnd.y, usrc);
+                const double rT = u53(w0, w1);
+                double cum[SLOTS], base = 0.0;
 #pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl) {
-                const int pos = lane + 32 * sl;
-                if (pos < n_ent && (rank[sl] == n_ent - 1 || rT <= mass[sl])) best = min(best, ((unsigned)rank[sl] << 8) | (unsigned)pos);
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    double v = pn[sl];
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const double t = __shfl_up_sync(0xffffffffu, v, off);
+                        if (lane >= off) v += t;
+                    }
+                    cum[sl] = v + base;
+                    base = __shfl_sync(0xffffffffu, cum[sl], 31);
+                }
+                const double target = rT * base;
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    const int pos = lane + 32 * sl;
+                    if (pos < n_ent && (pos == n_ent - 1 || target <= cum[sl])) best = min(best, ((unsigned)pos << 8) | (unsigned)pos);
+                }
             }
             best = __reduce_min_sync(0xffffffffu, best);
             const int wpos = (int)(best & 0xffu);

@@ -64,6 +64,7 @@ struct CollapsedParams {
     const uint32_t *xbits;        // [N][W]
     // tables shared by all chains: log(beta+n), log(gamma+n), log(beta+gamma+n), n = 0..N
     const double *logB, *logG, *logBG;
+    const double *logN;           // log(n), n = 0..N (dp: log N_k)
     // chain state (global, persists between launches)
     uint8_t *z_cur;               // [c][N] labels 0..K-1 (0xFF = unseated, dp sweep 1)
     int *cnt;                     // [c][K*(P+1)]: S_kd at k*(P+1)+d, N_k at k*(P+1)+P

@@ -406,3 +406,22 @@ def test_grid_large_p_tensor_path():
     _close(g["probs"][1][big], c["probs"][1][big], rtol=1e-4)
     assert (g["z"][0] != c["z"][0]).mean() < 5e-3
     assert np.allclose(g["pi"].sum(1), 1.0) and np.isfinite(g["theta"]).all()
+
+
+def test_dp_philox_posterior(oracle, datasets):
+    """gibbs_dp with Philox draws (inverse CDF over the used-list order) vs oracle chains (descending-sort
+    walk of RcppArmadillo::sample): same posterior -- number of occupied clusters and co-clustering rate."""
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    ns, burnin = 300, 100
+
+    def summary(z):  # z: S x N
+        kact = np.mean([len(np.unique(r)) for r in z])
+        co = np.mean(z[:, :10, None] == z[:, None, :10])     # co-clustering among the first ten observations
+        return kact, co
+    g = B.gibbs_dp(X, ns, burnin=burnin, maxK=30, chains=48, seed=31)
+    gs = np.array([summary(g["z"][c]) for c in range(48)])
+    os_ = np.array([summary(oracle.gibbs_dp(X, ns, alpha=0.0, burnin=burnin, maxK=30, seed=500 + c, probes=False).tail()["z"])
+                    for c in range(12)])
+    se = np.sqrt(gs.var(0) / 48 + os_.var(0) / 12)
+    assert (np.abs(gs.mean(0) - os_.mean(0)) < 4 * se + 0.02).all(), (gs.mean(0), os_.mean(0), se)
