@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbmm_b200.so")
 SOURCES = ["capi.cu", "dist.cu", "kern_full.cu", "kern_collapsed.cu", "kern_stephens.cu", "kern_finalize.cu",
-           "kern_big.cu", "kern_big_tc.cu", "kern_big_lp.cu"]
+           "kern_big.cu", "kern_big_tc.cu", "kern_big_lp.cu", "host_widen.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "--expt-extended-lambda"]
@@ -38,14 +38,17 @@ def build(force=False, verbose=False):
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(s)[0] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
             jobs.append((src, obj))
     nvcc = _nvcc()
 
     def cc(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        if src.endswith(".cpp"):
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-mavx2", "-pthread", "-c", src, "-o", obj]
+        else:
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
@@ -55,9 +58,9 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=8) as ex:
             list(ex.map(cc, jobs))
-    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
+    objs = [os.path.join(OBJ, os.path.splitext(s)[0] + ".o") for s in srcs]
     if jobs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr)

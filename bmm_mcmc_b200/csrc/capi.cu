@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -22,6 +23,7 @@
 namespace bmm {
 bool full_rows_fit_smem(int U, int K);
 }
+extern "C" void bmm_widen_u8_i32(const uint8_t *src, int32_t *dst, size_t n, int threads);  // host_widen.cpp
 
 namespace {
 
@@ -75,6 +77,7 @@ struct bmm_plan {
     bmm::CollapsedParams cp{};
     bmm::BigParams bp{};
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
+    int deb = 4;                  // bytes per allocation of the device-side R-layout z (1: widened on the host)
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
@@ -458,6 +461,47 @@ int run_segment(bmm_plan *pl, int j0, int j1) {
     return BMM_OK;
 }
 
+// Pinned staging for the byte-wide allocation history: two buffers, so the DMA of chunk c+1 overlaps
+// the host-side widening of chunk c.
+struct Staging {
+    uint8_t *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+} g_stage;
+
+int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
+    if (!dst || !src.p || n == 0) return BMM_OK;
+    const size_t CH = (size_t)32 << 20;
+    if (!g_stage.buf[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaHostAlloc((void **)&g_stage.buf[b], CH, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&g_stage.ev[b], cudaEventDisableTiming));
+        }
+        g_stage.bytes = CH;
+    }
+    static const int threads = [] {
+        const char *e = getenv("BMM_FETCH_THREADS");
+        // half the hardware threads, at most 8: measured on the 16-vCPU GPU boxes 8 workers reach
+        // ~120 GB/s of int32 output, 16 oversubscribe the cores the DMA completion path needs
+        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        return t < 1 ? 1 : (t > 8 && !e ? 8 : (t > 32 ? 32 : t));
+    }();
+    const size_t nch = (n + CH - 1) / CH;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t lo = c * CH, cnt = lo + CH <= n ? CH : n - lo;
+        cudaError_t e = cudaMemcpyAsync(g_stage.buf[c & 1], (const uint8_t *)src.p + lo, cnt, cudaMemcpyDeviceToHost, pl->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(g_stage.ev[c & 1], pl->stream);
+    };
+    CU(issue(0));
+    for (size_t c = 0; c < nch; ++c) {
+        if (c + 1 < nch) CU(issue(c + 1));
+        CU(cudaEventSynchronize(g_stage.ev[c & 1]));
+        const size_t lo = c * CH, cnt = lo + CH <= n ? CH : n - lo;
+        bmm_widen_u8_i32(g_stage.buf[c & 1], dst + lo, cnt, threads);
+    }
+    return BMM_OK;
+}
+
 int first_status(bmm_plan *pl, std::vector<int> &st) {
     st.assign(pl->C, 0);
     CU(cudaMemcpy(st.data(), pl->status.p, (size_t)pl->C * 4, cudaMemcpyDeviceToHost));
@@ -506,10 +550,15 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
     if (!rc) rc = pl->grid_path ? create_big(pl, init) : (uncollapsed ? create_full(pl, init) : create_collapsed(pl, init));
     if (!rc) {
         // R-layout allocation histories are produced on the device by the finalize kernel
-        const size_t eb = (args->flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+        // int32 output larger than a few MB: keep bytes on the device and widen on the host (fetch_z)
+        const size_t zelems = (size_t)pl->C * pl->S * pl->N;
+        const char *wenv = getenv("BMM_FETCH_WIDEN");
+        const bool widen = !(args->flags & BMM_FLAG_COMPACT_Z) && zelems >= ((size_t)8 << 20) && !(wenv && wenv[0] == '0');
+        pl->deb = ((args->flags & BMM_FLAG_COMPACT_Z) || widen) ? 1 : 4;
+        const size_t eb = (size_t)pl->deb;
         const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
-        cudaError_t e2 = no_z ? cudaSuccess : pl->z_orig.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
-        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc((size_t)pl->C * pl->S * pl->N * eb, false);
+        cudaError_t e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
+        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
         if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
     }
     if (!rc) { cudaError_t e3 = cudaDeviceSynchronize(); if (e3 != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e3)); }
@@ -546,7 +595,7 @@ int bmm_plan_run(bmm_plan *pl) {
     }
     CU(cudaEventRecord(pl->evs[3], pl->stream));
     CU(cudaEventRecord(pl->evk1, pl->stream));
-    const int eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+    const int eb = pl->deb;
     if (pl->z_orig.p)
         CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
                                   pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
@@ -615,15 +664,24 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     };
     CU(d2h(out->pi, pl->pi_out, C * S * K * 8));
     CU(d2h(out->alpha, pl->alpha_out, C * S * 8));
+    const bool widen = pl->deb == 1 && eb == 4;
     if (pl->relabel) {
         CU(d2h(out->permutations, pl->perm_out, C * S * K * 4));
-        CU(d2h(out->z, pl->z_rel, C * S * N * eb));
+        if (!widen) CU(d2h(out->z, pl->z_rel, C * S * N * eb));
         CU(d2h(out->theta, pl->theta_rel_out, C * K * P * S * 8));
-        CU(d2h(out->z_original, pl->z_orig, C * S * N * eb));
+        if (!widen) CU(d2h(out->z_original, pl->z_orig, C * S * N * eb));
         CU(d2h(out->theta_original, pl->theta_out, C * K * P * S * 8));
     } else {
-        CU(d2h(out->z, pl->z_orig, C * S * N * eb));
+        if (!widen) CU(d2h(out->z, pl->z_orig, C * S * N * eb));
         CU(d2h(out->theta, pl->theta_out, C * K * P * S * 8));
+    }
+    if (widen) {
+        if (pl->relabel) {
+            TRY(fetch_widen(pl, out->z, pl->z_rel, C * S * N));
+            TRY(fetch_widen(pl, out->z_original, pl->z_orig, C * S * N));
+        } else {
+            TRY(fetch_widen(pl, out->z, pl->z_orig, C * S * N));
+        }
     }
     CU(d2h(out->probs, pl->probs_out, C * ns * N * K * 8));
     CU(d2h(out->loglik, pl->loglik_out, C * ns * N * K * 8));

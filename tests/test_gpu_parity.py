@@ -425,3 +425,16 @@ def test_dp_philox_posterior(oracle, datasets):
                     for c in range(12)])
     se = np.sqrt(gs.var(0) / 48 + os_.var(0) / 12)
     assert (np.abs(gs.mean(0) - os_.mean(0)) < 4 * se + 0.02).all(), (gs.mean(0), os_.mean(0), se)
+
+
+def test_fetch_widening_equals_direct(datasets, monkeypatch):
+    """Large int32 z outputs travel as bytes and are widened on the host: same arrays as the direct int32 download."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    kw = dict(burnin=20, relabel=True, burnrelabel=10, chains=64, seed=8)
+    a = B.gibbs_full(X, 200, 3, **kw)                    # 64 * 180 * 1000 = 11.5M allocations: staged + widened
+    monkeypatch.setenv("BMM_FETCH_WIDEN", "0")
+    b = B.gibbs_full(X, 200, 3, **kw)
+    for k in ("z", "z_original", "permutations", "theta", "pi"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["z"].dtype == np.int32 and a["z"].min() >= 1 and a["z"].max() <= 3
