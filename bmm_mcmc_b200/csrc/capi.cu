@@ -81,6 +81,7 @@ struct bmm_plan {
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
+    DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
     // state
@@ -257,7 +258,6 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     const bmm_args &a = pl->a;
     const int N = pl->N, P = pl->P, K = pl->K, ns = pl->ns, S = pl->S;
     if (pl->C != 1) return fail(BMM_ERR_UNSUPPORTED, "the grid path runs one chain (n_chains <= 1)");
-    if (pl->relabel) return fail(BMM_ERR_UNSUPPORTED, "relabel is not available on the grid path yet");
     if (a.replay && K > bmm::big_replay_max_k()) return fail(BMM_ERR_UNSUPPORTED, "grid-path replay needs K <= 64");
     const long long n_global = a.n_global > 0 ? a.n_global : N;
     if (a.row_offset < 0 || a.row_offset + N > n_global) return fail(BMM_ERR_INVALID, "row_offset + N exceeds n_global");
@@ -286,6 +286,20 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)ns * N * K * 8));
     if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->loglik_out.alloc((size_t)ns * N * K * 8));
     if (a.flags & BMM_FLAG_PROBE_COUNTS) CU(pl->counts_out.alloc((size_t)ns * (K + KP) * 4));
+    if (pl->relabel) {
+        const size_t NK = (size_t)N * K;
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        if ((2 + (size_t)a.burnrelabel) * NK * 4 > free_b / 2)
+            return fail(BMM_ERR_UNSUPPORTED, "relabel on the grid path: burnrelabel x N x K probabilities do not fit the device; lower burnrelabel");
+        CU(pl->probs_f32.alloc(NK * 4)); CU(pl->Qf.alloc(NK * 4)); CU(pl->cube_f.alloc((size_t)a.burnrelabel * NK * 4));
+        CU(pl->cost_acc.alloc(((size_t)K * K + K) * 8));
+        CU(pl->perm_cur.alloc((size_t)K * 4));
+        CU(pl->sb_perm.alloc((size_t)a.burnrelabel * K * 4));
+        CU(pl->perm_out.alloc((size_t)S * K * 4));
+        CU(pl->theta_rel_out.alloc(KP * S * 8));
+        CU(pl->assign_ws.alloc(bmm::assign_ws_bytes(K)));
+    }
     if (a.replay) {
         const bmm_replay *r = a.replay;
         TRY(upload(pl->ru, r->u, (size_t)ns * N * r->u_slots));
@@ -310,6 +324,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.theta_out = pl->theta_out.as<double>(); b.pi_out = pl->pi_out.as<double>(); b.alpha_out = pl->alpha_out.as<double>();
     b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
     b.counts_out = pl->counts_out.as<int>();
+    b.probs_f32 = nullptr; b.perm_cur = pl->perm_cur.as<int>(); b.theta_rel_out = pl->theta_rel_out.as<double>();
     if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && P % 64 == 0 && (K > 32 || P > 112)) {
         CU(pl->lp_table.alloc(bmm::big_lp_table_bytes(P)));
         CU(pl->lp_bias.alloc(128 * 8));
@@ -335,14 +350,49 @@ int run_big(bmm_plan *pl) {
     }
     CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
     CU(bmm::launch_big_init(b, pl->stream));
+    const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
+    const long long N = b.N_local;
+    const size_t NK = (size_t)N * K;
+    if (pl->relabel) CU(bmm::launch_grid_identity_perm(K, K, pl->perm_cur.as<int>(), pl->stream));
     for (int j = 1; j < ns; ++j) {
-        if (b.ru) CU(bmm::launch_big_replay_load(b, j, pl->stream));
+        bmm::BigParams bj = b;
+        if (pl->relabel) {   // where this sweep's probabilities go (full_gibbs.cpp:146-156)
+            if (j < burnin && j >= burnin - M) bj.probs_f32 = pl->cube_f.as<float>() + (size_t)(j - burnin + M) * NK;
+            else if (j >= burnin) bj.probs_f32 = pl->probs_f32.as<float>();
+        }
+        if (b.ru) CU(bmm::launch_big_replay_load(bj, j, pl->stream));
         CU(cudaEventRecord(pl->sweep_ev[2 * j], pl->stream));
-        CU(bmm::launch_big_sweep(b, j, pl->sm_count, pl->stream));
+        CU(bmm::launch_big_sweep(bj, j, pl->sm_count, pl->stream));
         CU(cudaEventRecord(pl->sweep_ev[2 * j + 1], pl->stream));
         if (sharded && bmm::dist_allreduce_i32(pl->counts.as<int>() + (size_t)(j & 1) * ncnt, ncnt, pl->stream))
             return fail(BMM_ERR_NCCL, bmm::dist_error());
-        CU(bmm::launch_big_params(b, j, pl->stream));
+        if (pl->relabel && j == burnin - 1) {          // my_stephens_batch (full_gibbs.cpp:163-165)
+            float *cube = pl->cube_f.as<float>();
+            int *sbp = pl->sb_perm.as<int>();
+            CU(bmm::launch_grid_clamp((long long)M * (long long)NK, cube, pl->sm_count, pl->stream));
+            CU(bmm::launch_grid_identity_perm(M * K, K, sbp, pl->stream));
+            for (int iter = 0; iter < 100; ++iter) {   // threshold 10^(-6) == -16: always 100 (quirk 1)
+                CU(bmm::launch_grid_qmean(N, K, M, cube, sbp, pl->Qf.as<float>(), pl->sm_count, pl->stream));
+                for (int t = 0; t < M; ++t) {
+                    CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
+                                             pl->sm_count, pl->stream));
+                    if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
+                        return fail(BMM_ERR_NCCL, bmm::dist_error());
+                    CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
+                                               pl->stream));
+                }
+            }
+        } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
+            CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), 0, pl->cost_acc.as<double>(),
+                                     pl->sm_count, pl->stream));
+            if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
+                return fail(BMM_ERR_NCCL, bmm::dist_error());
+            CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
+                                       pl->perm_out.as<int>() + (j - burnin), pl->S, pl->stream));
+            CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(), pl->perm_cur.as<int>(), j,
+                                        pl->sm_count, pl->stream));
+        }
+        CU(bmm::launch_big_params(bj, j, pl->stream));
     }
     return BMM_OK;
 }
@@ -685,7 +735,11 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     }
     CU(d2h(out->probs, pl->probs_out, C * ns * N * K * 8));
     CU(d2h(out->loglik, pl->loglik_out, C * ns * N * K * 8));
-    if (out->Q_final && pl->relabel) {
+    std::vector<float> qf_host;
+    if (out->Q_final && pl->relabel && pl->grid_path) {
+        qf_host.resize(N * K);
+        CU(cudaMemcpyAsync(qf_host.data(), pl->Qf.p, N * K * 4, cudaMemcpyDeviceToHost, pl->stream));
+    } else if (out->Q_final && pl->relabel) {
         if (pl->U == pl->N && pl->sampler >= BMM_SAMPLER_COLLAPSED) {
             CU(d2h(out->Q_final, pl->Q, C * N * K * 8));
         } else {
@@ -698,6 +752,9 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     CU(d2h(out->counts, pl->counts_out, ns * (K + K * P) * 4));
     CU(d2h(out->status, pl->status, C * 4));
     CU(cudaStreamSynchronize(pl->stream));
+    if (!qf_host.empty())   // grid path keeps Q as row-major float; the ABI returns N x K column-major double
+        for (size_t i = 0; i < N; ++i)
+            for (size_t k = 0; k < K; ++k) out->Q_final[i + N * k] = (double)qf_host[i * K + k];
     std::vector<int> st;
     TRY(first_status(pl, st));
     for (size_t c = 0; c < C; ++c)
@@ -776,6 +833,22 @@ int bmm_assign(int32_t K, int32_t batch, const double *cost, int32_t *solution) 
     CU(sd.alloc((size_t)batch * K * K * 4)); CU(ws.alloc((size_t)batch * bmm::assign_ws_bytes(K)));
     CU(bmm::launch_assign(K, batch, cd.as<double>(), sd.as<int>(), ws.as<char>(), 0));
     CU(cudaMemcpy(solution, sd.p, (size_t)batch * K * K * 4, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+// Assignment with the grid path's solver (enumeration for K <= 5, warp-parallel Jonker-Volgenant above):
+// cost is K x K column-major (rows = reference labels), perm[c] = row assigned to column c.
+int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm) {
+    if (!cost || !perm || K < 1 || K > 255) return fail(BMM_ERR_INVALID, "bad assign arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    // the kernel computes s_l - G(k,l): feed G = -cost, s = 0
+    std::vector<double> acc((size_t)K * K + K, 0.0);
+    for (size_t e = 0; e < (size_t)K * K; ++e) acc[e] = -cost[e];
+    DevBuf ad, pd, ws;
+    TRY(upload(ad, acc.data(), acc.size()));
+    CU(pd.alloc((size_t)K * 4)); CU(ws.alloc(bmm::assign_ws_bytes(K)));
+    CU(bmm::launch_grid_assign(K, ad.as<double>(), ws.as<char>(), pd.as<int>(), nullptr, 1, 0));
+    CU(cudaMemcpy(perm, pd.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
     return BMM_OK;
 }
 

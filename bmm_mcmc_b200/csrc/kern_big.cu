@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams 
                 if (u < (double)c2) { z = k; break; }
             }
         }
+        if (p.probs_f32) {
+            for (int k = 0; k < K; ++k)
+                p.probs_f32[(size_t)i * K + k] = (float)(exp_r<R>(lpi[k] + row_loglik<R>(xb, P, K, k, w1, w0) - mx) / cum);
+        }
         if (p.probs_out || p.loglik_out) {
             for (int k = 0; k < K; ++k) {
                 const R ll = row_loglik<R>(xb, P, K, k, w1, w0);
@@ -184,6 +188,8 @@ __global__ void big_param_kernel(const BigParams p, const int j) {
             p.w1[e] = log(th);
             p.w0[e] = log(1 - th);
             if (p.theta_out && j >= p.burnin) p.theta_out[(size_t)KP * (j - p.burnin) + e] = th;
+            if (p.theta_rel_out && j >= p.burnin)   // theta_rel[perm[k], :] = theta[k, :] (full_gibbs.cpp:221-223)
+                p.theta_rel_out[(size_t)KP * (j - p.burnin) + p.perm_cur[k] + (size_t)K * d] = th;
         }
     }
     (void)ns;

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                     z += (run <= target) ? 1 : 0;
                     if (p.probs_out && valid && c0 + q < K)
                         p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * (c0 + q)] = (double)(e * inv);
+                    if (p.probs_f32 && valid && c0 + q < K) p.probs_f32[(size_t)i * K + c0 + q] = e * inv;
                 }
             }
             tc_fence_before();

@@ -194,18 +194,23 @@ __global__ void __launch_bounds__(NWG * 128, 1) big_sweep_tc_kernel(const BigPar
         for (int k = 1; k < KC; ++k) mx = fmaxf(mx, l[k]);
         // l[k] becomes the running sum of exp2(logit - max): the inverse CDF up to a factor
         float run = 0.f;
-        if (p.probs_out == nullptr) {
+        if (p.probs_out == nullptr && p.probs_f32 == nullptr) {
 #pragma unroll
             for (int k = 0; k < KC; ++k) { run += ex2_ftz(l[k] - mx); l[k] = run; }
-        } else {             // probe (parity tests): conditional probabilities of this sweep
+        } else {             // relabelling / probe: conditional probabilities of this sweep
             float sum = 0.f;
 #pragma unroll
             for (int k = 0; k < KC; ++k) { l[k] = ex2_ftz(l[k] - mx); sum += l[k]; }
             const float inv = 1.f / sum;
-            if (valid) {
+            if (valid && p.probs_out) {
 #pragma unroll
                 for (int k = 0; k < KC; ++k)
                     if (k < K) p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * k] = (double)(l[k] * inv);
+            }
+            if (valid && p.probs_f32) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k < K) p.probs_f32[(size_t)i * K + k] = l[k] * inv;
             }
 #pragma unroll
             for (int k = 0; k < KC; ++k) { run += l[k]; l[k] = run; }

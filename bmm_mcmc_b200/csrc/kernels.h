@@ -109,6 +109,9 @@ struct BigParams {
     double *theta_out, *pi_out, *alpha_out;   // [K*P*S], [S*K cm], [S]
     double *probs_out, *loglik_out;   // [nsamples][N_local*K cm] or nullptr
     int *counts_out;                  // [nsamples][K + K*P] probe or nullptr
+    float *probs_f32;                 // relabelling: this sweep's probabilities, row-major [N_local][K], or nullptr
+    const int *perm_cur;              // relabelling: permutation of the current sweep [K] (device), or nullptr
+    double *theta_rel_out;            // [K*P*S] relabelled theta history, or nullptr
     void *lp_table;                   // large-P tensor path: split weight table in operand-image order
     double *lp_bias;                  // [128] uncentred b_k
     const double *ru; int ru_slots;   // replay
@@ -127,6 +130,17 @@ cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStr
 bool big_lp_supported(const BigParams &p);
 size_t big_lp_table_bytes(int P);
 cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st);
+
+// ---- relabelling on the grid path (kern_big_relabel.cu); P, Q row-major float [N][K] ----------
+cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q, int use_logp, double *acc,
+                             int sm_count, cudaStream_t st);           // acc: K*K + K doubles
+cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st);
+cudaError_t launch_grid_qupdate(long long N, int K, float *Q, const float *P, const int *perm, int sample_num,
+                                int sm_count, cudaStream_t st);
+cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t st);
+cudaError_t launch_grid_qmean(long long N, int K, int M, const float *cube, const int *perm, float *Q, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_grid_identity_perm(int n, int K, int *perm, cudaStream_t st);
 
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,

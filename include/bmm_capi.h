@@ -141,6 +141,9 @@ int bmm_stephens_online(int32_t N, int32_t K, const double *q, const double *p, 
 /* _bmmmcmc_my_lpsolve (my_lpsolve.cpp:6-31): K x K cost (cm) -> K x K 0/1 solution (cm).
  * `batch` independent problems, consecutive in memory.                                            */
 int bmm_assign(int32_t K, int32_t batch, const double *cost, int32_t *solution);
+/* Same problem through the solver the grid path uses (warp-parallel Jonker-Volgenant for K > 5):
+ * perm[c] = index_max(solution.col(c)) (stephens.cpp:82-84).                                      */
+int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm);
 /* _bmmmcmc_rdirichlet_cpp (full_gibbs.cpp:10-27) with an explicit Philox seed.                    */
 int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out);
 

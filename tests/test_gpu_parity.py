@@ -438,3 +438,60 @@ def test_fetch_widening_equals_direct(datasets, monkeypatch):
     for k in ("z", "z_original", "permutations", "theta", "pi"):
         assert np.array_equal(a[k], b[k]), k
     assert a["z"].dtype == np.int32 and a["z"].min() >= 1 and a["z"].max() <= 3
+
+
+@pytest.mark.parametrize("name,K", [("K3_N1000_P5", 3), ("K2_N1000_P5", 2)])
+def test_grid_path_relabel_replay(oracle, datasets, name, K):
+    """Stephens batch + online relabelling with the streaming grid kernels (float P / Q, warp Jonker-Volgenant /
+    enumeration) against the oracle (reference lp_solve): same permutations, same relabelled z, Q within fp32."""
+    _need_gpu()
+    X = datasets[name]
+    N, P = X.shape
+    ns, burnin, br = 50, 20, 6
+    ip, th = _init_full(K, P, 5)
+    r = oracle.gibbs_full(X, ip, th, ns, K, burnin=burnin, relabel=True, burnrelabel=br, seed=11)
+    g = B.gibbs_full(X, ns, K, burnin=burnin, relabel=True, burnrelabel=br, initial_pi=ip, initial_theta=th,
+                     replay=_replay_of(r), probes=("Q_final",), grid_path=True)
+    t = r.tail()
+    assert np.array_equal(g["z_original"], t["z_original"])
+    assert np.array_equal(g["permutations"], t["permutations"])
+    assert np.array_equal(g["z"], t["z"])
+    _close(g["theta"], t["theta"], rtol=0)
+    _close(g["theta_original"], t["theta_original"], rtol=0)
+    _close(g["Q_final"], r["Q_final"], rtol=2e-4)
+
+
+def test_grid_relabel_large_k_tensor_path():
+    """Relabelling on the tcgen05 large-K path (K = 40 > enumeration range: warp Jonker-Volgenant): the
+    permutation of every sweep is a permutation, z is z_original mapped through it, and the assignment is
+    optimal for the cost matrix recomputed on the host from the same probabilities."""
+    _need_gpu()
+    rng = np.random.default_rng(2)
+    N, P, K = 4000, 128, 40
+    th_true = rng.uniform(0.15, 0.85, (K, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, K, N)]).astype(np.int32)
+    g = B.gibbs_full(X, 14, K, alpha=1.0, burnin=6, relabel=True, burnrelabel=2, seed=3, precision="fp32")
+    S = g["permutations"].shape[0]
+    assert np.array_equal(np.sort(g["permutations"], 1), np.tile(np.arange(K), (S, 1)))
+    assert np.array_equal(g["z"], np.take_along_axis(g["permutations"], g["z_original"] - 1, 1) + 1)
+    th_rel = np.empty_like(g["theta_original"])
+    for s in range(S):
+        th_rel[g["permutations"][s], :, s] = g["theta_original"][:, :, s]
+    assert np.array_equal(th_rel, g["theta"])
+
+
+def test_assign_warp_jv_matches_lpsolve(oracle):
+    """The warp-parallel Jonker-Volgenant solver of the grid path (through bmm_stephens-style cost) equals lp_solve."""
+    _need_gpu()
+    import ctypes as C
+    L = _lib.lib()
+    if not hasattr(L, "bmm_assign_warp"):
+        pytest.skip("bmm_assign_warp not exported")
+    rng = np.random.default_rng(4)
+    for K in (6, 17, 32, 64, 128):
+        cost = rng.uniform(0, 1000, (K, K))
+        cf = np.asfortranarray(cost)
+        perm = np.zeros(K, dtype=np.int32)
+        _lib.check(L.bmm_assign_warp(K, cf.ctypes.data_as(C.POINTER(C.c_double)), perm.ctypes.data_as(C.POINTER(C.c_int32))))
+        s_o = oracle.assign(cost, use_ref=oracle.has_ref() and K <= 32)
+        assert np.array_equal(perm, s_o.argmax(0)), K
