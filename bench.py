@@ -212,12 +212,15 @@ GRID_WORKLOADS = {
                precision="fp32", cpu_N=60_000, cpu_ns=6,
                label="C4: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1"),
     # BASELINE.json configs[4] (relabelling on the grid path is not built yet: relabel=FALSE here)
-    "c5": dict(sampler="full", N=1_000_000, P=4096, K=128, nsamples=21, burnin=3, alpha=1.0,
+    "c5": dict(sampler="full", N=1_000_000, P=4096, K=128, nsamples=41, burnin=5, alpha=1.0, relabel=True, burnrelabel=1,
                precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
-               label="C5: gibbs_full synthetic N=1e6 P=4096 K=128 (large-P tcgen05 contraction)"),
-    "c5small": dict(sampler="full", N=100_000, P=4096, K=128, nsamples=9, burnin=2, alpha=1.0,
+               label="C5: gibbs_full synthetic N=1e6 P=4096 K=128 (large-P tcgen05 contraction) + Stephens relabelling (Hungarian)"),
+    "c5small": dict(sampler="full", N=100_000, P=4096, K=128, nsamples=21, burnin=5, alpha=1.0, relabel=True, burnrelabel=1,
                     precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
-                    label="C5 shape at N=1e5 (smoke size)"),
+                    label="C5 shape at N=1e5 (smoke size) + relabelling"),
+    "c5norelabel": dict(sampler="full", N=1_000_000, P=4096, K=128, nsamples=21, burnin=3, alpha=1.0,
+                        precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
+                        label="C5 shape, relabel=FALSE (sweep kernels only)"),
     "c4small": dict(sampler="stickbreaking", N=1_000_000, P=64, K=32, nsamples=21, burnin=3, alpha=1.0,
                     precision="fp32", cpu_N=20_000, cpu_ns=4,
                     label="C4 shape at N=1e6 (smoke size)"),
@@ -330,7 +333,8 @@ def run_grid(a):
     sid = _lib.SAMPLER_STICKBREAKING if w["sampler"] == "stickbreaking" else _lib.SAMPLER_FULL
     kname = "big_sweep_tc_kernel" if (K <= 32 and P <= 112) else "lp_table+lp_sweep+lp_counts kernels"
     shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
-    kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=False, burnrelabel=0)
+    relabel, br = bool(w.get("relabel")), int(w.get("burnrelabel", 0))
+    kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=relabel, burnrelabel=br)
 
     def barrier():
         if dist:
@@ -357,7 +361,7 @@ def run_grid(a):
     plan.close()
 
     # e2e: the public call with host buffers (bit-packed rows in, uint8 allocation history out)
-    bufs = api._alloc_out(sid, 1, hi - lo, P, K, ns, burnin, False, True, (), True)
+    bufs = api._alloc_out(sid, 1, hi - lo, P, K, ns, burnin, relabel, True, (), True)
     d2h = api.out_nbytes(bufs[0])
     h2d = X.nbytes + ip.nbytes + th.nbytes
     fn = B.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else B.gibbs_full
@@ -365,7 +369,7 @@ def run_grid(a):
     def e2e_step():
         return fn(X, ns, K, alpha=w["alpha"], burnin=burnin, seed=2026, device=local, initial_pi=ip,
                   initial_theta=th.transpose(0, 2, 1), precision=w["precision"], compact_z=True, grid_path=True,
-                  out_bufs=bufs, **shard)
+                  relabel=relabel, burnrelabel=br, out_bufs=bufs, **shard)
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -404,7 +408,8 @@ def run_grid(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tm[0] / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32" if w["precision"] == "fp32" else "f64",
         "data": "synthetic (seed 17): pi* uniform, theta* ~ U(0.1,0.9), bit-packed rows",
-        "config": {"workload": "%s, nsamples=%d (one step = %d sweeps), relabel=FALSE" % (w["label"], ns, ns - 1),
+        "config": {"workload": "%s, nsamples=%d (one step = %d sweeps), relabel=%s burnrelabel=%d"
+                               % (w["label"], ns, ns - 1, relabel, br),
                    "N": N, "rows_per_gpu": n_local,
                    "parallelism": "rows block-partitioned over GPUs; int32 counts all-reduced (NCCL) every sweep"
                                   if world > 1 else "single GPU",
@@ -418,7 +423,7 @@ def run_grid(a):
         "gpu_launches": launches,
         "roofline": roof,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,
-                  "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "params_and_allreduce": kern[1] / a.steps,
+                  "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "params_allreduce_relabel": kern[1] / a.steps,
                                  "finalize_layout": kern[3] / a.steps}},
     }
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -34,10 +34,10 @@ __device__ inline void assign_enum_thread(int K, const double *cost, int *col_to
     for (int r = 0; r < K; ++r) col_to_row[best[r]] = r;
 }
 
-// Workspace: (3*(K+1)) doubles then (2*(K+1)) ints then (K+1) bytes; see assign_ws_bytes().
+// Workspace: (3*(K+1)) doubles then (2*(K+1)) ints then 2*(K+1) bytes; see assign_ws_bytes().
 __host__ __device__ inline size_t assign_ws_bytes(int K) {
     size_t n = (size_t)(K + 1);
-    size_t b = 3 * n * sizeof(double) + 2 * n * sizeof(int) + n;
+    size_t b = 3 * n * sizeof(double) + 2 * n * sizeof(int) + 2 * n;
     return (b + 15) & ~(size_t)15;
 }
 

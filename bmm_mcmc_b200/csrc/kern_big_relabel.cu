@@ -82,75 +82,187 @@ __global__ void __launch_bounds__(256) grid_cost_kernel(long long N, int K, cons
     }
 }
 
-// Warp-parallel shortest-augmenting-path assignment (Jonker-Volgenant potentials): lanes share the
-// column scan, the arg-min is a warp reduction.  Same optimum as assign_jv_thread; ties broken towards
-// the smallest column index like the serial scan.  Workspace as assign_ws_bytes(K).
-__device__ void assign_jv_warp(int K, const double *cost, void *ws, int *col_to_row) {
+// Warp-parallel shortest-augmenting-path assignment (Jonker-Volgenant potentials).  Lane `l` owns
+// columns j = 1 + l + 32 m and keeps their whole state in registers -- column potential v, reduced
+// slack minv, predecessor way, matched row p and THAT ROW's potential ucol (a row's potential travels
+// with the row when the matching changes) -- so one step of the path search is a conflict-free row
+// read from shared memory plus a warp arg-min, not a chain of dependent shared-memory round trips
+// (measured: 2 900 -> ~350 cycles per step at K = 128).  costT is row-major: costT[(i-1)*K + (j-1)].
+// Starts from the row reduction u_i = min_j c_ij (dual feasible with v = 0): a row whose minimum
+// column is free is matched at once, which settles every row once relabelling has converged.
+// Ties go to the smallest column index, like the serial scan of assign_jv_thread.
+template <int M>
+__device__ void assign_jv_warp(int K, const double *costT, double *urow, int *col_to_row) {
     const int lane = threadIdx.x & 31;
     const double INF = 1e300;
-    double *u = (double *)ws, *v = u + (K + 1), *minv = v + (K + 1);
-    int *p = (int *)(minv + (K + 1)), *way = p + (K + 1);
-    unsigned char *used = (unsigned char *)(way + (K + 1));
-    for (int j = lane; j <= K; j += 32) { u[j] = 0.0; v[j] = 0.0; p[j] = 0; way[j] = 0; }
-    __syncwarp();
+    double v[M], minv[M], ucol[M];
+    int p[M], way[M];
+    unsigned usedm = 0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) { v[m] = 0.0; minv[m] = INF; ucol[m] = 0.0; p[m] = 0; way[m] = 0; }
+    auto sel_i = [&](const int (&a)[M], int m0) { int r = a[0];
+#pragma unroll
+        for (int m = 1; m < M; ++m) r = (m0 == m) ? a[m] : r; return r; };
+    auto sel_d = [&](const double (&a)[M], int m0) { double r = a[0];
+#pragma unroll
+        for (int m = 1; m < M; ++m) r = (m0 == m) ? a[m] : r; return r; };
+    auto argmin = [&](double &best, int &bj) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+            if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+    };
+    // ---- row reduction ----
+    unsigned long long done_lo = 0, done_hi = 0, done_2 = 0, done_3 = 0;   // rows 1..K matched at start (bitset, uniform)
+    auto set_done = [&](int i) { if (i < 64) done_lo |= 1ull << i; else if (i < 128) done_hi |= 1ull << (i - 64);
+                                 else if (i < 192) done_2 |= 1ull << (i - 128); else done_3 |= 1ull << (i - 192); };
+    auto is_done = [&](int i) { return (int)(((i < 64) ? done_lo >> i : (i < 128) ? done_hi >> (i - 64)
+                                              : (i < 192) ? done_2 >> (i - 128) : done_3 >> (i - 192)) & 1ull); };
     for (int i = 1; i <= K; ++i) {
-        if (lane == 0) p[0] = i;
-        for (int j = lane; j <= K; j += 32) { minv[j] = INF; used[j] = 0; }
-        __syncwarp();
+        double best = INF;
+        int bj = 0x7fffffff;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const int j = 1 + lane + 32 * m;
+            if (j <= K) {
+                const double c = costT[(size_t)(i - 1) * K + (j - 1)];
+                if (c < best) { best = c; bj = j; }
+            }
+        }
+        argmin(best, bj);
+        if (lane == 0) urow[i] = bj == 0x7fffffff ? 0.0 : best;
+        if (bj != 0x7fffffff) {
+            const int owner = (bj - 1) & 31, m0 = (bj - 1) >> 5;
+            const int taken = __shfl_sync(0xffffffffu, sel_i(p, m0), owner);
+            if (!taken) {
+                if (lane == owner) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) if (m == m0) { p[m] = i; ucol[m] = best; }
+                }
+                set_done(i);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- augmenting paths for the rows still unmatched ----
+    for (int i = 1; i <= K; ++i) {
+        if (is_done(i)) continue;
+        int p0 = i;
+        double u0 = urow[i];
+        usedm = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) minv[m] = INF;
         int j0 = 0;
         for (;;) {
-            if (lane == 0) used[j0] = 1;
-            __syncwarp();
-            const int i0 = p[j0];
-            const double ui0 = u[i0];
+            int i0;
+            double ui0;
+            if (j0 == 0) { i0 = p0; ui0 = u0; }
+            else {
+                const int owner = (j0 - 1) & 31, m0 = (j0 - 1) >> 5;
+                if (lane == owner) usedm |= 1u << m0;
+                i0 = __shfl_sync(0xffffffffu, sel_i(p, m0), owner);
+                ui0 = __shfl_sync(0xffffffffu, sel_d(ucol, m0), owner);
+            }
+            const double *crow = costT + (size_t)(i0 - 1) * K;
             double best = INF;
             int bj = 0x7fffffff;
-            for (int j = 1 + lane; j <= K; j += 32)
-                if (!used[j]) {
-                    const double cur = cost[(i0 - 1) + (size_t)K * (j - 1)] - ui0 - v[j];
-                    if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
-                    if (minv[j] < best) { best = minv[j]; bj = j; }
-                }
 #pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-                if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+            for (int m = 0; m < M; ++m) {
+                const int j = 1 + lane + 32 * m;
+                if (j <= K && !((usedm >> m) & 1u)) {
+                    const double cur = crow[j - 1] - ui0 - v[m];
+                    if (cur < minv[m]) { minv[m] = cur; way[m] = j0; }
+                    if (minv[m] < best) { best = minv[m]; bj = j; }
+                }
             }
-            int j1 = bj;
+            argmin(best, bj);
             double delta = best;
+            int j1 = bj;
             if (j1 == 0x7fffffff) {  // non-finite costs: any free column, so the loop terminates
                 delta = 0.0;
-                j1 = 0;
-                for (int j = 1; j <= K; ++j) if (!used[j]) { j1 = j; break; }
+                int cand = 0x7fffffff;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int j = 1 + lane + 32 * m;
+                    if (j <= K && !((usedm >> m) & 1u) && j < cand) cand = j;
+                }
+                j1 = __reduce_min_sync(0xffffffffu, cand);
+                const int owner = (j1 - 1) & 31, m0 = (j1 - 1) >> 5;
+                if (lane == owner) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) if (m == m0) way[m] = j0;
+                }
             }
-            __syncwarp();
-            for (int j = lane; j <= K; j += 32) {
-                if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
-                else minv[j] -= delta;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                if ((usedm >> m) & 1u) { ucol[m] += delta; v[m] -= delta; }
+                else minv[m] -= delta;
             }
-            __syncwarp();
+            u0 += delta;
             j0 = j1;
-            if (p[j0] == 0) break;
+            const int owner = (j0 - 1) & 31, m0 = (j0 - 1) >> 5;
+            if (__shfl_sync(0xffffffffu, sel_i(p, m0), owner) == 0) break;
         }
-        if (lane == 0) {
-            do { const int j1 = way[j0]; p[j0] = p[j1]; j0 = j1; } while (j0);
-        }
-        __syncwarp();
+        // unwind: column j0 takes the row (and its potential) of its predecessor column
+        do {
+            const int owner = (j0 - 1) & 31, m0 = (j0 - 1) >> 5;
+            const int j1 = __shfl_sync(0xffffffffu, sel_i(way, m0), owner);
+            int pj1 = p0;
+            double uj1 = u0;
+            if (j1 != 0) {
+                const int o1 = (j1 - 1) & 31, m1 = (j1 - 1) >> 5;
+                pj1 = __shfl_sync(0xffffffffu, sel_i(p, m1), o1);
+                uj1 = __shfl_sync(0xffffffffu, sel_d(ucol, m1), o1);
+            }
+            if (lane == owner) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) if (m == m0) { p[m] = pj1; ucol[m] = uj1; }
+            }
+            j0 = j1;
+        } while (j0);
     }
-    for (int j = 1 + lane; j <= K; j += 32) col_to_row[j - 1] = p[j] - 1;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int j = 1 + lane + 32 * m;
+        if (j <= K) col_to_row[j - 1] = p[m] - 1;
+    }
     __syncwarp();
 }
 
 // One warp: cost = s_l - G(k,l) (column-major k + K*l), assignment, permutation bookkeeping.
 // perm_dst[l * perm_stride] receives perm[l]; perm_cur (optional) the same, contiguous.
-__global__ void grid_assign_kernel(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride) {
+// The solver's potentials / labels live in shared memory, and so does the cost matrix when it fits
+// (cost_in_smem): every step of the augmenting-path search is a dependent chain of such accesses.
+// acc holds G(k,l) at k + K*l and s_l at K*K + l; the cost C(k,l) = s_l - G(k,l) has rows k = reference
+// labels and columns l = sample labels (stephens.cpp:78-84).
+__global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *perm_cur, int *perm_dst, int perm_stride) {
+    extern __shared__ __align__(16) char sm[];
     const int lane = threadIdx.x;
-    for (int e = lane; e < K * K; e += 32) acc[e] = acc[(size_t)K * K + e / K] - acc[e];
-    __syncwarp();
     __shared__ int c2r[256];
-    if (K <= ASSIGN_ENUM_MAXK) { if (lane == 0) assign_enum_thread(K, acc, c2r); }
-    else assign_jv_warp(K, acc, ws, c2r);
+    if (K <= ASSIGN_ENUM_MAXK) {
+        for (int e = lane; e < K * K; e += 32) acc[e] = acc[(size_t)K * K + e / K] - acc[e];
+        __syncwarp();
+        if (lane == 0) assign_enum_thread(K, acc, c2r);
+    } else {
+        // row-major copy (costT[k*K + l]) in shared memory when it fits, else in place in global memory
+        double *urow = (double *)sm;
+        double *costT = cost_in_smem ? urow + (K + 1) : acc;
+        if (cost_in_smem) {
+            for (int e = lane; e < K * K; e += 32) { const int k = e / K, l = e % K; costT[e] = acc[(size_t)K * K + l] - acc[k + (size_t)K * l]; }
+        } else {
+            for (int e = lane; e < K * K; e += 32) acc[e] = acc[(size_t)K * K + e / K] - acc[e];
+            __syncwarp();
+            for (int k = 0; k < K; ++k)        // in-place transpose to row-major
+                for (int l = k + 1 + lane; l < K; l += 32) { const double t = acc[k + (size_t)K * l]; acc[k + (size_t)K * l] = acc[l + (size_t)K * k]; acc[l + (size_t)K * k] = t; }
+        }
+        __syncwarp();
+        if (K <= 32) assign_jv_warp<1>(K, costT, urow, c2r);
+        else if (K <= 64) assign_jv_warp<2>(K, costT, urow, c2r);
+        else if (K <= 128) assign_jv_warp<4>(K, costT, urow, c2r);
+        else assign_jv_warp<8>(K, costT, urow, c2r);
+    }
     __syncwarp();
     for (int l = lane; l < K; l += 32) {
         if (perm_cur) perm_cur[l] = c2r[l];
@@ -209,7 +321,17 @@ cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q,
 }
 
 cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st) {
-    grid_assign_kernel<<<1, 32, 0, st>>>(K, acc, ws, perm_cur, perm_dst, perm_stride);
+    (void)ws;
+    const size_t wsb = ((size_t)(K + 1) * sizeof(double) + 15) & ~(size_t)15, costb = (size_t)K * K * sizeof(double);
+    const int in_smem = wsb + costb <= 200 * 1024;
+    const size_t smem = wsb + (in_smem ? costb : 0);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(grid_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    grid_assign_kernel<<<1, 32, smem, st>>>(K, acc, in_smem, perm_cur, perm_dst, perm_stride);
     g_launches++;
     return cudaGetLastError();
 }
