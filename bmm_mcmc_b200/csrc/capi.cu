@@ -85,7 +85,7 @@ struct bmm_plan {
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
     // state
-    DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status;
+    DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status, cost_g;
     DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws;
     // histories
     DevBuf zhist, theta_out, theta_rel_out, pi_out, alpha_out, perm_out, probs_out, loglik_out, kactive;
@@ -214,6 +214,7 @@ int create_full(bmm_plan *pl, const bmm_init *init) {
         CU(pl->sb_ws.alloc((size_t)C * a.burnrelabel * bmm::assign_ws_bytes(K)));
         CU(pl->perm_out.alloc((size_t)C * S * K * 4));
         CU(pl->theta_rel_out.alloc((size_t)C * KP * S * 8));
+        if (K * K > bmm::COST_SMEM_MAX) CU(pl->cost_g.alloc((size_t)C * K * K * 8));
     }
     if (!use_hist) CU(pl->prob_g.alloc((size_t)C * UK * 8));
     if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->ll_g.alloc((size_t)C * UK * 8));
@@ -242,7 +243,7 @@ int create_full(bmm_plan *pl, const bmm_init *init) {
     f.theta_cur = pl->theta_cur.as<double>(); f.pi_cur = pl->pi_cur.as<double>(); f.alpha_cur = pl->alpha_cur.as<double>();
     f.Q = pl->Q.as<double>(); f.logQ = pl->logQ.as<double>(); f.cube = pl->cube.as<double>();
     f.prob_g = pl->prob_g.as<double>(); f.hist_g = nullptr; f.ll_g = pl->ll_g.as<double>();
-    f.assign_ws = pl->assign_ws.as<char>(); f.status = pl->status.as<int>();
+    f.assign_ws = pl->assign_ws.as<char>(); f.status = pl->status.as<int>(); f.cost_g = pl->cost_g.as<double>();
     f.zhist = pl->zhist.as<uint8_t>(); f.theta_out = pl->theta_out.as<double>(); f.theta_rel_out = pl->theta_rel_out.as<double>();
     f.pi_out = pl->pi_out.as<double>(); f.alpha_out = pl->alpha_out.as<double>(); f.perm_out = pl->perm_out.as<int>();
     f.probs_out = pl->probs_out.as<double>(); f.loglik_out = pl->loglik_out.as<double>();
@@ -456,6 +457,7 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
         CU(pl->sb_ws.alloc((size_t)C * a.burnrelabel * bmm::assign_ws_bytes(K)));
         CU(pl->perm_out.alloc((size_t)C * S * K * 4));
         CU(pl->theta_rel_out.alloc((size_t)C * KP * S * 8));
+        if (K * K > bmm::COST_SMEM_MAX) CU(pl->cost_g.alloc((size_t)C * K * K * 8));
     }
     CU(pl->assign_ws.alloc((size_t)C * bmm::assign_ws_bytes(K)));
     CU(pl->status.alloc((size_t)C * 4));
@@ -479,12 +481,13 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     q.dp_used = pl->dp_used.as<int>(); q.dp_free = pl->dp_free.as<uint8_t>();
     q.Q = pl->Q.as<double>(); q.logQ = pl->logQ.as<double>(); q.probs_sample = pl->probs_sample.as<double>();
     q.cube = pl->cube.as<double>(); q.assign_ws = pl->assign_ws.as<char>(); q.status = pl->status.as<int>();
+    q.cost_g = pl->cost_g.as<double>();
     q.zhist = pl->zhist.as<uint8_t>(); q.theta_out = pl->theta_out.as<double>(); q.theta_rel_out = pl->theta_rel_out.as<double>();
     q.alpha_out = pl->alpha_out.as<double>(); q.perm_out = pl->perm_out.as<int>();
     q.probs_out = pl->probs_out.as<double>(); q.kactive_out = pl->kactive.as<int>();
     q.ru = pl->ru.as<double>(); q.ru_slots = a.replay ? a.replay->u_slots : 0; q.ralpha = pl->ralpha.as<double>();
     if (bmm::collapsed_smem_bytes(q) > 200 * 1024)
-        return fail(BMM_ERR_UNSUPPORTED, "N*P too large for the chain-per-warp collapsed kernel");
+        return fail(BMM_ERR_UNSUPPORTED, "N*P (bit-packed data + allocations) too large for the shared memory of the chain-per-warp collapsed kernel");
     return BMM_OK;
 }
 

@@ -30,7 +30,7 @@ __host__ __device__ inline size_t collapsed_layout(const CollapsedParams &p, cha
     size_t off = 0;
     auto take = [&](size_t bytes) { char *r = base + off; off += (bytes + 7) & ~(size_t)7; return r; };
     double *logA = (double *)take(p.dp ? 0 : (size_t)(p.N + 1) * 8);
-    double *cost = (double *)take(p.relabel ? (size_t)p.K * p.K * 8 : 0);
+    double *cost = (double *)take(p.relabel && p.K * p.K <= COST_SMEM_MAX ? (size_t)p.K * p.K * 8 : 0);
     uint32_t *x = (uint32_t *)take((size_t)p.N * p.W * 4);
     int *cnt = (int *)take((size_t)p.K * (p.P + 1) * 4);
     int *perm = (int *)take((size_t)p.K * 4);
@@ -72,7 +72,7 @@ __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s,
         // window sweeps were stashed straight into their cube slice (see stash_target)
         if (j >= p.burnin) {
             stephens_online_block(N, K, nullptr, p.Q + (size_t)c * NK, p.logQ + (size_t)c * NK,
-                                  p.probs_sample + (size_t)c * NK, j, s.cost, s.perm,
+                                  p.probs_sample + (size_t)c * NK, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm,
                                   p.assign_ws + (size_t)c * assign_ws_bytes(K));
         }
     }

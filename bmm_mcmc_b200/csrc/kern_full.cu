@@ -34,7 +34,7 @@ __host__ __device__ inline size_t full_layout(const FullParams &p, char *base, F
     auto takeD = [&](size_t n) { double *r = (double *)(base + off); off += n * sizeof(double); return r; };
     auto takeI = [&](size_t n) { int *r = (int *)(base + off); off += n * sizeof(int); return r; };
     double *theta = takeD(KP), *w1 = takeD(KP), *w0 = takeD(KP), *pi = takeD(K), *lpi = takeD(K), *gsc = takeD(K);
-    double *cost = takeD(K * K), *scal = takeD(4);
+    double *cost = takeD(K * K <= (size_t)COST_SMEM_MAX ? K * K : 0), *scal = takeD(4);
     double *prob = nullptr, *Q = nullptr, *logQ = nullptr;
     if (p.use_hist) { prob = takeD(UK); if (p.relabel) { Q = takeD(UK); logQ = takeD(UK); } }
     int *ck = takeI(K), *Vkd = takeI(KP), *perm = takeI(K), *hist = nullptr;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                 double *dst = p.cube + ((size_t)c * p.burnrelabel + (j - p.burnin + p.burnrelabel)) * UK;
                 for (size_t e = tid; e < UK; e += nthr) dst[e] = prob[e];
             } else if (j >= p.burnin) {
-                stephens_online_block(U, K, p.wt, Q, logQ, prob, j, s.cost, s.perm, aws);
+                stephens_online_block(U, K, p.wt, Q, logQ, prob, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm, aws);
             }
         }
         // ---- F: parameter draws

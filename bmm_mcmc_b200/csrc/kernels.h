@@ -35,6 +35,7 @@ struct FullParams {
     int *hist_g;                  // [c][U*K]
     double *ll_g;                 // [c][U*K] (loglik probe only)
     char *assign_ws;              // [c][assign_ws_bytes(K)]
+    double *cost_g;               // [c][K*K] Stephens cost when K*K doubles do not fit shared memory, else nullptr
     int *status;                  // [c]
     // histories
     uint8_t *zhist;               // [c][nsamples][N], labels 1..K
@@ -49,6 +50,8 @@ struct FullParams {
     const double *ru; int ru_slots;
     const double *rpi, *rtheta, *ralpha;
 };
+// K x K cost matrices up to this many entries live in shared memory, larger ones in cost_g
+constexpr int COST_SMEM_MAX = 64 * 64;
 size_t full_smem_bytes(const FullParams &p, int threads);
 cudaError_t launch_full(const FullParams &p, int n_chains, int threads, cudaStream_t st);
 
@@ -75,6 +78,7 @@ struct CollapsedParams {
     double *probs_sample;         // [c][N*K]
     double *cube;                 // [c][burnrelabel][N*K]
     char *assign_ws;
+    double *cost_g;               // [c][K*K] or nullptr (see FullParams)
     int *status;
     // histories
     uint8_t *zhist;               // [c][nsamples][N] labels 1..K

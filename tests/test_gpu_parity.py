@@ -495,3 +495,88 @@ def test_assign_warp_jv_matches_lpsolve(oracle):
         _lib.check(L.bmm_assign_warp(K, cf.ctypes.data_as(C.POINTER(C.c_double)), perm.ctypes.data_as(C.POINTER(C.c_int32))))
         s_o = oracle.assign(cost, use_ref=oracle.has_ref() and K <= 32)
         assert np.array_equal(perm, s_o.argmax(0)), K
+
+
+# ---- edge cases ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,P,K", [(1, 1, 1), (2, 1, 2), (7, 33, 3), (50, 64, 5), (40, 70, 9)])
+def test_edge_shapes_replay_all_samplers(oracle, N, P, K):
+    """Degenerate and ragged shapes (single observation / variable / cluster, P crossing a 32-bit word, K above
+    the enumeration range) through every sampler, in replay against the oracle."""
+    _need_gpu()
+    rng = np.random.default_rng(N * 100 + P)
+    X = (rng.random((N, P)) < 0.4).astype(np.int32)
+    ns, burnin = 12, 3
+    ip, th = _init_full(K, P, 3)
+    r = oracle.gibbs_full(X, ip, th, ns, K, burnin=burnin, seed=2)
+    for grid in (False, True):
+        g = B.gibbs_full(X, ns, K, burnin=burnin, initial_pi=ip, initial_theta=th, replay=_replay_of(r), probes=("probs",),
+                         grid_path=grid)
+        _close(g["probs"][1:], r["probs"][1:], atol=1e-300)
+        assert np.array_equal(g["z"], r.tail()["z"]), ("full", grid)
+    r = oracle.gibbs_stickbreaking(X, ip, th, ns, K, burnin=burnin, seed=2)
+    g = B.gibbs_stickbreaking(X, ns, K, burnin=burnin, initial_pi=ip, initial_theta=th, replay=_replay_of(r))
+    assert np.array_equal(g["z"], r.tail()["z"])
+    iz = RRng(3).sample_int(K, N)
+    try:
+        r = oracle.gibbs_collapsed(X, iz, ns, K, burnin=burnin, seed=2)
+    except RuntimeError:
+        # N = 1: removing the only observation empties every cluster, all probabilities are 0 and the
+        # reference's rmultinom returns NA (collapsed_gibbs.cpp:104,131-133,154); the GPU flags it
+        with pytest.raises(_lib.BmmError) as e:
+            B.gibbs_collapsed(X, ns, K, burnin=burnin, initial_K=iz, seed=2)
+        assert e.value.code == -9
+        r = None
+    if r is not None:
+        g = B.gibbs_collapsed(X, ns, K, burnin=burnin, initial_K=iz, replay=_replay_of(r, keys=("alpha",)))
+        assert np.array_equal(g["z"], r.tail()["z"])
+    try:
+        r = oracle.gibbs_dp(X, ns, alpha=0.0, burnin=burnin, maxK=max(K + 2, 4), seed=2)
+    except RuntimeError:
+        return
+    g = B.gibbs_dp(X, ns, burnin=burnin, maxK=max(K + 2, 4), replay=_replay_of(r, keys=("alpha",)))
+    assert np.array_equal(g["z"], r.tail()["z"])
+
+
+def test_edge_burnin_zero_and_minimal_run(oracle, datasets):
+    """burnin = 0 returns the initial state as iteration 0; nsamples = 2 is the shortest run."""
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    K = 2
+    ip, th = _init_full(K, X.shape[1], 4)
+    for grid in (False, True):
+        g = B.gibbs_full(X, 2, K, burnin=0, initial_pi=ip, initial_theta=th, seed=1, grid_path=grid)
+        assert g["theta"].shape == (K, 5, 2) and g["z"].shape == (2, 100)
+        _close(g["theta"][:, :, 0], th, rtol=0)
+        _close(g["pi"][0], ip, rtol=0)
+        assert g["alpha"][0, 0] == 1.0
+    iz = RRng(3).sample_int(K, 100)
+    c = B.gibbs_collapsed(X, 2, K, burnin=0, initial_K=iz, seed=1)
+    assert np.array_equal(c["z"][0], iz)
+
+
+def test_edge_large_k_chain_path(oracle):
+    """K = 72 clusters on the chain kernels: 4 labels per lane in the collapsed kernel, K x K cost matrix in global
+    memory (above COST_SMEM_MAX), Hungarian relabelling."""
+    _need_gpu()
+    rng = np.random.default_rng(9)
+    N, P, K = 300, 6, 72
+    X = (rng.random((N, P)) < 0.5).astype(np.int32)
+    ns, burnin, br = 10, 4, 2
+    iz = RRng(3).sample_int(K, N)
+    r = oracle.gibbs_collapsed(X, iz, ns, K, burnin=burnin, relabel=True, burnrelabel=br, seed=2, use_ref=False)
+    g = B.gibbs_collapsed(X, ns, K, burnin=burnin, relabel=True, burnrelabel=br, initial_K=iz,
+                          replay=_replay_of(r, keys=("alpha",)))
+    assert np.array_equal(g["z_original"], r.tail()["z_original"])
+    S = g["permutations"].shape[0]
+    assert np.array_equal(np.sort(g["permutations"], 1), np.tile(np.arange(K), (S, 1)))
+
+
+def test_invalid_arguments_are_rejected(datasets):
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    for kw, code in ((dict(nsamples=1, K=2), -1), (dict(nsamples=10, K=0), -1), (dict(nsamples=10, K=300), -1),
+                     (dict(nsamples=10, K=2, burnin=10), -1), (dict(nsamples=10, K=2, beta=0.0), -1),
+                     (dict(nsamples=20, K=2, burnin=1, relabel=True), -1)):
+        with pytest.raises(_lib.BmmError) as e:
+            B.gibbs_collapsed(X, kw.pop("nsamples"), kw.pop("K"), **kw)
+        assert e.value.code == code, kw
