@@ -89,17 +89,35 @@ __device__ __forceinline__ double update_alpha_dev(Stream &s, double alpha_old, 
 // rmultinom(1, prob, K) replay rule (R nmath rmultinom.c / rbinom.c inversion branch, SURVEY App. A
 // items 3-4): sequential conditional binomials; one recorded uniform per non-zero category visited.
 // `getp(k)` returns prob[k]; u points at this draw's recorded uniforms.  Returns the 0-based label.
-// p_tot is a double here (the reference's is long double): decisions can differ only when a uniform
-// lies within an ulp of a boundary.
+// The reference keeps the running total p_tot in `long double` (x87, 64-bit significand).  A plain double
+// total goes wrong exactly where it matters: when the categories left have equal probabilities (clusters
+// with identical sufficient statistics) pp = p_k / p_tot sits on the 0.5 switch of the rbinom inversion
+// rule, and which side it lands on must not be decided by cancellation noise of the subtractions.  The
+// total is therefore carried as an unevaluated double-double sum (error-free additions, >= 106 bits),
+// which reproduces the extended-precision result whenever that result is itself above its own noise.
+struct DD { double hi, lo; };
+__device__ __forceinline__ DD dd_add(DD x, double y) {
+    const double s = __dadd_rn(x.hi, y), bb = __dadd_rn(s, -x.hi);
+    double e = __dadd_rn(__dadd_rn(x.hi, -__dadd_rn(s, -bb)), __dadd_rn(y, -bb));
+    e = __dadd_rn(e, x.lo);
+    const double hi = __dadd_rn(s, e);
+    return DD{hi, __dadd_rn(e, -__dadd_rn(hi, -s))};
+}
+__device__ __forceinline__ double dd_div_into(double a, DD t) {   // (double)(a / t)
+    const double q1 = a / t.hi;
+    const double r = __dadd_rn(__fma_rn(-q1, t.hi, a), -__dmul_rn(q1, t.lo));
+    return __dadd_rn(q1, r / t.hi);
+}
+
 template <typename GetP>
 __device__ __forceinline__ int rmultinom1_replay(int K, GetP getp, const double *__restrict__ u) {
-    double p_tot = 0.0;
-    for (int k = 0; k < K; ++k) p_tot += getp(k);
+    DD p_tot{0.0, 0.0};
+    for (int k = 0; k < K; ++k) p_tot = dd_add(p_tot, getp(k));
     int slot = 0;
     for (int k = 0; k < K - 1; ++k) {
         double pk = getp(k);
         if (pk != 0.0) {
-            double pp = pk / p_tot;
+            double pp = dd_div_into(pk, p_tot);
             int got;
             if (pp < 1.0) {
                 double p = fmin(pp, 1.0 - pp), q = 1.0 - p;
@@ -111,7 +129,7 @@ __device__ __forceinline__ int rmultinom1_replay(int K, GetP getp, const double 
             }
             if (got) return k;
         }
-        p_tot -= pk;
+        p_tot = dd_add(p_tot, -pk);
     }
     return K - 1;
 }
