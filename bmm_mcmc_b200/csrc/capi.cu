@@ -2,10 +2,13 @@
 // de-duplication of X, device-resident plans, launches, result download.  No CPU fallback: every
 // compute entry point needs a CUDA device and fails with BMM_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -41,15 +44,62 @@ int fail(int code, const std::string &msg) {
             return fail(BMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
 
+// Device allocations are recycled across calls: cudaMalloc / cudaFree of the multi-GB history buffers
+// cost 10-200 ms per call (cudaFree synchronises and unmaps), more than the sampling itself at C2 size.
+// Freed blocks go to a per-device free list keyed by size and are handed out again on an exact-size
+// match (repeated runs of one configuration, which is what a caller looping over data sets or seeds
+// does); bmm_release_cache() returns everything to the driver, and so does an out-of-memory retry.
+struct DevCache {
+    std::mutex m;
+    std::map<std::pair<int, size_t>, std::vector<void *>> free_list;
+    size_t cached = 0;
+    void *take(int dev, size_t n) {
+        std::lock_guard<std::mutex> g(m);
+        auto it = free_list.find({dev, n});
+        if (it == free_list.end() || it->second.empty()) return nullptr;
+        void *p = it->second.back();
+        it->second.pop_back();
+        cached -= n;
+        return p;
+    }
+    void give(int dev, size_t n, void *p) {
+        std::lock_guard<std::mutex> g(m);
+        free_list[{dev, n}].push_back(p);
+        cached += n;
+    }
+    void release() {
+        std::lock_guard<std::mutex> g(m);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : free_list) {
+            cudaSetDevice(kv.first.first);
+            for (void *p : kv.second) cudaFree(p);
+        }
+        free_list.clear();
+        cached = 0;
+        cudaSetDevice(cur);
+    }
+} g_cache;
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    int dev = 0;
+    ~DevBuf() { if (p) g_cache.give(dev, bytes, p); }
     cudaError_t alloc(size_t n, bool zero = true) {
         bytes = n;
         if (n == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) { p = nullptr; return e; }
+        cudaGetDevice(&dev);
+        p = g_cache.take(dev, n);
+        if (!p) {
+            cudaError_t e = cudaMalloc(&p, n);
+            if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
+                cudaGetLastError();
+                g_cache.release();
+                e = cudaMalloc(&p, n);
+            }
+            if (e != cudaSuccess) { p = nullptr; return e; }
+        }
         return zero ? cudaMemset(p, 0, n) : cudaSuccess;
     }
     template <typename T> T *as() const { return (T *)p; }
@@ -699,6 +749,11 @@ int bmm_host_alloc(uint64_t bytes, void **ptr_out) {
     return BMM_OK;
 }
 
+int bmm_release_cache(void) {
+    g_cache.release();
+    return BMM_OK;
+}
+
 int bmm_host_free(void *ptr) {
     if (ptr) CU(cudaFreeHost(ptr));
     return BMM_OK;
@@ -783,11 +838,19 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
     if (out->counts) a.flags |= BMM_FLAG_PROBE_COUNTS;
     bmm_plan *pl = nullptr;
+    static const bool trace = getenv("BMM_TRACE") != nullptr;   // wall-clock phases of the one-shot call on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     int rc = bmm_plan_create(sampler, &a, init, &pl);
     if (rc) return rc;
+    const double t1 = now();
     rc = bmm_plan_run(pl);
+    if (!rc && trace) rc = bmm_plan_sync(pl);
+    const double t2 = now();
     if (!rc) rc = bmm_plan_fetch(pl, out);
+    const double t3 = now();
     bmm_plan_destroy(pl);
+    if (trace) fprintf(stderr, "bmm trace: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 

@@ -183,6 +183,9 @@ int bmm_dist_finalize(void);
 /* Page-locked host memory for output buffers (cudaHostAlloc): D2H into it runs at PCIe speed.    */
 int bmm_host_alloc(uint64_t bytes, void **ptr_out);
 int bmm_host_free(void *ptr);
+/* Device buffers of finished calls are kept for reuse by the next call of the same shape (cudaMalloc /
+ * cudaFree of GB-sized histories cost more than the sampling); this returns them to the driver.      */
+int bmm_release_cache(void);
 const char *bmm_last_error(void);
 int bmm_device_count(void);
 uint64_t bmm_launch_count(void);   /* kernels launched by this library so far */
