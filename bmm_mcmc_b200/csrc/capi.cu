@@ -376,7 +376,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
     b.counts_out = pl->counts_out.as<int>();
     b.probs_f32 = nullptr; b.perm_cur = pl->perm_cur.as<int>(); b.theta_rel_out = pl->theta_rel_out.as<double>();
-    if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && P % 64 == 0 && (K > 32 || P > 112)) {
+    if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && (K > 32 || P > 112)) {
         CU(pl->lp_table.alloc(bmm::big_lp_table_bytes(P)));
         CU(pl->lp_bias.alloc(128 * 8));
         if (!pl->zhist.p) return fail(BMM_ERR_INVALID, "internal: allocation buffer missing");

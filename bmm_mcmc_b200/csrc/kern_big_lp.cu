@@ -46,14 +46,16 @@ constexpr double LOG2E_D = 1.4426950408889634;
 __global__ void lp_table_kernel(const BigParams p) {
     const int K = p.K, P = p.P;
     unsigned char *img = (unsigned char *)p.lp_table;
-    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < P; d += gridDim.x * blockDim.x) {
-        const double *w1 = p.w1 + (size_t)K * d, *w0 = p.w0 + (size_t)K * d;
+    const int Ppad = (P + LP_DK - 1) / LP_DK * LP_DK;   // features beyond P: zero weights (their bits are zero too)
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < Ppad; d += gridDim.x * blockDim.x) {
+        const bool real = d < P;
+        const double *w1 = p.w1 + (size_t)K * (real ? d : 0), *w0 = p.w0 + (size_t)K * (real ? d : 0);
         double mean = 0.0;
         for (int k = 0; k < K; ++k) mean += w1[k] - w0[k];
         mean /= K;
         unsigned char *col = img + (size_t)(d >> 3) * LP_NCOL * 16 + (d & 7) * 2;
         for (int k = 0; k < LP_KC; ++k) {
-            const double D = k < K ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
+            const double D = (real && k < K) ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
             const __nv_bfloat16 hi = __double2bfloat16(D);
             const double r1 = D - (double)__bfloat162float(hi);
             const __nv_bfloat16 mid = __double2bfloat16(r1);
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int K = p.K, W = p.W;
-    const int nsteps = p.P / LP_DK;
+    const int nsteps = (p.P + LP_DK - 1) / LP_DK;   // the last step may be partial: missing words read as zero bits
     float *bias = (float *)(smem + LpSmem::BIAS_OFF);
     uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[2], empty[2], accfull, accempty
     uint32_t *tmem_slot = (uint32_t *)(bars + 6);
@@ -143,10 +145,19 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
             const long long i = tile * 128 + t;
             const bool valid = i < p.N_local;
             const uint32_t *xb = p.xbits + (size_t)(valid ? i : 0) * W;
-            uint2 nxt = valid ? *(const uint2 *)xb : make_uint2(0u, 0u);
+            // two 32-bit words per step; rows are only 4-byte aligned when W is odd, so the words are read singly
+            auto load_step = [&](int c) {
+                uint2 v = make_uint2(0u, 0u);
+                if (valid) {
+                    if (2 * c < W) v.x = xb[2 * c];
+                    if (2 * c + 1 < W) v.y = xb[2 * c + 1];
+                }
+                return v;
+            };
+            uint2 nxt = load_step(0);
             for (int c = 0; c < nsteps && ok; ++c, ++g) {
                 const uint2 cur = nxt;
-                if (c + 1 < nsteps && valid) nxt = *(const uint2 *)(xb + 2 * (c + 1));
+                if (c + 1 < nsteps) nxt = load_step(c + 1);
                 uint4 ex[8];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
@@ -359,13 +370,13 @@ __global__ void __launch_bounds__(128, 2) lp_counts_kernel(const BigParams p, co
 
 }  // namespace
 
-// float path, K <= 128 clusters, P a multiple of 64 (packed rows then are 8-byte aligned per step)
+// float path, K <= 128 clusters, any P (padded to a multiple of 64 with zero weights)
 bool big_lp_supported(const BigParams &p) {
-    return p.precision == 1 && p.K <= LP_KC && p.P % LP_DK == 0 && p.P >= LP_DK && p.ru == nullptr &&
+    return p.precision == 1 && p.K <= LP_KC && p.ru == nullptr &&
            p.loglik_out == nullptr && p.lp_table != nullptr;
 }
 
-size_t big_lp_table_bytes(int P) { return (size_t)P / 8 * LP_NCOL * 16; }
+size_t big_lp_table_bytes(int P) { return (size_t)((P + LP_DK - 1) / LP_DK * LP_DK) / 8 * LP_NCOL * 16; }
 
 cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     static bool attr_set = false;
@@ -375,7 +386,7 @@ cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStr
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    lp_table_kernel<<<(p.P + 63) / 64, 64, 0, st>>>(p);
+    lp_table_kernel<<<(p.P + 63) / 64, 64, 0, st>>>(p);   // one thread per (padded) feature
     lp_bias_kernel<<<LP_KC, 128, 0, st>>>(p);
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     const int ctas = (int)(ntiles < sm_count ? ntiles : sm_count);
