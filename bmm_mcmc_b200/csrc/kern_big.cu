@@ -333,7 +333,8 @@ cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st) {
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     static const bool no_tc = getenv("BMM_NO_TC") != nullptr;  // A/B switch: CUDA-core float path
     if (!no_tc && !(p.flags & 32u /* BMM_FLAG_NO_TENSOR */)) {
-        if (big_tc_supported(p)) return launch_big_sweep_tc(p, j, sm_count, st);
+        static const bool no_ws = getenv("BMM_TC_WS") && getenv("BMM_TC_WS")[0] == '0';   // A/B: single-role kernel
+        if (big_tc_supported(p)) return no_ws ? launch_big_sweep_tc(p, j, sm_count, st) : launch_big_sweep_ws(p, j, sm_count, st);
         if (big_lp_supported(p)) return launch_big_sweep_lp(p, j, sm_count, st);
     }
     long long blocks = ((long long)p.N_local + BIG_THREADS - 1) / BIG_THREADS;

@@ -1,0 +1,336 @@
+// Warp-specialised tensor-core z-sweep for K <= 32, P <= 112 (BASELINE config C4): the same two
+// contractions as kern_big_tc.cu (loglh = X D^T on tcgen05; counts = [X|1]^T onehot(z)), but the work
+// of one 128-observation tile is split over dedicated warps connected by mbarrier rings, so the bit
+// expansion, the tensor pipe and the per-observation epilogue run concurrently instead of in lockstep
+// (the ncu profile of the single-role kernel showed its four warpgroups convoying: ALU phase and
+// tensor phase of a round did not overlap).
+//
+//   warps 0-3    producers: packed row -> bf16 A stage (ring of NS stages) -> arrive full_A
+//   warp  4      one thread issues GEMM1(k) into accumulator k % NA, tcgen05.commit publishes it
+//   warp  5      one thread issues GEMM2(k) from A stage + one-hot stage; its commits free both stages
+//   warps 8-19   three epilogue warpgroups (tile k goes to warpgroup k % 3): TMEM lane = observation,
+//                softmax, Philox inverse-CDF draw, 1-byte allocation, one-hot row -> B2 stage
+//
+// Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace bmm {
+namespace {
+
+constexpr int WS_KC = 32;
+constexpr int WS_NS = 5;      // A stages
+constexpr int WS_NA = 4;      // GEMM1 accumulators (96 TMEM columns each)
+constexpr int WS_NB = 4;      // one-hot stages
+constexpr int WS_NEPI = 3;    // epilogue warpgroups (4 at 80 registers/thread measured no faster)
+constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
+constexpr int WS_CHUNK = 2048;
+constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
+constexpr int WS_B1_ROW = 3 * WS_KC * 16;
+
+// shared memory: [A ring][B2 ring][B1 table][bias][barriers][tmem slot].  GEMM2 reads 16 chunks (M = 128)
+// from an A stage that only holds NCH + 1: the rows beyond are whatever follows (other stages, one-hot
+// rows, the weight table -- all finite bf16) and land in accumulator lanes that are never read.
+template <int NCH>
+struct WsLayout {
+    static constexpr int A_STAGE = (NCH + 1) * WS_CHUNK;
+    static constexpr int B2_OFF = WS_NS * A_STAGE;
+    static constexpr int B1_OFF = B2_OFF + WS_NB * WS_B2_BYTES;
+    static constexpr int BIAS_OFF = B1_OFF + NCH * WS_B1_ROW;
+    static constexpr int BAR_OFF = BIAS_OFF + WS_KC * 4;
+    static constexpr int NBAR = 2 * WS_NS + 2 * WS_NA + 2 * WS_NB + 1;
+    static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16;
+    static_assert(B1_OFF + NCH * WS_B1_ROW - (WS_NS - 1) * A_STAGE >= 16 * WS_CHUNK, "GEMM2 over-read must stay inside finite bf16 data");
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigParams p, const int j) {
+    using L = WsLayout<NCH>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = p.K, P = p.P, W = p.W;
+    constexpr int ONES = NCH * 8;
+    constexpr int NW = (NCH + 3) / 4;
+    unsigned char *B1 = smem + L::B1_OFF;
+    float *bias = (float *)(smem + L::BIAS_OFF);
+    uint64_t *bars = (uint64_t *)(smem + L::BAR_OFF);
+    uint32_t *tmem_slot = (uint32_t *)(bars + L::NBAR);
+    const uint32_t full_a = smem_u32(bars), free_a = full_a + 8 * WS_NS;
+    const uint32_t acc_full = free_a + 8 * WS_NS, acc_free = acc_full + 8 * WS_NA;
+    const uint32_t b2_full = acc_free + 8 * WS_NA, b2_free = b2_full + 8 * WS_NB;
+    const uint32_t all_done = b2_free + 8 * WS_NB;
+
+    // ---- prologue ----
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 192) {
+        for (int s = 0; s < WS_NS; ++s) { mbar_init(full_a + 8 * s, 128); mbar_init(free_a + 8 * s, 1); }
+        for (int a = 0; a < WS_NA; ++a) { mbar_init(acc_full + 8 * a, 1); mbar_init(acc_free + 8 * a, 128); }
+        for (int b = 0; b < WS_NB; ++b) { mbar_init(b2_full + 8 * b, 128); mbar_init(b2_free + 8 * b, 1); }
+        mbar_init(all_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < WS_KC * NCH * 8; e += WS_THREADS) {
+        const int k = e % WS_KC, d = e / WS_KC;
+        double D = 0.0;
+        if (k < K && d < P) D = (p.w1[k + K * d] - p.w0[k + K * d]) * 1.4426950408889634;
+        const __nv_bfloat16 hi = __double2bfloat16(D);
+        const double r1 = D - (double)__bfloat162float(hi);
+        const __nv_bfloat16 mid = __double2bfloat16(r1);
+        const __nv_bfloat16 lo = __double2bfloat16(r1 - (double)__bfloat162float(mid));
+        unsigned char *cell = B1 + (d >> 3) * WS_B1_ROW + k * 16 + (d & 7) * 2;
+        *(__nv_bfloat16 *)(cell + 0 * WS_KC * 16) = hi;
+        *(__nv_bfloat16 *)(cell + 1 * WS_KC * 16) = mid;
+        *(__nv_bfloat16 *)(cell + 2 * WS_KC * 16) = lo;
+    }
+    for (int k = tid; k < WS_KC; k += WS_THREADS) {
+        float b = -INFINITY;
+        if (k < K) {
+            double s0 = 0.0;
+            for (int d = 0; d < P; ++d) s0 += p.w0[k + K * d];
+            b = (float)((p.lpi[k] + s0) * 1.4426950408889634);
+        }
+        bias[k] = b;
+    }
+    // the ones column of [X | 1] (chunk NCH of every A stage) and zeroed one-hot stages
+    for (int e = tid; e < WS_NS * 128; e += WS_THREADS)
+        *(uint4 *)(smem + (e / 128) * L::A_STAGE + NCH * WS_CHUNK + (e % 128) * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
+    for (int e = tid; e < WS_NB * WS_B2_BYTES / 16; e += WS_THREADS) *(uint4 *)(smem + L::B2_OFF + e * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc2 = tmem_base + WS_NA * 3 * WS_KC;
+    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    const long long T = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+    bool ok = true;
+
+    if (warp < 4) {
+        // ================= producers =================
+        const int t = tid;
+        auto load_row = [&](long long k, uint32_t (&xw)[NW]) {
+            const long long i = (blockIdx.x + k * gridDim.x) * 128 + t;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) xw[w] = 0u;
+            if (k < T && i < p.N_local) {
+                const uint32_t *xb = p.xbits + (size_t)i * W;
+                if (NW == 2 && W == 2) { const uint2 v = *(const uint2 *)xb; xw[0] = v.x; xw[NW - 1] = v.y; }
+                else {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) if (w < W) xw[w] = xb[w];
+                }
+            }
+        };
+        // rows of the next PF tiles are kept in flight: one tile lasts ~0.3 us, a DRAM round trip ~0.8 us
+        constexpr int PF = 4;
+        uint32_t ring[PF][NW];
+#pragma unroll
+        for (int d = 0; d < PF; ++d) load_row(d, ring[d]);
+        for (long long k0 = 0; k0 < T && ok; k0 += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                const long long k = k0 + d;
+                if (k >= T || !ok) break;
+                uint4 ex[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t byte = ring[d][c >> 2] >> ((c & 3) * 8);
+                    ex[c] = make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
+                }
+                load_row(k + PF, ring[d]);
+                const int s = (int)(k % WS_NS);
+                const long long n = k / WS_NS;
+                if (n > 0) ok = mbar_wait(free_a + 8 * s, (uint32_t)((n - 1) & 1));
+                if (!ok) break;
+                unsigned char *A = smem + s * L::A_STAGE;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) *(uint4 *)(A + c * WS_CHUNK + t * 16) = ex[c];
+                fence_async_smem();
+                mbar_arrive(full_a + 8 * s);
+            }
+        }
+    } else if (warp == 4) {
+        // ================= GEMM1 issuer =================
+        // (one thread per GEMM: a single thread issuing both was the bottleneck -- ~300 dependent
+        //  instructions per tile; descriptors are base + constant offset in the 16-byte address field)
+        if (tid == 128) {
+            constexpr uint32_t IDESC1 = umma_idesc(128, 3 * WS_KC, 0, 0);
+            const uint64_t da0 = umma_desc(smem_u32(smem), WS_CHUNK, 128), db0 = umma_desc(smem_u32(B1), WS_B1_ROW, 128);
+            for (long long k = 0; k < T && ok; ++k) {
+                const int s = (int)(k % WS_NS), a = (int)(k % WS_NA);
+                const long long na = k / WS_NA;
+                ok = mbar_wait(full_a + 8 * s, (uint32_t)((k / WS_NS) & 1));
+                if (ok && na > 0) ok = mbar_wait(acc_free + 8 * a, (uint32_t)((na - 1) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < NCH / 2; ++kk)
+                    umma_bf16(tmem_base + (uint32_t)(a * 3 * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
+                              db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
+                umma_commit(acc_full + 8 * a);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ================= GEMM2 issuer =================
+        if (tid == 160) {
+            constexpr uint32_t IDESC2 = umma_idesc(128, WS_KC, 1, 1);
+            const uint64_t da0 = umma_desc(smem_u32(smem), 128, WS_CHUNK), db0 = umma_desc(smem_u32(smem + L::B2_OFF), 128, WS_CHUNK);
+            for (long long q = 0; q < T && ok; ++q) {
+                const int s = (int)(q % WS_NS), b = (int)(q % WS_NB);
+                ok = mbar_wait(b2_full + 8 * b, (uint32_t)((q / WS_NB) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4), db = db0 + (uint64_t)((b * WS_B2_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(free_a + 8 * s);
+                umma_commit(b2_free + 8 * b);
+            }
+            umma_commit(all_done);
+        }
+        __syncwarp();
+    } else if (warp >= 8) {
+        // ================= epilogue warpgroups =================
+        const int e = (warp - 8) >> 2, t = (tid - 256) & 127, wq = warp & 3;
+        const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
+        const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+        uint8_t *zrow = p.zhist ? p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local : nullptr;
+        for (long long k = e; k < T && ok; k += WS_NEPI) {
+            const long long i = (blockIdx.x + k * gridDim.x) * 128 + t;
+            const bool valid = i < p.N_local;
+            const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
+            const float u = ((float)(((gi & 1) ? rnd.z : rnd.x) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+            const int a = (int)(k % WS_NA), b = (int)(k % WS_NB);
+            ok = mbar_wait(acc_full + 8 * a, (uint32_t)((k / WS_NA) & 1));
+            if (!ok) break;
+            tc_fence_after();
+            float l[WS_KC];
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * 3 * WS_KC + part * WS_KC), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) l[q] = part == 0 ? __uint_as_float(v[q]) + bias[q] : l[q] + __uint_as_float(v[q]);
+            }
+            tc_fence_before();
+            mbar_arrive(acc_free + 8 * a);      // accumulator a may be overwritten by GEMM1(k + NA)
+            float mx = l[0];
+#pragma unroll
+            for (int q = 1; q < WS_KC; ++q) mx = fmaxf(mx, l[q]);
+            float run = 0.f;
+            if (p.probs_out == nullptr && p.probs_f32 == nullptr) {
+#pragma unroll
+                for (int q = 0; q < WS_KC; ++q) { run += ex2_ftz(l[q] - mx); l[q] = run; }
+            } else {
+                float sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < WS_KC; ++q) { l[q] = ex2_ftz(l[q] - mx); sum += l[q]; }
+                const float inv = 1.f / sum;
+                if (valid && p.probs_out) {
+#pragma unroll
+                    for (int q = 0; q < WS_KC; ++q)
+                        if (q < K) p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * q] = (double)(l[q] * inv);
+                }
+                if (valid && p.probs_f32) {
+#pragma unroll
+                    for (int q = 0; q < WS_KC; ++q)
+                        if (q < K) p.probs_f32[(size_t)i * K + q] = l[q] * inv;
+                }
+#pragma unroll
+                for (int q = 0; q < WS_KC; ++q) { run += l[q]; l[q] = run; }
+            }
+            if (!(run > 0.f) || !isfinite(run)) *p.status = -9;  // BMM_ERR_PROB
+            const float target = u * run;
+            int z = 0;
+#pragma unroll
+            for (int q = 0; q < WS_KC; ++q) z += (l[q] <= target) ? 1 : 0;
+            z = min(z, K - 1);
+            if (valid && zrow) zrow[i] = (uint8_t)(z + 1);
+            const long long nb = k / WS_NB;
+            if (nb > 0) ok = mbar_wait(b2_free + 8 * b, (uint32_t)((nb - 1) & 1));
+            if (!ok) break;
+            {
+                unsigned char *B2 = smem + L::B2_OFF + b * WS_B2_BYTES;
+                const uint32_t h = valid ? ((z & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+                const int wsel = (z & 7) >> 1, csel = z >> 3;
+                const uint4 hot = make_uint4(wsel == 0 ? h : 0u, wsel == 1 ? h : 0u, wsel == 2 ? h : 0u, wsel == 3 ? h : 0u);
+#pragma unroll
+                for (int cc = 0; cc < WS_KC / 8; ++cc)
+                    *(uint4 *)(B2 + cc * WS_CHUNK + t * 16) = (csel == cc) ? hot : make_uint4(0u, 0u, 0u, 0u);
+            }
+            fence_async_smem();
+            mbar_arrive(b2_full + 8 * b);
+        }
+    }
+    // ---- flush the counts: TMEM lane d of acc2 holds V_kd (d < P) or c_k (d == ONES) ----
+    if (warp >= 8 && warp < 12) {
+        const int t = tid - 256;
+        if (ok && T > 0) ok = mbar_wait(all_done, 0u);
+        if (ok && T > 0) {
+            tc_fence_after();
+            int *gcnt = p.counts + (size_t)(j & 1) * (K + K * P);
+            uint32_t v[32];
+            tmem_ld32(acc2 + ((uint32_t)((warp & 3) * 32) << 16), v);
+            tmem_ld_wait();
+            if (t < P || t == ONES) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int n = (int)(__uint_as_float(v[q]) + 0.5f);
+                    if (q < K && n) atomicAdd(t == ONES ? &gcnt[q] : &gcnt[K + q + K * t], n);
+                }
+            }
+        }
+    }
+    if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int NCH>
+cudaError_t launch_ws_nch(const BigParams &p, int j, int sm_count, cudaStream_t st) {
+    using L = WsLayout<NCH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(big_sweep_ws_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    long long ctas = ntiles < sm_count ? ntiles : sm_count;
+    if (ctas < 1) ctas = 1;
+    big_sweep_ws_kernel<NCH><<<(int)ctas, WS_THREADS, L::TOTAL, st>>>(p, j);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st) {
+    switch ((p.P + 15) / 16) {
+        case 1: return launch_ws_nch<2>(p, j, sm_count, st);
+        case 2: return launch_ws_nch<4>(p, j, sm_count, st);
+        case 3: return launch_ws_nch<6>(p, j, sm_count, st);
+        case 4: return launch_ws_nch<8>(p, j, sm_count, st);
+        case 5: return launch_ws_nch<10>(p, j, sm_count, st);
+        case 6: return launch_ws_nch<12>(p, j, sm_count, st);
+        default: return launch_ws_nch<14>(p, j, sm_count, st);
+    }
+}
+
+}  // namespace bmm

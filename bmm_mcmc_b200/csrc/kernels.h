@@ -130,6 +130,8 @@ cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st);
 // tcgen05 sweep (kern_big_tc.cu): log-likelihood and sufficient statistics as tensor-core contractions
 bool big_tc_supported(const BigParams &p);
 cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStream_t st);
+// same shapes, warp-specialised (producer / MMA / epilogue warps over mbarrier rings): kern_big_ws.cu
+cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st);
 // large-P / large-K tcgen05 path (kern_big_lp.cu): pipelined k-loop contraction + counts kernel
 bool big_lp_supported(const BigParams &p);
 size_t big_lp_table_bytes(int P);
