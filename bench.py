@@ -325,7 +325,7 @@ def run_grid(a):
     from bmm_mcmc_b200 import _lib, api, dist as bdist
     L = _lib.lib()
     assert L.bmm_device_count() > local, "no CUDA device: the product path has no CPU fallback"
-    bdist.init(rank, world, local)
+    p2p = bdist.init(rank, world, local)
     N, P, K, ns, burnin = w["N"], w["P"], w["K"], w["nsamples"], w["burnin"]
     lo, hi = bdist.shard_rows(N, world, rank)
     X = synth_rows(lo, hi, P, K)
@@ -411,7 +411,8 @@ def run_grid(a):
         "config": {"workload": "%s, nsamples=%d (one step = %d sweeps), relabel=%s burnrelabel=%d"
                                % (w["label"], ns, ns - 1, relabel, br),
                    "N": N, "rows_per_gpu": n_local,
-                   "parallelism": "rows block-partitioned over GPUs; int32 counts all-reduced (NCCL) every sweep"
+                   "parallelism": ("rows block-partitioned over GPUs; int32 counts all-reduced every sweep by %s"
+                                   % ("a one-shot push over IPC-mapped NVLink peer memory" if p2p else "NCCL"))
                                   if world > 1 else "single GPU",
                    "l2": "per-sweep input (%.0f MB of packed rows + allocations) vs 126 MB L2; sweeps alternate "
                          "history rows" % (n_local * bytes_per_update / 1e6)},

@@ -415,8 +415,12 @@ int run_big(bmm_plan *pl) {
         CU(cudaEventRecord(pl->sweep_ev[2 * j], pl->stream));
         CU(bmm::launch_big_sweep(bj, j, pl->sm_count, pl->stream));
         CU(cudaEventRecord(pl->sweep_ev[2 * j + 1], pl->stream));
-        if (sharded && bmm::dist_allreduce_i32(pl->counts.as<int>() + (size_t)(j & 1) * ncnt, ncnt, pl->stream))
-            return fail(BMM_ERR_NCCL, bmm::dist_error());
+        if (sharded) {   // counts of all ranks: one-shot push over peer memory when attached, else NCCL
+            int *cj = pl->counts.as<int>() + (size_t)(j & 1) * ncnt;
+            const int rc_ar = bmm::dist_p2p_ready(ncnt) ? bmm::dist_p2p_allreduce_i32(cj, ncnt, pl->status.as<int>(), pl->stream)
+                                                         : bmm::dist_allreduce_i32(cj, ncnt, pl->stream);
+            if (rc_ar) return fail(BMM_ERR_NCCL, bmm::dist_error());
+        }
         if (pl->relabel && j == burnin - 1) {          // my_stephens_batch (full_gibbs.cpp:163-165)
             float *cube = pl->cube_f.as<float>();
             int *sbp = pl->sb_perm.as<int>();

@@ -178,6 +178,13 @@ int bmm_plan_destroy(bmm_plan *plan);
 int bmm_dist_unique_id(uint8_t id_out[128]);
 int bmm_dist_init(int32_t rank, int32_t world, const uint8_t id[128], int32_t device);
 int bmm_dist_finalize(void);
+/* Optional one-shot all-reduce over NVLink peer memory for the per-sweep count exchange (replaces the
+ * NCCL call, which is latency-bound at a few KB).  After bmm_dist_init every rank calls
+ * bmm_dist_p2p_local(cap_ints, handle) -- cap_ints >= K + K*P of the largest run -- ships its 64-byte
+ * CUDA IPC handle to all ranks (rank order), and calls bmm_dist_p2p_attach(handles[world][64]).       */
+int bmm_dist_p2p_local(uint64_t cap_ints, uint8_t handle_out[64]);
+int bmm_dist_p2p_attach(const uint8_t *handles);
+int bmm_dist_p2p_detach(void);   /* back to NCCL; call on every rank if any attach failed */
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 /* Page-locked host memory for output buffers (cudaHostAlloc): D2H into it runs at PCIe speed.    */

@@ -50,12 +50,14 @@ dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_n_sharded_equals_unsharded(tmp_path):
+@pytest.mark.parametrize("p2p", ["0", "1"])
+def test_n_sharded_equals_unsharded(tmp_path, p2p):
+    """p2p = 1: counts exchanged by the one-shot push over IPC-mapped peer memory instead of NCCL."""
     import bmm_mcmc_b200 as B
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, BMM_ROOT=ROOT, BMM_OUT=str(tmp_path))
+    env = dict(os.environ, BMM_ROOT=ROOT, BMM_OUT=str(tmp_path), BMM_P2P=p2p)
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                     "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], check=True, env=env,
                    timeout=300)
