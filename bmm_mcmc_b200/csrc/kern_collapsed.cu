@@ -9,6 +9,8 @@
 // integers plus constants, so the values are identical to evaluating the logs in place.
 // Operation order inside one conditional follows the reference: per cluster a d-ordered sum of
 // (selected log - denominator), exp(LHS + logLH), division by the sum.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "stephens.cuh"
 
@@ -215,6 +217,168 @@ __global__ void __launch_bounds__(32) collapsed_kernel(const CollapsedParams p) 
     for (int e = lane; e < K * P1; e += 32) p.cnt[(size_t)c * K * P1 + e] = s.cnt[e];
     for (int e = lane; e < N; e += 32) p.z_cur[(size_t)c * N + e] = s.z[e];
     if (lane == 0) p.alpha_cur[c] = alpha_sh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// finite-K collapsed Gibbs, low-latency variant for K <= 32 clusters and P <= 8 variables (all the
+// bundled data sets).  The sweep is one long dependent chain, so what matters is the length of that
+// chain per update, not throughput: lane k keeps its cluster's sufficient statistics S_kd, N_k in
+// REGISTERS, an observation is one byte of bits, the four log tables sit in shared memory, the
+// normaliser is a log2(K)-step butterfly, and in Philox mode the draw compares u * total against the
+// running sums (no division).  The arithmetic of one conditional -- d-ordered sum of (selected log -
+// denominator), exp(LHS + logLH) -- is unchanged (collapsed_gibbs.cpp:105-130), so replay-mode parity
+// holds exactly as for the generic kernel.
+// ------------------------------------------------------------------------------------------------
+struct FastTabs { double *logB, *logG, *logBG, *logA; uint8_t *xs; };
+
+__host__ __device__ inline size_t collapsed_fast_extra(const CollapsedParams &p, char *base, FastTabs *t) {
+    const size_t n1 = (size_t)p.N + 1;
+    size_t off = 0;
+    double *logB = (double *)(base + off); off += n1 * 8;
+    double *logG = (double *)(base + off); off += n1 * 8;
+    double *logBG = (double *)(base + off); off += n1 * 8;
+    double *logA = (double *)(base + off); off += n1 * 8;
+    uint8_t *xs = (uint8_t *)(base + off); off += ((size_t)p.N + 15) & ~(size_t)15;
+    if (t) { t->logB = logB; t->logG = logG; t->logBG = logBG; t->logA = logA; t->xs = xs; }
+    return off;
+}
+
+template <int PM, int WIDTH>
+__global__ void __launch_bounds__(32) collapsed_fast_kernel(const CollapsedParams p) {
+    extern __shared__ __align__(16) char smem_raw[];
+    __shared__ double alpha_sh;
+    CSmem s;
+    const size_t base_bytes = collapsed_layout(p, smem_raw, &s);
+    FastTabs tb;
+    collapsed_fast_extra(p, smem_raw + base_bytes, &tb);
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const int K = p.K, P = p.P, N = p.N, W = p.W, ns = p.nsamples, P1 = P + 1;
+    const uint32_t chain = (uint32_t)(p.chain_offset + c);
+    const bool replay = p.ru != nullptr;
+    const size_t NK = (size_t)N * K;
+
+    for (int e = lane; e < N; e += 32) { tb.xs[e] = (uint8_t)(p.xbits[(size_t)e * W] & 0xFFu); s.z[e] = p.z_cur[(size_t)c * N + e]; }
+    for (int e = lane; e <= N; e += 32) { tb.logB[e] = p.logB[e]; tb.logG[e] = p.logG[e]; tb.logBG[e] = p.logBG[e]; }
+    for (int k = lane; k < K; k += 32) s.perm[k] = k;
+    int S[PM], Nk = 0;
+#pragma unroll
+    for (int d = 0; d < PM; ++d) S[d] = (lane < K && d < P) ? p.cnt[((size_t)c * K + lane) * P1 + d] : 0;
+    if (lane < K) Nk = p.cnt[((size_t)c * K + lane) * P1 + P];
+    if (lane == 0) alpha_sh = p.alpha_cur[c];
+    __syncthreads();
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    double alpha_tab = -1.0;
+    const uint2 key = make_uint2((uint32_t)p.seed, chain);
+    const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+
+    for (int j = p.j_begin; j < p.j_end; ++j) {
+        const double alpha = replay && p.ralpha ? p.ralpha[(size_t)c * ns + (j - 1)] : alpha_sh;
+        if (alpha != alpha_tab) {  // log(N_k + alpha/K) table (collapsed_gibbs.cpp:105)
+            for (int n = lane; n <= N; n += 32) tb.logA[n] = log(n + (alpha / K));
+            alpha_tab = alpha;
+            __syncwarp();
+        }
+        const double left_denom = log(N - 1 + alpha);
+        uint8_t *zrow = p.zhist + ((size_t)c * ns + j) * N;
+        double *stash_dst = stash_target(p, c, j);
+        const bool need_probs = stash_dst || p.probs_out || replay;
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        int a = s.z[0];
+        uint32_t xb = tb.xs[0];
+        for (int i = 0; i < N; ++i) {
+            if (!replay && (i & 63) == 0)
+                rnd = philox4x32_10(make_uint4((uint32_t)((i >> 1) + lane), 0u, sid, (uint32_t)j), key);
+            // next observation's byte and label are fetched now; they do not depend on this update
+            const int inext = i + 1 < N ? i + 1 : i;
+            const int a_next = s.z[inext];
+            const uint32_t xb_next = tb.xs[inext];
+            const int own = (lane == a);
+            const int Nk1 = Nk - own;
+            double v = 0.0;
+            if (lane < K && Nk1 > 0) {  // empty cluster: probability exactly 0 (collapsed_gibbs.cpp:104,131-133)
+                const double LHS = tb.logA[Nk1] - left_denom;
+                const double denom = tb.logBG[Nk1];
+                double sel[PM];
+#pragma unroll
+                for (int d = 0; d < PM; ++d) {
+                    const int xd = (xb >> d) & 1;
+                    const int Sd = S[d] - (own & xd);
+                    sel[d] = d < P ? (xd ? tb.logB[Sd] : tb.logG[Nk1 - Sd]) : 0.0;
+                }
+                double logLH = 0.0;
+#pragma unroll
+                for (int d = 0; d < PM; ++d) if (d < P) logLH += sel[d] - denom;
+                v = exp(LHS + logLH);
+            }
+            double tot = v;
+#pragma unroll
+            for (int off = 1; off < WIDTH; off <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+            if (!(tot > 0.0) || !isfinite(tot)) { if (lane == 0) p.status[c] = -9; }
+            int z;
+            if (need_probs) {
+                const double pr = v / tot;
+                if (lane < K) {
+                    if (stash_dst) stash_dst[i + (size_t)N * lane] = pr;
+                    if (p.probs_out) p.probs_out[((size_t)c * ns + j) * NK + i + (size_t)N * lane] = pr;
+                }
+                auto getp = [&](int k) { return __shfl_sync(0xffffffffu, pr, k); };
+                if (replay) z = rmultinom1_replay(K, getp, p.ru + (((size_t)c * ns + j) * N + i) * p.ru_slots);
+                else {
+                    const int src = (i & 63) >> 1;
+                    const uint32_t w0 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.z : rnd.x, src);
+                    const uint32_t w1 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.w : rnd.y, src);
+                    z = categorical_icdf(K, getp, u53(w0, w1));
+                }
+            } else {
+                const int src = (i & 63) >> 1;
+                const uint32_t w0 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.z : rnd.x, src);
+                const uint32_t w1 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.w : rnd.y, src);
+                const double target = u53(w0, w1) * tot;
+                double cum = v;                               // inclusive prefix sums over the lanes
+#pragma unroll
+                for (int off = 1; off < WIDTH; off <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, cum, off);
+                    if (lane >= off) cum += t;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, lane < K - 1 && target < cum);
+                z = hit ? __ffs(hit) - 1 : K - 1;
+            }
+            if (z != a) {
+                const int da = (lane == z) - (lane == a);     // +1 for the new cluster, -1 for the old one
+                Nk += da;
+#pragma unroll
+                for (int d = 0; d < PM; ++d) S[d] += da * (int)((xb >> d) & 1);
+                if (lane == 0) s.z[i] = (uint8_t)z;
+            }
+            if (lane == 0) zrow[i] = (uint8_t)(z + 1);
+            a = a_next;
+            xb = xb_next;
+        }
+        // the end-of-sweep code (theta estimates, relabelling) reads the statistics from shared memory
+        if (lane < K) {
+#pragma unroll
+            for (int d = 0; d < PM; ++d) if (d < P) s.cnt[lane * P1 + d] = S[d];
+            s.cnt[lane * P1 + P] = Nk;
+        }
+        __syncwarp();
+        collapsed_after_sweep(p, s, c, j, &alpha_sh, K, nullptr, 0);
+    }
+    if (lane < K) {
+#pragma unroll
+        for (int d = 0; d < PM; ++d) if (d < P) p.cnt[((size_t)c * K + lane) * P1 + d] = S[d];
+        p.cnt[((size_t)c * K + lane) * P1 + P] = Nk;
+    }
+    for (int e = lane; e < N; e += 32) p.z_cur[(size_t)c * N + e] = s.z[e];
+    if (lane == 0) p.alpha_cur[c] = alpha_sh;
+}
+
+template <int WIDTH>
+cudaError_t launch_fast_w(const CollapsedParams &p, int n_chains, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(collapsed_fast_kernel<8, WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    collapsed_fast_kernel<8, WIDTH><<<n_chains, 32, smem, st>>>(p);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,10 +632,30 @@ cudaError_t launch_slots(const CollapsedParams &p, int n_chains, size_t smem, cu
 
 }  // namespace
 
-size_t collapsed_smem_bytes(const CollapsedParams &p) { return collapsed_layout(p, (char *)0, nullptr); }
+static bool collapsed_fast_ok(const CollapsedParams &p) {
+    return !p.dp && p.K <= 32 && p.P <= 8 &&
+           collapsed_layout(p, (char *)0, nullptr) + collapsed_fast_extra(p, (char *)0, nullptr) <= 200 * 1024;
+}
+
+size_t collapsed_smem_bytes(const CollapsedParams &p) {
+    return collapsed_layout(p, (char *)0, nullptr) + (collapsed_fast_ok(p) ? collapsed_fast_extra(p, (char *)0, nullptr) : 0);
+}
 
 cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_t st) {
     const size_t smem = collapsed_smem_bytes(p);
+    // Measured on B200 (K3_N1000_P5 / K2_N100_P5): one chain 1.21e6 vs 0.86e6 updates/s in favour of the
+    // register-resident kernel, 1024 chains 6.4e8 vs 8.4e8 in favour of the generic one (with several
+    // warps per scheduler its shorter instruction stream wins), so the choice follows the chain count.
+    // BMM_COLLAPSED_KERNEL=fast|generic overrides.
+    static const char *force = getenv("BMM_COLLAPSED_KERNEL");
+    const bool want_fast = force ? force[0] == 'f' : n_chains <= 148;
+    if (want_fast && collapsed_fast_ok(p)) {
+        if (p.K <= 2) return launch_fast_w<2>(p, n_chains, smem, st);
+        if (p.K <= 4) return launch_fast_w<4>(p, n_chains, smem, st);
+        if (p.K <= 8) return launch_fast_w<8>(p, n_chains, smem, st);
+        if (p.K <= 16) return launch_fast_w<16>(p, n_chains, smem, st);
+        return launch_fast_w<32>(p, n_chains, smem, st);
+    }
     if (p.K <= 32) return launch_slots<1>(p, n_chains, smem, st);
     if (p.K <= 64) return launch_slots<2>(p, n_chains, smem, st);
     if (p.K <= 128) return launch_slots<4>(p, n_chains, smem, st);
