@@ -647,7 +647,7 @@ cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_
     // register-resident kernel, 1024 chains 6.4e8 vs 8.4e8 in favour of the generic one (with several
     // warps per scheduler its shorter instruction stream wins), so the choice follows the chain count.
     // BMM_COLLAPSED_KERNEL=fast|generic overrides.
-    static const char *force = getenv("BMM_COLLAPSED_KERNEL");
+    const char *force = getenv("BMM_COLLAPSED_KERNEL");
     const bool want_fast = force ? force[0] == 'f' : n_chains <= 148;
     if (want_fast && collapsed_fast_ok(p)) {
         if (p.K <= 2) return launch_fast_w<2>(p, n_chains, smem, st);

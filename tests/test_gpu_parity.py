@@ -97,10 +97,13 @@ def test_stickbreaking_replay(oracle, datasets):
     assert np.array_equal(g["permutations"][:, occ], t["permutations"][:, occ])
 
 
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
 @pytest.mark.parametrize("name,K,relabel,alpha", [("K2_N100_P5", 2, False, 0.0), ("K3_N1000_P5", 3, True, 0.0),
                                                   ("K2_N1000_P5", 4, True, 1.5)])
-def test_collapsed_replay(oracle, datasets, name, K, relabel, alpha):
+def test_collapsed_replay(oracle, datasets, monkeypatch, name, K, relabel, alpha, kernel):
+    """Both collapsed kernels: the register-resident low-latency one (few chains) and the generic one."""
     _need_gpu()
+    monkeypatch.setenv("BMM_COLLAPSED_KERNEL", kernel)
     X = datasets[name]
     N, P = X.shape
     ns, burnin, br = 40, 12, 5
