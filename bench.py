@@ -331,7 +331,7 @@ def run_grid(a):
     X = synth_rows(lo, hi, P, K)
     ip, th = grid_init(K, P)
     sid = _lib.SAMPLER_STICKBREAKING if w["sampler"] == "stickbreaking" else _lib.SAMPLER_FULL
-    kname = "big_sweep_tc_kernel" if (K <= 32 and P <= 112) else "lp_table+lp_sweep+lp_counts kernels"
+    kname = "big_sweep_ws_kernel" if (K <= 32 and P <= 112) else "lp_table+lp_sweep+lp_counts kernels"
     shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
     relabel, br = bool(w.get("relabel")), int(w.get("burnrelabel", 0))
     kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=relabel, burnrelabel=br)
@@ -571,7 +571,7 @@ def main():
     per_sweep_hist = (2 if relabel else 1) * K * P * 8 + K * 8 + 8 + (K * 4 if relabel else 0)
     bytes_launch = C_ * (sweeps2 * N * 1 + S * per_sweep_hist)
     dur_s = kern[2] / a.steps / 1e3
-    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_kernel", "dp": "dp_kernel"}[smp]
+    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_fast_kernel" if C_ <= 148 else "collapsed_kernel", "dp": "dp_kernel"}[smp]
     achieved = bytes_launch / dur_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
