@@ -573,8 +573,17 @@ def main():
     dur_s = kern[2] / a.steps / 1e3
     kname = {"full": "full_chain_kernel", "collapsed": "collapsed_fast_kernel" if C_ <= 148 else "collapsed_kernel", "dp": "dp_kernel"}[smp]
     achieved = bytes_launch / dur_s / 1e9
+    traffic = None   # dram bytes of the dominant launch from the committed ncu --set full capture of this configuration
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(kname, {})
+        if tr.get("workload") == a.workload and tr.get("chains") == C_ and tr.get("nsamples") == ns:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": int(bytes_launch),
+                "peak_source": pk_src,
                 "kernel": "%s (sweeps %d..%d, %d chains)" % (kname, burnin if relabel else 1, ns - 1, C_),
                 "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[2] / max(kern.sum(), 1e-9)),
                 "note": "C1-C3 are on-chip (issue/latency) bound by construction: chain state lives in shared "
