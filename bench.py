@@ -571,7 +571,7 @@ def main():
     per_sweep_hist = (2 if relabel else 1) * K * P * 8 + K * 8 + 8 + (K * 4 if relabel else 0)
     bytes_launch = C_ * (sweeps2 * N * 1 + S * per_sweep_hist)
     dur_s = kern[2] / a.steps / 1e3
-    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_fast_kernel" if C_ <= 148 else "collapsed_kernel", "dp": "dp_kernel"}[smp]
+    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_fast_kernel", "dp": "dp_kernel"}[smp]
     achieved = bytes_launch / dur_s / 1e9
     traffic = None   # dram bytes of the dominant launch from the committed ncu --set full capture of this configuration
     try:

@@ -56,10 +56,10 @@ struct Stream {
         return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     }
     // Gamma(shape, 1): Marsaglia-Tsang (shape < 1 boosted).  Same law as R::rgamma(shape, 1).
-    __device__ double gamma(double shape) {
+    __device__ __forceinline__ double gamma(double shape) {
         if (!(shape > 0.0)) return 0.0;
         double boost = 1.0;
-        if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+        if (shape < 1.0) { boost = exp(log(uniform()) / shape); shape += 1.0; }
         double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
         for (int it = 0; it < 256; ++it) {
             double x = normal(), v = 1.0 + c * x;
@@ -75,14 +75,25 @@ struct Stream {
         double s = x + y;
         return s > 0.0 ? x / s : 0.5;
     }
+    // Out-of-line copy: ~300 fp64-heavy instructions per inlined call.  Measured per kernel (ncu showed
+    // instruction-fetch stalls in the chain kernels): sharing one copy makes dp_kernel 30 % faster
+    // (8.7e8 -> 1.13e9 updates/s), does nothing for full_chain_kernel and halves collapsed_kernel, so
+    // only the DP path uses it.
+    __device__ __noinline__ double gamma_shared(double shape) { return gamma(shape); }
+    __device__ double beta_shared(double a, double b) {
+        double x = gamma_shared(a), y = gamma_shared(b);
+        double s = x + y;
+        return s > 0.0 ? x / s : 0.5;
+    }
 };
 
 // update_alpha (utils.cpp:6-14): alpha' = pi*G(a+K, 1/b_eps) + (1-pi)*G(a+K-1, 1/b_eps)
+template <bool SHARED = false>
 __device__ __forceinline__ double update_alpha_dev(Stream &s, double alpha_old, double a, double b, int N, int K) {
-    double b_eps = b - log(s.beta(alpha_old + 1.0, (double)N));
+    double b_eps = b - log(SHARED ? s.beta_shared(alpha_old + 1.0, (double)N) : s.beta(alpha_old + 1.0, (double)N));
     double pi1 = a + K - 1, pi2 = N * b_eps, pi = pi1 / (pi1 + pi2);
-    double g1 = s.gamma(a + K) / b_eps;
-    double g2 = s.gamma(a + K - 1) / b_eps;
+    double g1 = (SHARED ? s.gamma_shared(a + K) : s.gamma(a + K)) / b_eps;
+    double g2 = (SHARED ? s.gamma_shared(a + K - 1) : s.gamma(a + K - 1)) / b_eps;
     return pi * g1 + (1 - pi) * g2;
 }
 

@@ -66,6 +66,7 @@ __device__ inline double *stash_target(const CollapsedParams &p, int c, int j) {
 
 // Relabelling hooks + theta estimates + alpha + history rows, common to both collapsed samplers.
 // Called by the whole (32-thread) block after the i loop of sweep j.
+template <bool DP = false>
 __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s, int c, int j, double *alpha_sh,
                                             int Kalpha, const int *used, int nused) {
     const int lane = threadIdx.x, K = p.K, P = p.P, N = p.N, ns = p.nsamples, S = ns - p.burnin;
@@ -99,7 +100,7 @@ __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s,
         if (p.ralpha) al = p.ralpha[(size_t)c * ns + j];
         else if (p.alpha0 == 0.0) {
             Stream st(p.seed, (uint32_t)(p.chain_offset + c), (uint32_t)j, ST_ALPHA, 0u);
-            al = update_alpha_dev(st, al, p.a, p.b, N, Kalpha);
+            al = update_alpha_dev<DP>(st, al, p.a, p.b, N, Kalpha);
         }
         *alpha_sh = al;
         if (j >= p.burnin) p.alpha_out[(size_t)c * S + (j - p.burnin)] = al;
@@ -232,11 +233,11 @@ __global__ void __launch_bounds__(32) collapsed_kernel(const CollapsedParams p) 
 struct FastTabs { double *logB, *logG, *logBG, *logA; uint8_t *xs; };
 
 __host__ __device__ inline size_t collapsed_fast_extra(const CollapsedParams &p, char *base, FastTabs *t) {
+    // only the alpha-dependent table is per chain; log(beta+n), log(gamma+n), log(beta+gamma+n) are shared
+    // by all chains and read through L1 (keeping them here cost 24 KB per chain at N = 1000: 2 waves at C2 size)
     const size_t n1 = (size_t)p.N + 1;
     size_t off = 0;
-    double *logB = (double *)(base + off); off += n1 * 8;
-    double *logG = (double *)(base + off); off += n1 * 8;
-    double *logBG = (double *)(base + off); off += n1 * 8;
+    double *logB = nullptr, *logG = nullptr, *logBG = nullptr;
     double *logA = (double *)(base + off); off += n1 * 8;
     uint8_t *xs = (uint8_t *)(base + off); off += ((size_t)p.N + 15) & ~(size_t)15;
     if (t) { t->logB = logB; t->logG = logG; t->logBG = logBG; t->logA = logA; t->xs = xs; }
@@ -258,7 +259,6 @@ __global__ void __launch_bounds__(32) collapsed_fast_kernel(const CollapsedParam
     const size_t NK = (size_t)N * K;
 
     for (int e = lane; e < N; e += 32) { tb.xs[e] = (uint8_t)(p.xbits[(size_t)e * W] & 0xFFu); s.z[e] = p.z_cur[(size_t)c * N + e]; }
-    for (int e = lane; e <= N; e += 32) { tb.logB[e] = p.logB[e]; tb.logG[e] = p.logG[e]; tb.logBG[e] = p.logBG[e]; }
     for (int k = lane; k < K; k += 32) s.perm[k] = k;
     int S[PM], Nk = 0;
 #pragma unroll
@@ -297,13 +297,13 @@ __global__ void __launch_bounds__(32) collapsed_fast_kernel(const CollapsedParam
             double v = 0.0;
             if (lane < K && Nk1 > 0) {  // empty cluster: probability exactly 0 (collapsed_gibbs.cpp:104,131-133)
                 const double LHS = tb.logA[Nk1] - left_denom;
-                const double denom = tb.logBG[Nk1];
+                const double denom = __ldg(&p.logBG[Nk1]);
                 double sel[PM];
 #pragma unroll
                 for (int d = 0; d < PM; ++d) {
                     const int xd = (xb >> d) & 1;
                     const int Sd = S[d] - (own & xd);
-                    sel[d] = d < P ? (xd ? tb.logB[Sd] : tb.logG[Nk1 - Sd]) : 0.0;
+                    sel[d] = d < P ? (xd ? __ldg(&p.logB[Sd]) : __ldg(&p.logG[Nk1 - Sd])) : 0.0;
                 }
                 double logLH = 0.0;
 #pragma unroll
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
         if (lane == 0) { nused_sh = nused; kvar_sh = Kvar; }
         if (p.kactive_out && lane == 0) p.kactive_out[(size_t)c * ns + j] = Kvar;
         __syncthreads();
-        collapsed_after_sweep(p, s, c, j, &alpha_sh, Kvar, s.used, nused);
+        collapsed_after_sweep<true>(p, s, c, j, &alpha_sh, Kvar, s.used, nused);
     }
     __syncthreads();
     for (int e = lane; e < maxK * P1; e += 32) p.cnt[(size_t)c * maxK * P1 + e] = s.cnt[e];
@@ -642,14 +642,14 @@ size_t collapsed_smem_bytes(const CollapsedParams &p) {
 }
 
 cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_t st) {
-    const size_t smem = collapsed_smem_bytes(p);
-    // Measured on B200 (K3_N1000_P5 / K2_N100_P5): one chain 1.21e6 vs 0.86e6 updates/s in favour of the
-    // register-resident kernel, 1024 chains 6.4e8 vs 8.4e8 in favour of the generic one (with several
-    // warps per scheduler its shorter instruction stream wins), so the choice follows the chain count.
-    // BMM_COLLAPSED_KERNEL=fast|generic overrides.
+    size_t smem = collapsed_layout(p, (char *)0, nullptr);   // the generic kernels: no table area (occupancy!)
+    // Measured on B200 (K3_N1000_P5): the register-resident kernel gives 1.07e6 vs 0.88e6 updates/s for one
+    // chain and 1.01e9 vs 0.86e9 for 1024 chains, so it is used whenever the shape fits (K <= 32, P <= 8).
+    // BMM_COLLAPSED_KERNEL=fast|generic overrides (the parity tests run both).
     const char *force = getenv("BMM_COLLAPSED_KERNEL");
-    const bool want_fast = force ? force[0] == 'f' : n_chains <= 148;
+    const bool want_fast = force ? force[0] == 'f' : true;
     if (want_fast && collapsed_fast_ok(p)) {
+        smem += collapsed_fast_extra(p, (char *)0, nullptr);
         if (p.K <= 2) return launch_fast_w<2>(p, n_chains, smem, st);
         if (p.K <= 4) return launch_fast_w<4>(p, n_chains, smem, st);
         if (p.K <= 8) return launch_fast_w<8>(p, n_chains, smem, st);
