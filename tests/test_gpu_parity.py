@@ -584,3 +584,45 @@ def test_invalid_arguments_are_rejected(datasets):
         with pytest.raises(_lib.BmmError) as e:
             B.gibbs_collapsed(X, kw.pop("nsamples"), kw.pop("K"), **kw)
         assert e.value.code == code, kw
+
+
+def test_posterior_means_collapsed_and_stickbreaking(oracle, datasets):
+    """Philox chains of the two remaining samplers against oracle chains: label-invariant posterior
+    summaries (sorted cluster shares, theta rows ordered by share) within Monte Carlo error."""
+    _need_gpu()
+    X = datasets["K2_N1000_P5"]
+    N, P = X.shape
+    ns, burnin = 300, 100
+
+    def summary(z, theta, K):                      # z: S x N, theta: K x P x S
+        share = np.stack([(z == k + 1).mean(1) for k in range(K)], 1)            # S x K
+        order = np.argsort(-share.mean(0))
+        th = np.nanmean(theta, 2)[order]
+        return share.mean(0)[order][:2], th[:2]
+
+    # collapsed, K = 2
+    g = B.gibbs_collapsed(X, ns, 2, burnin=burnin, chains=24, seed=5)
+    gs = [summary(g["z"][c], g["theta"][c], 2) for c in range(24)]
+    os_ = []
+    for c in range(6):
+        iz = RRng(40 + c).sample_int(2, N)
+        t = oracle.gibbs_collapsed(X, iz, ns, 2, burnin=burnin, seed=300 + c, probes=False).tail()
+        os_.append(summary(t["z"], t["theta"], 2))
+    for idx in (0, 1):
+        gm, om = np.mean([s[idx] for s in gs], 0), np.mean([s[idx] for s in os_], 0)
+        se = np.std([s[idx] for s in gs], 0) / np.sqrt(24) + np.std([s[idx] for s in os_], 0) / np.sqrt(6) + 0.01
+        assert (np.abs(gm - om) < 4 * se).all(), ("collapsed", idx, gm, om)
+    assert np.allclose(np.mean([s[0] for s in gs], 0), [0.7, 0.3], atol=0.05)     # documented truth, R/bmm-mcmc.R:31-35
+
+    # stick-breaking, maxK = 6: the two occupied sticks carry the same shares
+    g = B.gibbs_stickbreaking(X, ns, 6, burnin=burnin, chains=24, seed=7)
+    gs = [summary(g["z"][c], g["theta"][c], 6) for c in range(24)]
+    os_ = []
+    for c in range(4):
+        ip, th = _init_full(6, P, 70 + c)
+        t = oracle.gibbs_stickbreaking(X, ip, th, ns, 6, burnin=burnin, seed=400 + c, probes=False).tail()
+        os_.append(summary(t["z"], t["theta"], 6))
+    for idx in (0, 1):
+        gm, om = np.mean([s[idx] for s in gs], 0), np.mean([s[idx] for s in os_], 0)
+        se = np.std([s[idx] for s in gs], 0) / np.sqrt(24) + np.std([s[idx] for s in os_], 0) / np.sqrt(4) + 0.015
+        assert (np.abs(gm - om) < 4 * se).all(), ("stickbreaking", idx, gm, om)
