@@ -22,11 +22,13 @@
 #define BMM_FLAG_PROBE_PROBS 0x100u
 #define BMM_FLAG_PROBE_LOGLIK 0x200u
 #define BMM_FLAG_PROBE_COUNTS 0x400u
+#define BMM_FLAG_PIPELINE 0x800u       // internal: run_once overlaps sampling with the z download (chunks of sweeps)
 
 namespace bmm {
 bool full_rows_fit_smem(int U, int K);
 }
 extern "C" void bmm_widen_u8_i32(const uint8_t *src, int32_t *dst, size_t n, int threads);  // host_widen.cpp
+extern "C" void bmm_widen_rows_u8_i32(const uint8_t *src, int32_t *dst, size_t rows, size_t cs, size_t stride, size_t off, int threads);
 
 namespace {
 
@@ -127,6 +129,11 @@ struct bmm_plan {
     bmm::CollapsedParams cp{};
     bmm::BigParams bp{};
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
+    bool pipelined = false;       // z is delivered chunk by chunk while later sweeps still run (run_once only)
+    int CH = 0;                   // sweeps per chunk
+    DevBuf zc_orig[2], zc_rel[2]; // chunk buffers [chain][observation][CH] bytes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ck_done[2] = {nullptr, nullptr}, ck_copied[2] = {nullptr, nullptr};
     int deb = 4;                  // bytes per allocation of the device-side R-layout z (1: widened on the host)
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
@@ -150,6 +157,8 @@ struct bmm_plan {
         if (evk1) cudaEventDestroy(evk1);
         for (auto &e : evs) if (e) cudaEventDestroy(e);
         for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
+        for (int b = 0; b < 2; ++b) { if (ck_done[b]) cudaEventDestroy(ck_done[b]); if (ck_copied[b]) cudaEventDestroy(ck_copied[b]); }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -664,8 +673,22 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
         pl->deb = ((args->flags & BMM_FLAG_COMPACT_Z) || widen) ? 1 : 4;
         const size_t eb = (size_t)pl->deb;
         const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
-        cudaError_t e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
-        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
+        cudaError_t e2 = cudaSuccess;
+        pl->pipelined = (args->flags & BMM_FLAG_PIPELINE) && widen && !pl->grid_path;
+        if (pl->pipelined) {
+            pl->CH = 64;
+            const size_t cb = (size_t)pl->C * pl->N * pl->CH;
+            for (int b = 0; b < 2 && e2 == cudaSuccess; ++b) {
+                e2 = pl->zc_orig[b].alloc(cb, false);
+                if (e2 == cudaSuccess && pl->relabel) e2 = pl->zc_rel[b].alloc(cb, false);
+                if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ck_done[b], cudaEventDisableTiming);
+                if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ck_copied[b], cudaEventDisableTiming);
+            }
+            if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking);
+        } else {
+            e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
+            if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
+        }
         if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
     }
     if (!rc) { cudaError_t e3 = cudaDeviceSynchronize(); if (e3 != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e3)); }
@@ -834,6 +857,75 @@ int bmm_plan_destroy(bmm_plan *pl) {
     return BMM_OK;
 }
 
+// One-shot call with the allocation matrices delivered while the chain still runs: the post-burn-in
+// sweeps go in chunks of CH; chunk k is transposed to [chain][observation][CH] bytes on the device,
+// DMA'd into pinned staging on a second stream and widened by the host workers into its slice of the
+// S x N column-major int32 matrices while chunk k+1 is being sampled.  The S x N matrices are >90 % of
+// the returned bytes, and widening them (host memory bandwidth) takes longer than the sampling.
+static int run_fetch_pipelined(bmm_plan *pl, bmm_out *out) {
+    CU(cudaSetDevice(pl->a.device));
+    const int ns = pl->ns, burnin = pl->a.burnin, S = pl->S, CH = pl->CH, K = pl->K;
+    const size_t C = pl->C, N = pl->N;
+    const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
+    static uint8_t *stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    static size_t stage_bytes = 0;
+    const size_t cb = C * N * CH;
+    if (cb > stage_bytes) {
+        for (auto &row : stage) for (auto &b : row) { if (b) cudaFreeHost(b); b = nullptr; }
+        for (auto &row : stage) for (auto &b : row) CU(cudaHostAlloc((void **)&b, cb, cudaHostAllocDefault));
+        stage_bytes = cb;
+    }
+    static const int threads = [] {
+        const char *e = getenv("BMM_FETCH_THREADS");
+        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        return t < 1 ? 1 : (t > 8 && !e ? 8 : (t > 32 ? 32 : t));
+    }();
+    CU(cudaEventRecord(pl->ev0, pl->stream));
+    TRY(run_segment(pl, 1, burnin));
+    if (pl->relabel)
+        CU(bmm::launch_stephens_batch(pl->C, pl->U, K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
+                                      pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(), pl->logQ.as<double>(),
+                                      pl->sb_perm.as<int>(), pl->sb_cost.as<double>(), pl->sb_ws.as<char>(), pl->stream));
+    const int nck = (S + CH - 1) / CH;
+    auto enqueue = [&](int k) -> int {
+        const int j0 = burnin + k * CH, cs = std::min(CH, ns - j0), b = k & 1;
+        if (k >= 2) CU(cudaStreamWaitEvent(pl->stream, pl->ck_copied[b], 0));
+        TRY(run_segment(pl, j0, j0 + cs));
+        CU(bmm::launch_finalize_chunk(pl->C, pl->N, ns, j0, cs, K, S, k * CH, pl->zhist.as<uint8_t>(),
+                                      pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->zc_orig[b].as<uint8_t>(),
+                                      pl->relabel ? pl->zc_rel[b].as<uint8_t>() : nullptr, pl->stream));
+        CU(cudaEventRecord(pl->ck_done[b], pl->stream));
+        return BMM_OK;
+    };
+    TRY(enqueue(0));
+    if (nck > 1) TRY(enqueue(1));
+    int32_t *dst_main = out->z, *dst_orig = pl->relabel ? out->z_original : nullptr;
+    for (int k = 0; k < nck; ++k) {
+        const int j0 = burnin + k * CH, cs = std::min(CH, ns - j0), b = k & 1;
+        const size_t bytes = C * N * cs;
+        CU(cudaStreamWaitEvent(pl->copy_stream, pl->ck_done[b], 0));
+        CU(cudaMemcpyAsync(stage[b][0], pl->zc_orig[b].p, bytes, cudaMemcpyDeviceToHost, pl->copy_stream));
+        if (pl->relabel) CU(cudaMemcpyAsync(stage[b][1], pl->zc_rel[b].p, bytes, cudaMemcpyDeviceToHost, pl->copy_stream));
+        CU(cudaEventRecord(pl->ck_copied[b], pl->copy_stream));
+        if (k + 2 < nck) TRY(enqueue(k + 2));
+        CU(cudaEventSynchronize(pl->ck_copied[b]));
+        if (pl->relabel) {
+            if (dst_main) bmm_widen_rows_u8_i32(stage[b][1], dst_main, C * N, cs, S, (size_t)k * CH, threads);
+            if (dst_orig) bmm_widen_rows_u8_i32(stage[b][0], dst_orig, C * N, cs, S, (size_t)k * CH, threads);
+        } else if (dst_main) {
+            bmm_widen_rows_u8_i32(stage[b][0], dst_main, C * N, cs, S, (size_t)k * CH, threads);
+        }
+    }
+    CU(cudaEventRecord(pl->ev1, pl->stream));
+    for (int e = 0; e < 5; ++e) CU(cudaEventRecord(pl->evs[e], pl->stream));
+    CU(cudaEventRecord(pl->evk0, pl->stream));
+    CU(cudaEventRecord(pl->evk1, pl->stream));
+    pl->ran = true;
+    bmm_out rest = *out;       // everything but the allocation matrices comes the ordinary way
+    rest.z = nullptr; rest.z_original = nullptr;
+    return bmm_plan_fetch(pl, &rest);
+}
+
 static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm_out *out) {
     if (!out) return fail(BMM_ERR_INVALID, "out is NULL");
     if (!args) return fail(BMM_ERR_INVALID, "args is NULL");
@@ -841,6 +933,15 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     if (out->probs) a.flags |= BMM_FLAG_PROBE_PROBS;
     if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
     if (out->counts) a.flags |= BMM_FLAG_PROBE_COUNTS;
+    {   // Overlapping sampling and download (run_fetch_pipelined) is OFF unless BMM_PIPELINE=1: chunking by
+        // sweeps makes the host write 256-byte pieces of every S x N column per chunk, and those scattered
+        // non-temporal stores ran at ~8 GB/s instead of ~120 GB/s (C2: 899 ms against 131 ms unpipelined).
+        const char *pe = getenv("BMM_PIPELINE");
+        const long long C = a.n_chains < 1 ? 1 : a.n_chains, S = (long long)a.nsamples - a.burnin;
+        if ((pe && pe[0] == '1') && out->z && !(a.flags & BMM_FLAG_COMPACT_Z) && !a.replay && S >= 256 &&
+            C * S * a.N >= ((long long)64 << 20) && !(a.relabel && !out->z_original))
+            a.flags |= BMM_FLAG_PIPELINE;
+    }
     bmm_plan *pl = nullptr;
     static const bool trace = getenv("BMM_TRACE") != nullptr;   // wall-clock phases of the one-shot call on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -848,10 +949,16 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     int rc = bmm_plan_create(sampler, &a, init, &pl);
     if (rc) return rc;
     const double t1 = now();
-    rc = bmm_plan_run(pl);
-    if (!rc && trace) rc = bmm_plan_sync(pl);
-    const double t2 = now();
-    if (!rc) rc = bmm_plan_fetch(pl, out);
+    double t2;
+    if (pl->pipelined) {
+        rc = run_fetch_pipelined(pl, out);
+        t2 = t1;
+    } else {
+        rc = bmm_plan_run(pl);
+        if (!rc && trace) rc = bmm_plan_sync(pl);
+        t2 = now();
+        if (!rc) rc = bmm_plan_fetch(pl, out);
+    }
     const double t3 = now();
     bmm_plan_destroy(pl);
     if (trace) fprintf(stderr, "bmm trace: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);

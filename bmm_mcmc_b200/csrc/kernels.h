@@ -162,6 +162,9 @@ cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long s
 // elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).
 cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
                               const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st);
+// sweeps [j0, j0 + cs) as bytes in [chain][observation][cs] order (pipelined download)
+cudaError_t launch_finalize_chunk(int n_chains, int N, int nsamples, int j0, int cs, int K, int S, int sidx0,
+                                  const uint8_t *zhist, const int *perm_out, uint8_t *z_orig, uint8_t *z_rel, cudaStream_t st);
 // expand a per-row matrix [c][U*K] to per-observation [c][N*K]
 cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
                                cudaStream_t st);

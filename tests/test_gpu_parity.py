@@ -626,3 +626,20 @@ def test_posterior_means_collapsed_and_stickbreaking(oracle, datasets):
         gm, om = np.mean([s[idx] for s in gs], 0), np.mean([s[idx] for s in os_], 0)
         se = np.std([s[idx] for s in gs], 0) / np.sqrt(24) + np.std([s[idx] for s in os_], 0) / np.sqrt(4) + 0.015
         assert (np.abs(gm - om) < 4 * se).all(), ("stickbreaking", idx, gm, om)
+
+
+@pytest.mark.parametrize("sampler,relabel", [("full", True), ("full", False), ("collapsed", False)])
+def test_pipelined_download_equals_plain(datasets, monkeypatch, sampler, relabel):
+    """BMM_PIPELINE=1: above 64M allocations the one-shot call samples in chunks of sweeps and downloads /
+    widens each chunk while the next one runs: identical outputs to the plain call (ragged last chunk).
+    (Off by default: measured slower, see capi.cu.)"""
+    _need_gpu()
+    monkeypatch.setenv("BMM_PIPELINE", "1")
+    X = datasets["K3_N1000_P5"]
+    kw = dict(burnin=30, relabel=relabel, burnrelabel=10, chains=256, seed=8)
+    f = B.gibbs_full if sampler == "full" else B.gibbs_collapsed
+    a = f(X, 300, 3, **kw)                                # 256 * 270 * 1000 = 69M allocations, S = 270 = 4 * 64 + 14
+    monkeypatch.setenv("BMM_PIPELINE", "0")
+    b = f(X, 300, 3, **kw)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
