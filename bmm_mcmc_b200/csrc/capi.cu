@@ -55,6 +55,8 @@ struct DevCache {
     std::mutex m;
     std::map<std::pair<int, size_t>, std::vector<void *>> free_list;
     size_t cached = 0;
+    size_t cap = (size_t)24 << 30;   // bytes kept across calls (all devices), BMM_CACHE_GB overrides
+    DevCache() { if (const char *e = getenv("BMM_CACHE_GB")) cap = (size_t)atoll(e) << 30; }
     void *take(int dev, size_t n) {
         std::lock_guard<std::mutex> g(m);
         auto it = free_list.find({dev, n});
@@ -66,6 +68,14 @@ struct DevCache {
     }
     void give(int dev, size_t n, void *p) {
         std::lock_guard<std::mutex> g(m);
+        if (cached + n > cap) {      // keep the idle footprint bounded: beyond the cap blocks go back to the driver
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != dev) cudaSetDevice(dev);
+            cudaFree(p);
+            if (cur != dev) cudaSetDevice(cur);
+            return;
+        }
         free_list[{dev, n}].push_back(p);
         cached += n;
     }
