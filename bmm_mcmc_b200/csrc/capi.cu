@@ -608,8 +608,11 @@ int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
     static const int threads = [] {
         const char *e = getenv("BMM_FETCH_THREADS");
         // half the hardware threads, at most 8: measured on the 16-vCPU GPU boxes 8 workers reach
-        // ~120 GB/s of int32 output, 16 oversubscribe the cores the DMA completion path needs
-        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        // ~120 GB/s of int32 output, 16 oversubscribe the cores the DMA completion path needs.  With one
+        // process per GPU (torchrun sets LOCAL_WORLD_SIZE) the cores are shared between the ranks.
+        int ranks = 1;
+        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(lw) > 0 ? atoi(lw) : 1;
+        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / (2 * ranks);
         return t < 1 ? 1 : (t > 8 && !e ? 8 : (t > 32 ? 32 : t));
     }();
     const size_t nch = (n + CH - 1) / CH;
@@ -887,7 +890,9 @@ static int run_fetch_pipelined(bmm_plan *pl, bmm_out *out) {
     }
     static const int threads = [] {
         const char *e = getenv("BMM_FETCH_THREADS");
-        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        int ranks = 1;
+        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(lw) > 0 ? atoi(lw) : 1;
+        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / (2 * ranks);
         return t < 1 ? 1 : (t > 8 && !e ? 8 : (t > 32 ? 32 : t));
     }();
     CU(cudaEventRecord(pl->ev0, pl->stream));
