@@ -47,6 +47,7 @@ class Out(C.Structure):
         ("pi", _dbl_p), ("alpha", _dbl_p), ("permutations", _i32_p), ("z", _i32_p), ("theta", _dbl_p),
         ("z_original", _i32_p), ("theta_original", _dbl_p), ("probs", _dbl_p), ("loglik", _dbl_p),
         ("Q_final", _dbl_p), ("status", _i32_p), ("counts", _i32_p),
+        ("z_freq", C.POINTER(C.c_uint32)), ("z_last", _i32_p),
     ]
 
 

@@ -168,8 +168,9 @@ def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probe
     res["theta"] = _chain_cm(Cn, (K, P, S), np.float64, pinned)
     out.theta = _p(res["theta"], C.c_double)
     if relabel:
-        res["z_original"] = _chain_cm(Cn, (S, N), zt, pinned)
-        out.z_original = C.cast(res["z_original"].ctypes.data, C.POINTER(C.c_int32))
+        if not no_z:
+            res["z_original"] = _chain_cm(Cn, (S, N), zt, pinned)
+            out.z_original = C.cast(res["z_original"].ctypes.data, C.POINTER(C.c_int32))
         res["theta_original"] = _chain_cm(Cn, (K, P, S), np.float64, pinned)
         out.theta_original = _p(res["theta_original"], C.c_double)
     if "probs" in probes:
@@ -184,6 +185,12 @@ def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probe
     if "counts" in probes:
         res["counts"] = np.zeros((Cn, nsamples, K + K * P), dtype=np.int32)
         out.counts = _p(res["counts"], C.c_int32)
+    if "z_freq" in probes:       # grid path posterior summaries (usable with no_z_history)
+        res["z_freq"] = _chain_cm(Cn, (N, K), np.uint32)
+        out.z_freq = _p(res["z_freq"], C.c_uint32)
+    if "z_last" in probes:
+        res["z_last"] = np.zeros((Cn, N), dtype=np.int32)
+        out.z_last = _p(res["z_last"], C.c_int32)
     status = np.zeros(Cn, dtype=np.int32)
     out.status = _p(status, C.c_int32)
     return res, out, status
@@ -217,6 +224,8 @@ class Plan:
             args.flags |= 0x200
         if "counts" in probes:
             args.flags |= 0x400
+        if "z_freq" in probes:
+            args.flags |= 0x1000
         self.h = C.c_void_p()
         _lib.check(self.L.bmm_plan_create(sampler, C.byref(args), C.byref(init), C.byref(self.h)))
 

@@ -22,6 +22,7 @@
 #define BMM_FLAG_PROBE_PROBS 0x100u
 #define BMM_FLAG_PROBE_LOGLIK 0x200u
 #define BMM_FLAG_PROBE_COUNTS 0x400u
+#define BMM_FLAG_PROBE_ZFREQ 0x1000u
 #define BMM_FLAG_PIPELINE 0x800u       // internal: run_once overlaps sampling with the z download (chunks of sweeps)
 
 namespace bmm {
@@ -149,6 +150,7 @@ struct bmm_plan {
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
+    DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
     // state
@@ -356,6 +358,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     if (a.flags & BMM_FLAG_PROBE_PROBS) CU(pl->probs_out.alloc((size_t)ns * N * K * 8));
     if (a.flags & BMM_FLAG_PROBE_LOGLIK) CU(pl->loglik_out.alloc((size_t)ns * N * K * 8));
     if (a.flags & BMM_FLAG_PROBE_COUNTS) CU(pl->counts_out.alloc((size_t)ns * (K + KP) * 4));
+    if (a.flags & BMM_FLAG_PROBE_ZFREQ) CU(pl->zfreq.alloc((size_t)N * K * 4));
     if (pl->relabel) {
         const size_t NK = (size_t)N * K;
         size_t free_b = 0, total_b = 0;
@@ -419,6 +422,7 @@ int run_big(bmm_plan *pl) {
         pl->sweep_ev.push_back(e);
     }
     CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
+    if (pl->zfreq.p) CU(cudaMemsetAsync(pl->zfreq.p, 0, pl->zfreq.bytes, pl->stream));
     CU(bmm::launch_big_init(b, pl->stream));
     const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
     const long long N = b.N_local;
@@ -466,6 +470,9 @@ int run_big(bmm_plan *pl) {
             CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(), pl->perm_cur.as<int>(), j,
                                         pl->sm_count, pl->stream));
         }
+        if (pl->zfreq.p && j >= burnin)
+            CU(bmm::launch_grid_zfreq(N, K, pl->zhist.as<uint8_t>() + (size_t)(b.keep_history ? j : 0) * N,
+                                      pl->relabel ? pl->perm_cur.as<int>() : nullptr, pl->zfreq.as<unsigned>(), pl->sm_count, pl->stream));
         CU(bmm::launch_big_params(bj, j, pl->stream));
     }
     return BMM_OK;
@@ -834,6 +841,7 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     CU(d2h(out->probs, pl->probs_out, C * ns * N * K * 8));
     CU(d2h(out->loglik, pl->loglik_out, C * ns * N * K * 8));
     std::vector<float> qf_host;
+    std::vector<uint8_t> zlast_host;
     if (out->Q_final && pl->relabel && pl->grid_path) {
         qf_host.resize(N * K);
         CU(cudaMemcpyAsync(qf_host.data(), pl->Qf.p, N * K * 4, cudaMemcpyDeviceToHost, pl->stream));
@@ -848,8 +856,17 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
         }
     }
     CU(d2h(out->counts, pl->counts_out, ns * (K + K * P) * 4));
+    if (pl->grid_path) {
+        CU(d2h(out->z_freq, pl->zfreq, N * K * 4));
+        if (out->z_last && pl->zhist.p) {   // bytes -> int32 through a small staging vector
+            zlast_host.resize(N);
+            const uint8_t *src = pl->zhist.as<uint8_t>() + (pl->bp.keep_history ? (ns - 1) * N : 0);
+            CU(cudaMemcpyAsync(zlast_host.data(), src, N, cudaMemcpyDeviceToHost, pl->stream));
+        }
+    }
     CU(d2h(out->status, pl->status, C * 4));
     CU(cudaStreamSynchronize(pl->stream));
+    for (size_t i = 0; i < zlast_host.size(); ++i) out->z_last[i] = (int32_t)zlast_host[i];
     if (!qf_host.empty())   // grid path keeps Q as row-major float; the ABI returns N x K column-major double
         for (size_t i = 0; i < N; ++i)
             for (size_t k = 0; k < K; ++k) out->Q_final[i + N * k] = (double)qf_host[i * K + k];
@@ -948,6 +965,7 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     if (out->probs) a.flags |= BMM_FLAG_PROBE_PROBS;
     if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
     if (out->counts) a.flags |= BMM_FLAG_PROBE_COUNTS;
+    if (out->z_freq) a.flags |= BMM_FLAG_PROBE_ZFREQ;
     {   // Overlapping sampling and download (run_fetch_pipelined) is OFF unless BMM_PIPELINE=1: chunking by
         // sweeps makes the host write 256-byte pieces of every S x N column per chunk, and those scattered
         // non-temporal stores ran at ~8 GB/s instead of ~120 GB/s (C2: 899 ms against 131 ms unpipelined).

@@ -302,7 +302,21 @@ __global__ void grid_identity_perm_kernel(int n, int K, int *perm) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) perm[e] = e % K;
 }
 
+__global__ void grid_zfreq_kernel(long long N, int K, const uint8_t *__restrict__ z, const int *__restrict__ perm,
+                                  unsigned *__restrict__ zfreq) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int zi = (int)z[i] - 1;
+        if (zi >= 0 && zi < K) zfreq[i + N * (perm ? perm[zi] : zi)] += 1u;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_grid_zfreq(long long N, int K, const uint8_t *z, const int *perm, unsigned *zfreq, int sm_count, cudaStream_t st) {
+    grid_zfreq_kernel<<<sm_count * 8, 256, 0, st>>>(N, K, z, perm, zfreq);
+    g_launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q, int use_logp, double *acc,
                              int sm_count, cudaStream_t st) {

@@ -147,6 +147,8 @@ cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t 
 cudaError_t launch_grid_qmean(long long N, int K, int M, const float *cube, const int *perm, float *Q, int sm_count,
                               cudaStream_t st);
 cudaError_t launch_grid_identity_perm(int n, int K, int *perm, cudaStream_t st);
+// posterior summary: zfreq[i + N*perm[z_i - 1]] += 1 over one sweep's allocations (perm may be nullptr)
+cudaError_t launch_grid_zfreq(long long N, int K, const uint8_t *z, const int *perm, unsigned *zfreq, int sm_count, cudaStream_t st);
 
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,

@@ -120,6 +120,11 @@ typedef struct bmm_out {
     int32_t *status;         /* [chain] 0 or a BMM_ERR_* raised inside that chain                  */
     int32_t *counts;         /* grid path probe: [nsamples][K + K*P] sufficient statistics of every
                                 sweep, c_k then V_kd (k + K*d) (full_gibbs.cpp:182-200)             */
+    /* grid path posterior summaries: what a large-N caller needs instead of the S x N
+     * history, which BMM_FLAG_NO_Z_HISTORY suppresses.                                             */
+    uint32_t *z_freq;        /* [N x K cm] number of post-burn-in sweeps observation i spent in label k
+                                (relabelled labels when relabel)                                    */
+    int32_t *z_last;         /* [N] allocations of the last sweep, 1-based, original labels          */
 } bmm_out;
 
 /* ---- samplers: replace the four sampler .Call symbols ---------------------------------------- */

@@ -643,3 +643,20 @@ def test_pipelined_download_equals_plain(datasets, monkeypatch, sampler, relabel
     b = f(X, 300, 3, **kw)
     for k in a:
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("relabel", [False, True])
+def test_grid_posterior_summaries(datasets, relabel):
+    """z_freq / z_last (what a large-N caller keeps instead of the S x N history) equal the same summaries
+    computed from the full history; and they are available with no_z_history."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    K, ns, burnin = 3, 60, 20
+    kw = dict(burnin=burnin, relabel=relabel, burnrelabel=5, seed=6, grid_path=True)
+    g = B.gibbs_full(X, ns, K, probes=("z_freq", "z_last"), **kw)
+    freq = np.stack([(g["z"] == k + 1).sum(0) for k in range(K)], 1)
+    assert np.array_equal(g["z_freq"], freq)
+    assert np.array_equal(g["z_last"], (g["z_original"] if relabel else g["z"])[-1])
+    h = B.gibbs_full(X, ns, K, probes=("z_freq", "z_last"), no_z_history=True, **kw)
+    assert "z" not in h and np.array_equal(h["z_freq"], g["z_freq"]) and np.array_equal(h["z_last"], g["z_last"])
+    _close(h["theta"], g["theta"], rtol=0)
