@@ -349,7 +349,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     TRY(upload(pl->alpha_cur, al.data(), 1));
     CU(pl->w1.alloc(KP * 8)); CU(pl->w0.alloc(KP * 8)); CU(pl->lpi.alloc((size_t)K * 8)); CU(pl->gsc.alloc((size_t)K * 8));
     CU(pl->counts.alloc(2 * (K + KP) * 4));
-    CU(pl->status.alloc(4));
+    CU(pl->status.alloc(8));   // [0] chain status, [1] scratch flag of the batch relabelling loop
     const bool keep = !(a.flags & BMM_FLAG_NO_Z_HISTORY);
     CU(pl->zhist.alloc(keep ? (size_t)ns * N : (size_t)N));
     CU(pl->theta_out.alloc(KP * S * 8));
@@ -449,16 +449,25 @@ int run_big(bmm_plan *pl) {
             int *sbp = pl->sb_perm.as<int>();
             CU(bmm::launch_grid_clamp((long long)M * (long long)NK, cube, pl->sm_count, pl->stream));
             CU(bmm::launch_grid_identity_perm(M * K, K, sbp, pl->stream));
-            for (int iter = 0; iter < 100; ++iter) {   // threshold 10^(-6) == -16: always 100 (quirk 1)
+            // The reference always runs 100 iterations (threshold 10^(-6) == -16, quirk 1).  Once an iteration
+            // leaves every permutation unchanged the following ones recompute the same Q, costs and
+            // assignments, so stopping there returns exactly what the 100th iteration would.
+            int *flag = pl->status.as<int>() + 1;
+            for (int iter = 0; iter < 100; ++iter) {
                 CU(bmm::launch_grid_qmean(N, K, M, cube, sbp, pl->Qf.as<float>(), pl->sm_count, pl->stream));
+                CU(cudaMemsetAsync(flag, 0, sizeof(int), pl->stream));
                 for (int t = 0; t < M; ++t) {
                     CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
                                              pl->sm_count, pl->stream));
                     if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
                         return fail(BMM_ERR_NCCL, bmm::dist_error());
                     CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
-                                               pl->stream));
+                                               pl->stream, flag));
                 }
+                int changed = 1;   // every rank sees the same all-reduced costs, hence the same flag
+                CU(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+                CU(cudaStreamSynchronize(pl->stream));
+                if (!changed) break;
             }
         } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
             CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), 0, pl->cost_acc.as<double>(),

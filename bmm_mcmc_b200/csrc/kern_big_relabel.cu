@@ -237,7 +237,8 @@ __device__ void assign_jv_warp(int K, const double *costT, double *urow, int *co
 // (cost_in_smem): every step of the augmenting-path search is a dependent chain of such accesses.
 // acc holds G(k,l) at k + K*l and s_l at K*K + l; the cost C(k,l) = s_l - G(k,l) has rows k = reference
 // labels and columns l = sample labels (stephens.cpp:78-84).
-__global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *perm_cur, int *perm_dst, int perm_stride) {
+__global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *perm_cur, int *perm_dst, int perm_stride,
+                                   int *changed) {
     extern __shared__ __align__(16) char sm[];
     const int lane = threadIdx.x;
     __shared__ int c2r[256];
@@ -266,7 +267,10 @@ __global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *pe
     __syncwarp();
     for (int l = lane; l < K; l += 32) {
         if (perm_cur) perm_cur[l] = c2r[l];
-        if (perm_dst) perm_dst[(size_t)l * perm_stride] = c2r[l];
+        if (perm_dst) {
+            if (changed && perm_dst[(size_t)l * perm_stride] != c2r[l]) *changed = 1;
+            perm_dst[(size_t)l * perm_stride] = c2r[l];
+        }
     }
 }
 
@@ -334,7 +338,8 @@ cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q,
     return cudaGetLastError();
 }
 
-cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st) {
+cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st,
+                               int *changed) {
     (void)ws;
     const size_t wsb = ((size_t)(K + 1) * sizeof(double) + 15) & ~(size_t)15, costb = (size_t)K * K * sizeof(double);
     const int in_smem = wsb + costb <= 200 * 1024;
@@ -345,7 +350,7 @@ cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int 
         if (e != cudaSuccess) return e;
         attr = smem;
     }
-    grid_assign_kernel<<<1, 32, smem, st>>>(K, acc, in_smem, perm_cur, perm_dst, perm_stride);
+    grid_assign_kernel<<<1, 32, smem, st>>>(K, acc, in_smem, perm_cur, perm_dst, perm_stride, changed);
     g_launches++;
     return cudaGetLastError();
 }

@@ -140,7 +140,9 @@ cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStr
 // ---- relabelling on the grid path (kern_big_relabel.cu); P, Q row-major float [N][K] ----------
 cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q, int use_logp, double *acc,
                              int sm_count, cudaStream_t st);           // acc: K*K + K doubles
-cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st);
+// *changed (device, optional) is set to 1 when the stored permutation differs from the new one
+cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st,
+                               int *changed = nullptr);
 cudaError_t launch_grid_qupdate(long long N, int K, float *Q, const float *P, const int *perm, int sample_num,
                                 int sm_count, cudaStream_t st);
 cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t st);
