@@ -33,6 +33,16 @@ __host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
     return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// Allocation draws of the uncollapsed samplers: observation gi of sweep j uses word gi & 3 of
+// Philox(counter = (gi >> 2, gi >> 34, stream, j)), i.e. one Philox evaluation serves four consecutive
+// observations (the chain-per-block kernel draws them in one lane).  32 bits per uniform: categories
+// below 2^-32 are never drawn, far under any Monte Carlo resolution.
+__host__ __device__ __forceinline__ uint32_t philox_word(const uint4 &r, int h) {
+    return h == 0 ? r.x : (h == 1 ? r.y : (h == 2 ? r.z : r.w));
+}
+__host__ __device__ __forceinline__ double u32_unit(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+__host__ __device__ __forceinline__ float u32_unit_f(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+
 // Sequential stream for the (rare, rejection-based) parameter draws.
 // key = (seed_lo, chain); counter = (attempt, index, stream, sweep ^ seed_hi-mix)
 struct Stream {

@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams 
             z = rmultinom1_replay(K, [&](int k) { return pr[k]; },
                                   p.ru + ((size_t)j * p.N_local + i) * p.ru_slots);
         } else {
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
-            const double u = (gi & 1) ? u53(rnd.z, rnd.w) : u53(rnd.x, rnd.y);
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
+            const double u = u32_unit(philox_word(rnd, (int)(gi & 3)));
             R c2 = 0;
             z = K - 1;
             for (int k = 0; k < K - 1; ++k) {

@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
             if (!ok) break;
             // ---- epilogue: this thread's observation = TMEM lane t ----
             const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
-            const float u = ((float)(((gi & 1) ? rnd.z : rnd.x) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
+            const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
             ok = mbar_wait(accfull, (uint32_t)(tile_it & 1));
             if (!ok) break;
             tc_fence_after();

@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) big_sweep_tc_kernel(const BigPar
         }
         load_row(tile + tstride, xw);   // prefetch the next tile's row; used at the top of the next iteration
         // this observation's uniform (same counters as the other uncollapsed kernels)
-        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
-        // top 24 bits of the word pair the fp64 kernels turn into a 53-bit uniform
-        const float u = ((float)(((gi & 1) ? rnd.z : rnd.x) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
+        // top 24 bits of the 32-bit word the fp64 kernels use for this observation
+        const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
         ok = mbar_wait(bar1, (uint32_t)(it & 1));
         if (!ok) break;
         tc_fence_after();

@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             const long long i = (blockIdx.x + k * gridDim.x) * 128 + t;
             const bool valid = i < p.N_local;
             const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 1), (uint32_t)(gi >> 33), sid, (uint32_t)j), key);
-            const float u = ((float)(((gi & 1) ? rnd.z : rnd.x) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
+            const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
             const int a = (int)(k % WS_NA), b = (int)(k % WS_NB);
             ok = mbar_wait(acc_full + 8 * a, (uint32_t)((k / WS_NA) & 1));
             if (!ok) break;

@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
         } else {
             const uint2 key = make_uint2((uint32_t)p.seed, chain);
             const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
-            for (int i2 = tid; 2 * i2 < N; i2 += nthr) {
-                uint4 rnd = philox4x32_10(make_uint4((uint32_t)i2, 0u, sid, (uint32_t)j), key);
+            for (int i4 = tid; 4 * i4 < N; i4 += nthr) {
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)i4, 0u, sid, (uint32_t)j), key);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int i = 2 * i2 + h;
+                for (int h = 0; h < 4; ++h) {
+                    const int i = 4 * i4 + h;
                     if (i >= N) break;
-                    const double uu = h ? u53(rnd.z, rnd.w) : u53(rnd.x, rnd.y);
+                    const double uu = u32_unit(philox_word(rnd, h));
                     const int r = p.rowid[i];
                     int z = categorical_icdf(K, [&](int k) { return prob[r + (size_t)U * k]; }, uu);
                     zrow[i] = (uint8_t)(z + 1);
