@@ -31,6 +31,45 @@ __global__ void finalize_z_kernel(int N, int nsamples, int burnin, int K, const 
     }
 }
 
+// Byte-wide output with N and S multiples of 4: 64 x 64 tiles, 32-bit loads along the observations and
+// 32-bit stores along the sweeps (the 1-byte-per-thread version above reached ~1 TB/s of the 6.4).
+__global__ void __launch_bounds__(256) finalize_z_u8x4_kernel(int N, int nsamples, int burnin, int K,
+                                                              const uint8_t *__restrict__ zhist, const int *__restrict__ perm_out,
+                                                              uint8_t *__restrict__ z_orig, uint8_t *__restrict__ z_rel) {
+    __shared__ uint8_t tile[64][68];
+    const int c = blockIdx.z, S = nsamples - burnin, t = threadIdx.x;
+    const int i0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
+    const uint8_t *src = zhist + ((size_t)c * nsamples + burnin) * N;
+    {
+        const int col4 = t & 15;
+        for (int r = t >> 4; r < 64; r += 16) {
+            const int s = s0 + r, i = i0 + 4 * col4;
+            uint32_t v = 0u;
+            if (s < S && i < N) v = *(const uint32_t *)(src + (size_t)s * N + i);   // N % 4 == 0: i + 3 < N
+            *(uint32_t *)&tile[r][4 * col4] = v;
+        }
+    }
+    __syncthreads();
+    const int w = t & 15;
+    const int sw = s0 + 4 * w;
+    if (sw < S) {
+        for (int r = t >> 4; r < 64; r += 16) {
+            const int i = i0 + r;
+            if (i >= N) break;
+            uint32_t o = 0u, rl = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t z = tile[4 * w + q][r];
+                o |= z << (8 * q);
+                if (z_rel) rl |= (uint32_t)((z >= 1 && (int)z <= K) ? perm_out[(size_t)c * S * K + (sw + q) + (size_t)S * (z - 1)] + 1 : 0) << (8 * q);
+            }
+            const size_t off = (size_t)c * S * N + (size_t)S * i + sw;
+            if (z_orig) *(uint32_t *)(z_orig + off) = o;
+            if (z_rel) *(uint32_t *)(z_rel + off) = rl;
+        }
+    }
+}
+
 // Chunk variant for the pipelined download: sweeps [j0, j0 + cs) of every chain, as bytes, laid out
 // [chain][observation][cs] so that the host can widen each row straight into its place in the S x N
 // column-major matrix.  perm_out is indexed with the absolute sweep offset sidx0 = j0 - burnin.
@@ -80,6 +119,9 @@ cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int
         if (elem_bytes == 4)
             finalize_z_kernel<int32_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
                 z_orig ? (int32_t *)z_orig + off : nullptr, z_rel ? (int32_t *)z_rel + off : nullptr);
+        else if (N % 4 == 0 && S % 4 == 0)
+            finalize_z_u8x4_kernel<<<dim3((N + 63) / 64, (S + 63) / 64, nc), 256, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+                z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
         else
             finalize_z_kernel<uint8_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
                 z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
