@@ -358,6 +358,7 @@ def run_grid(a):
     wall_s = time.perf_counter() - t0
     launches = int(L.bmm_launch_count() - l0)
     clk = clocks.stop()
+    plan.check()      # a chain that stopped with an error status invalidates the timing
     plan.close()
 
     # e2e: the public call with host buffers (bit-packed rows in, uint8 allocation history out)
@@ -523,6 +524,7 @@ def main():
     wall_s = time.perf_counter() - t0
     launches = int(L.bmm_launch_count() - l0)
     clk = clocks.stop()
+    plan.check()      # a chain that stopped with an error status invalidates the timing
     plan.close()
 
     # ---- end-to-end arm (e2e): the public call with host buffers, every step ------------------

@@ -235,6 +235,11 @@ class Plan:
     def sync(self):
         _lib.check(self.L.bmm_plan_sync(self.h))
 
+    def check(self):
+        """Raise if any chain of the last run stopped with an error status (fetch with no output buffers)."""
+        out = _lib.Out()
+        _lib.check(self.L.bmm_plan_fetch(self.h, C.byref(out)))
+
     def elapsed_ms(self):
         a, b = C.c_float(), C.c_float()
         _lib.check(self.L.bmm_plan_elapsed_ms(self.h, C.byref(a), C.byref(b)))

@@ -50,12 +50,18 @@ __global__ void lp_table_kernel(const BigParams p) {
     for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < Ppad; d += gridDim.x * blockDim.x) {
         const bool real = d < P;
         const double *w1 = p.w1 + (size_t)K * (real ? d : 0), *w0 = p.w0 + (size_t)K * (real ? d : 0);
+        // theta_kd drawn as exactly 0 or 1 gives log 0 = -inf; the reference then computes 0 * -inf = NaN and
+        // dies (full_gibbs.cpp:97).  Here such a weight is clamped to +-1e4 (a factor 2^-10000 = 0), which is
+        // the limit the reference's formula is reaching for, and the centring only uses finite entries.
         double mean = 0.0;
-        for (int k = 0; k < K; ++k) mean += w1[k] - w0[k];
-        mean /= K;
+        int nfin = 0;
+        for (int k = 0; k < K; ++k) { const double D = w1[k] - w0[k]; if (isfinite(D)) { mean += D; ++nfin; } }
+        mean = nfin ? mean / nfin : 0.0;
         unsigned char *col = img + (size_t)(d >> 3) * LP_NCOL * 16 + (d & 7) * 2;
         for (int k = 0; k < LP_KC; ++k) {
-            const double D = (real && k < K) ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
+            double D = (real && k < K) ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
+            D = fmin(fmax(D, -1.0e4), 1.0e4);
+            if (D != D) D = 0.0;
             const __nv_bfloat16 hi = __double2bfloat16(D);
             const double r1 = D - (double)__bfloat162float(hi);
             const __nv_bfloat16 mid = __double2bfloat16(r1);
@@ -119,11 +125,14 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
         mbar_init(accfull, 1); mbar_init(accempty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        double mean = 0.0;
-        for (int k = 0; k < K; ++k) mean += p.lp_bias[k];
-        mean /= K;
-        for (int k = tid; k < LP_KC; k += LP_THREADS) bias[k] = k < K ? (float)(p.lp_bias[k] - mean) : -INFINITY;
+    {   // shift by the largest finite b_k (a cluster with pi_k = 0 has b_k = -inf and simply never wins)
+        double top = -INFINITY;
+        for (int k = 0; k < K; ++k) { const double b = p.lp_bias[k]; if (isfinite(b)) top = fmax(top, b); }
+        if (!isfinite(top)) top = 0.0;
+        for (int k = tid; k < LP_KC; k += LP_THREADS) {
+            const double b = k < K ? p.lp_bias[k] - top : -INFINITY;
+            bias[k] = b == b ? (float)b : -INFINITY;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -149,8 +158,11 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
             auto load_step = [&](int c) {
                 uint2 v = make_uint2(0u, 0u);
                 if (valid) {
-                    if (2 * c < W) v.x = xb[2 * c];
-                    if (2 * c + 1 < W) v.y = xb[2 * c + 1];
+                    if ((W & 1) == 0) { if (2 * c < W) v = *(const uint2 *)(xb + 2 * c); }   // 8-byte aligned rows
+                    else {
+                        if (2 * c < W) v.x = xb[2 * c];
+                        if (2 * c + 1 < W) v.y = xb[2 * c + 1];
+                    }
                 }
                 return v;
             };

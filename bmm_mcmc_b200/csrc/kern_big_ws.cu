@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         const int k = e % WS_KC, d = e / WS_KC;
         double D = 0.0;
         if (k < K && d < P) D = (p.w1[k + K * d] - p.w0[k + K * d]) * 1.4426950408889634;
+        D = fmin(fmax(D, -1.0e4), 1.0e4);     // theta exactly 0 / 1: log 0 = -inf would make 0 * inf = NaN in the contraction
+        if (D != D) D = 0.0;
         const __nv_bfloat16 hi = __double2bfloat16(D);
         const double r1 = D - (double)__bfloat162float(hi);
         const __nv_bfloat16 mid = __double2bfloat16(r1);
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (k < K) {
             double s0 = 0.0;
             for (int d = 0; d < P; ++d) s0 += p.w0[k + K * d];
-            b = (float)((p.lpi[k] + s0) * 1.4426950408889634);
+            const double bb = (p.lpi[k] + s0) * 1.4426950408889634;
+            b = bb == bb ? (float)fmax(bb, -3.0e38) : -INFINITY;
         }
         bias[k] = b;
     }
