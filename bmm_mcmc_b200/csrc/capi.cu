@@ -148,7 +148,7 @@ struct bmm_plan {
     int deb = 4;                  // bytes per allocation of the device-side R-layout z (1: widened on the host)
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
-    DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias;
+    DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias, cnt_ws;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
     DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
     // data
@@ -401,9 +401,10 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && (K > 32 || P > 112)) {
         CU(pl->lp_table.alloc(bmm::big_lp_table_bytes(P)));
         CU(pl->lp_bias.alloc(128 * 8));
+        CU(pl->cnt_ws.alloc((2 * ((size_t)K + 1) + (size_t)N) * 4, false));
         if (!pl->zhist.p) return fail(BMM_ERR_INVALID, "internal: allocation buffer missing");
     }
-    b.lp_table = pl->lp_table.p; b.lp_bias = pl->lp_bias.as<double>();
+    b.lp_table = pl->lp_table.p; b.lp_bias = pl->lp_bias.as<double>(); b.cnt_ws = pl->cnt_ws.as<int>();
     b.ru = pl->ru.as<double>(); b.ru_slots = a.replay ? a.replay->u_slots : 0;
     b.rpi = pl->rpi.as<double>(); b.rtheta = pl->rtheta.as<double>(); b.ralpha = pl->ralpha.as<double>();
     return BMM_OK;

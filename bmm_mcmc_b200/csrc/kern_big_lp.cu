@@ -14,9 +14,8 @@
 //                                   128 x 384 fp32 accumulator and commits stage-empty / accumulator-full.
 //                      Epilogue: three passes over TMEM (max, sum, inverse-CDF walk) because 128 logits
 //                      do not fit the register file; 1-byte allocation to HBM.
-//   lp_counts_kernel   V_kd = [X]^T onehot(z): CTA (feature group of 256, observation split), the
-//                      MN-major operand layout of kern_big_tc.cu, two 128 x 128 accumulators in TMEM,
-//                      exact integer counts flushed with atomics; c_k as a shared-memory histogram.
+//   (counts)           V_kd, c_k from the allocations: kern_big_counts.cu (counting sort + bit-sliced counters
+//                      on the packed rows; a tcgen05 [X]^T onehot(z) kernel used to sit here and was 10x slower).
 //
 // Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186) at sizes
 // where the reference itself cannot run (its unstabilised exp underflows at P = 4096, full_gibbs.cpp:106).
@@ -279,107 +278,6 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     }
 }
 
-// ---- sufficient statistics ------------------------------------------------------------------------
-constexpr int LC_DG = 256;                          // features per CTA
-constexpr int LC_A_HALF = 16 * 2048;                // [16 chunks][128 obs][16 B] = 128 features
-constexpr int LC_B2 = (LP_KC / 8) * 2048;           // one-hot [16 chunks][128 obs][16 B]
-constexpr int LC_SMEM = 2 * LC_A_HALF + LC_B2 + 64;
-
-__global__ void __launch_bounds__(128, 2) lp_counts_kernel(const BigParams p, const int j, const int nsplit) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int hist[LP_KC];
-    __shared__ uint32_t tmem_slot;
-    const int t = threadIdx.x, warp = t >> 5;
-    const int K = p.K, P = p.P, W = p.W;
-    const int dg = blockIdx.x / nsplit, sp = blockIdx.x % nsplit;
-    unsigned char *A = smem, *B2 = smem + 2 * LC_A_HALF;
-    uint64_t *bar = (uint64_t *)(smem + 2 * LC_A_HALF + LC_B2);
-    const uint32_t bar_a = smem_u32(bar);
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (t == 32) { mbar_init(bar_a, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    hist[t] = 0;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t acc = tmem_slot, lane_sel = (uint32_t)(warp * 32) << 16;
-    constexpr uint32_t IDESC = umma_idesc(128, LP_KC, 1, 1);
-    const uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
-    const long long ntiles = ((long long)p.N_local + 127) / 128;
-    const int w0 = dg * (LC_DG / 32);                // first 32-bit word of this feature group
-    bool ok = true;
-    int it = 0;
-    for (long long tile = sp; tile < ntiles && ok; tile += nsplit, ++it) {
-        const long long i = tile * 128 + t;
-        const bool valid = i < p.N_local;
-        uint32_t xw[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) xw[w] = (valid && w0 + w < W) ? p.xbits[(size_t)i * W + w0 + w] : 0u;
-        const int z = valid ? (int)zrow[i] - 1 : -1;
-        if (it > 0) ok = mbar_wait(bar_a, (uint32_t)((it - 1) & 1));
-        if (!ok) break;
-#pragma unroll
-        for (int ch = 0; ch < 32; ++ch) {
-            const uint32_t byte = xw[ch >> 2] >> ((ch & 3) * 8);
-            *(uint4 *)(A + (ch >> 4) * LC_A_HALF + (ch & 15) * 2048 + t * 16) =
-                make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
-        }
-        {
-            const uint32_t h = z >= 0 ? ((z & 1) ? 0x3F800000u : 0x3F80u) : 0u;
-            const int wsel = (z & 7) >> 1, csel = z >> 3;
-            const uint4 hot = make_uint4(wsel == 0 ? h : 0u, wsel == 1 ? h : 0u, wsel == 2 ? h : 0u, wsel == 3 ? h : 0u);
-#pragma unroll
-            for (int cc = 0; cc < LP_KC / 8; ++cc)
-                *(uint4 *)(B2 + cc * 2048 + t * 16) = (csel == cc) ? hot : make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (dg == 0 && z >= 0) atomicAdd(&hist[z], 1);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(A), b0 = smem_u32(B2);
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    umma_bf16(acc + (uint32_t)(h * LP_KC), umma_desc(a0 + h * LC_A_HALF + kk * 256, 128, 2048),
-                              umma_desc(b0 + kk * 256, 128, 2048), IDESC, (it > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(bar_a);
-        }
-    }
-    if (ok && it > 0) ok = mbar_wait(bar_a, (uint32_t)((it - 1) & 1));
-    if (!ok) *p.status = -10;
-    int *gcnt = p.counts + (size_t)(j & 1) * (K + (size_t)K * P);
-    if (ok && it > 0) {
-        tc_fence_after();
-        for (int h = 0; h < 2; ++h) {
-            const int d = dg * LC_DG + h * 128 + t;
-            for (int c0 = 0; c0 < LP_KC; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(acc + lane_sel + (uint32_t)(h * LP_KC + c0), v);
-                tmem_ld_wait();
-                if (d < P) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int k = c0 + q, n = (int)(__uint_as_float(v[q]) + 0.5f);
-                        if (k < K && n) atomicAdd(&gcnt[K + k + (size_t)K * d], n);
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (dg == 0 && t < K && hist[t]) atomicAdd(&gcnt[t], hist[t]);
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(acc), "r"(256) : "memory");
-    }
-}
-
 }  // namespace
 
 // float path, K <= 128 clusters, any P (padded to a multiple of 64 with zero weights)
@@ -394,7 +292,6 @@ cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStr
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(lp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LpSmem::TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(lp_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -403,13 +300,11 @@ cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStr
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     const int ctas = (int)(ntiles < sm_count ? ntiles : sm_count);
     lp_sweep_kernel<<<ctas, LP_THREADS, LpSmem::TOTAL, st>>>(p, j);
-    const int ndg = (p.P + LC_DG - 1) / LC_DG;
-    int nsplit = (2 * sm_count + ndg - 1) / ndg;
-    if (nsplit > ntiles) nsplit = (int)ntiles;
-    if (nsplit < 1) nsplit = 1;
-    lp_counts_kernel<<<ndg * nsplit, 128, LC_SMEM, st>>>(p, j, nsplit);
-    g_launches += 4;
-    return cudaGetLastError();
+    g_launches += 3;
+    // counts of this sweep from the allocations just written (kern_big_counts.cu)
+    const uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
+    return launch_big_counts(p.N_local, p.K, p.P, p.W, p.xbits, zrow, p.counts + (size_t)(j & 1) * (p.K + (size_t)p.K * p.P),
+                             p.cnt_ws, sm_count, st);
 }
 
 }  // namespace bmm

@@ -118,6 +118,7 @@ struct BigParams {
     double *theta_rel_out;            // [K*P*S] relabelled theta history, or nullptr
     void *lp_table;                   // large-P tensor path: split weight table in operand-image order
     double *lp_bias;                  // [128] uncentred b_k
+    int *cnt_ws;                      // scratch of launch_big_counts: 2*(K+1) + N_local ints
     const double *ru; int ru_slots;   // replay
     const double *rpi, *rtheta, *ralpha;
 };
@@ -132,6 +133,10 @@ bool big_tc_supported(const BigParams &p);
 cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStream_t st);
 // same shapes, warp-specialised (producer / MMA / epilogue warps over mbarrier rings): kern_big_ws.cu
 cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st);
+// sufficient statistics from the bit-packed rows (kern_big_counts.cu): counting sort by cluster + bit-sliced
+// per-variable counters; counts must be zero on entry, ws holds 2*(K+1) + N ints
+cudaError_t launch_big_counts(long long N, int K, int P, int W, const uint32_t *xbits, const uint8_t *z, int *counts,
+                              int *ws, int sm_count, cudaStream_t st);
 // large-P / large-K tcgen05 path (kern_big_lp.cu): pipelined k-loop contraction + counts kernel
 bool big_lp_supported(const BigParams &p);
 size_t big_lp_table_bytes(int P);
