@@ -1,25 +1,25 @@
 // Large-P / large-K tensor-core path of the grid sampler (BASELINE config C5: N = 1e6, P = 4096,
-// K = 128).  Same algebra as kern_big_tc.cu -- loglh = X D^T + b on tcgen05 with D split into three
-// bf16 terms, sufficient statistics as [X]^T onehot(z) -- but P no longer fits one shared-memory tile,
+// K = 128).  Same algebra as kern_big_tc.cu -- loglh = X D^T + b on tcgen05 with D split into two
+// fp16 terms, sufficient statistics as [X]^T onehot(z) -- but P no longer fits one shared-memory tile,
 // so the contraction runs as a pipelined k-loop and the statistics as a second kernel:
 //
-//   lp_table_kernel    per sweep: D (log2 units) split hi|mid|lo, written to global memory already in
-//                      the shared-memory operand image ([64-feature step][16-B chunk][3*128 rows][16 B]),
-//                      so a stage is one contiguous 48 KB block.
-//   lp_sweep_kernel    persistent, one 128-observation tile at a time per CTA, 2-stage mbarrier pipeline:
-//                        warps 0-3  expand 64 bits per observation and step into the bf16 A stage, later
-//                                   run the epilogue (one observation per thread = one TMEM lane);
+//   lp_table_kernel    per sweep: D (log2 units) split into fp16 hi|lo (22 significant bits; the 0/1 rows are
+//                      exact in fp16), written to global memory already in the shared-memory operand image
+//                      ([64-feature step][16-B chunk][2*128 rows][16 B]), so a stage is one contiguous 32 KB block.
+//   lp_sweep_kernel    persistent, one 128-observation tile at a time per CTA, 4-stage mbarrier pipeline:
+//                        warps 0-3  expand 64 bits per observation and step into the fp16 A stage;
 //                        warp 4     one thread streams the B stage with cp.async.bulk (mbarrier tx count);
-//                        warp 5     one thread issues 8 tcgen05.mma (M128 N192 K16) per step into a
-//                                   128 x 384 fp32 accumulator and commits stage-empty / accumulator-full.
-//                      Epilogue: three passes over TMEM (max, sum, inverse-CDF walk) because 128 logits
-//                      do not fit the register file; 1-byte allocation to HBM.
+//                        warp 5     one thread issues 4 tcgen05.mma (M128 N256 K16) per step into one of two
+//                                   128 x 256 fp32 accumulators in TMEM and commits stage-empty / accumulator-full;
+//                        warps 6-9  epilogue of the previous tile while the next one is being multiplied:
+//                                   three passes over TMEM (max, sum, inverse-CDF walk) because 128 logits
+//                                   do not fit the register file; 1-byte allocation to HBM.
 //   (counts)           V_kd, c_k from the allocations: kern_big_counts.cu (counting sort + bit-sliced counters
 //                      on the packed rows; a tcgen05 [X]^T onehot(z) kernel used to sit here and was 10x slower).
 //
 // Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186) at sizes
 // where the reference itself cannot run (its unstabilised exp underflows at P = 4096, full_gibbs.cpp:106).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -29,12 +29,13 @@ namespace bmm {
 namespace {
 
 constexpr int LP_KC = 128;                  // clusters, padded
-constexpr int LP_NCOL = 3 * LP_KC;          // accumulator columns: hi | mid | lo
+constexpr int LP_NCOL = 2 * LP_KC;          // accumulator columns: hi | lo
 constexpr int LP_DK = 64;                   // features per pipeline step
 constexpr int LP_A_STAGE = 8 * 2048;        // [8 chunks][128 rows][16 B]
-constexpr int LP_B_STAGE = 8 * LP_NCOL * 16;  // [8 chunks][384 rows][16 B]
+constexpr int LP_B_STAGE = 8 * LP_NCOL * 16;  // [8 chunks][256 rows][16 B]
 constexpr int LP_STAGE = LP_A_STAGE + LP_B_STAGE;
-constexpr int LP_THREADS = 192;
+constexpr int LP_NS = 4;                    // pipeline stages (48 KB each)
+constexpr int LP_THREADS = 320;             // warps 0-3 rows -> A stage, 4 B streamer, 5 MMA issuer, 6-9 epilogue
 constexpr double LOG2E_D = 1.4426950408889634;
 
 // ---- per-sweep tables -----------------------------------------------------------------------------
@@ -61,13 +62,10 @@ __global__ void lp_table_kernel(const BigParams p) {
             double D = (real && k < K) ? (w1[k] - w0[k] - mean) * LOG2E_D : 0.0;
             D = fmin(fmax(D, -1.0e4), 1.0e4);
             if (D != D) D = 0.0;
-            const __nv_bfloat16 hi = __double2bfloat16(D);
-            const double r1 = D - (double)__bfloat162float(hi);
-            const __nv_bfloat16 mid = __double2bfloat16(r1);
-            const __nv_bfloat16 lo = __double2bfloat16(r1 - (double)__bfloat162float(mid));
-            *(__nv_bfloat16 *)(col + (0 * LP_KC + k) * 16) = hi;
-            *(__nv_bfloat16 *)(col + (1 * LP_KC + k) * 16) = mid;
-            *(__nv_bfloat16 *)(col + (2 * LP_KC + k) * 16) = lo;
+            const __half hi = __double2half(D);
+            const __half lo = __double2half(D - (double)__half2float(hi));
+            *(__half *)(col + (0 * LP_KC + k) * 16) = hi;
+            *(__half *)(col + (1 * LP_KC + k) * 16) = lo;
         }
     }
 }
@@ -86,21 +84,19 @@ __global__ void lp_bias_kernel(const BigParams p) {
 
 // ---- the sweep ------------------------------------------------------------------------------------
 struct LpSmem {
-    static constexpr int BIAS_OFF = LP_STAGE * 2;
+    static constexpr int BIAS_OFF = LP_STAGE * LP_NS;
     static constexpr int BAR_OFF = BIAS_OFF + LP_KC * 4;
-    static constexpr int TOTAL = BAR_OFF + 8 * 8 + 16;
+    static constexpr int TOTAL = BAR_OFF + (2 * LP_NS + 4) * 8 + 16;
 };
 
-// logits of 32 clusters [c0, c0+32) of this thread's observation: hi + mid + lo + bias
+// logits of 32 clusters [c0, c0+32) of this thread's observation: hi + lo + bias
 __device__ __forceinline__ void lp_logits32(uint32_t acc, uint32_t lane_sel, int c0, const float *bias, float (&l)[32]) {
+    uint32_t v[32], w[32];
+    tmem_ld32(acc + lane_sel + (uint32_t)c0, v);
+    tmem_ld32(acc + lane_sel + (uint32_t)(LP_KC + c0), w);
+    tmem_ld_wait();
 #pragma unroll
-    for (int part = 0; part < 3; ++part) {
-        uint32_t v[32];
-        tmem_ld32(acc + lane_sel + (uint32_t)(part * LP_KC + c0), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) l[q] = part == 0 ? __uint_as_float(v[q]) + bias[c0 + q] : l[q] + __uint_as_float(v[q]);
-    }
+    for (int q = 0; q < 32; ++q) l[q] = (__uint_as_float(v[q]) + __uint_as_float(w[q])) + bias[c0 + q];
 }
 
 __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams p, const int j) {
@@ -109,19 +105,21 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     const int K = p.K, W = p.W;
     const int nsteps = (p.P + LP_DK - 1) / LP_DK;   // the last step may be partial: missing words read as zero bits
     float *bias = (float *)(smem + LpSmem::BIAS_OFF);
-    uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[2], empty[2], accfull, accempty
-    uint32_t *tmem_slot = (uint32_t *)(bars + 6);
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
-    const uint32_t accfull = smem_u32(&bars[4]), accempty = smem_u32(&bars[5]);
+    uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[NS], empty[NS], accfull[2], accempty[2]
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * LP_NS + 4);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[LP_NS]);
+    const uint32_t accfull0 = smem_u32(&bars[2 * LP_NS]), accempty0 = smem_u32(&bars[2 * LP_NS + 2]);
 
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 160) {
-        mbar_init(full0, 129); mbar_init(full0 + 8, 129);      // 128 row threads + the bulk-copy thread
-        mbar_init(empty0, 1); mbar_init(empty0 + 8, 1);        // tcgen05.commit
-        mbar_init(accfull, 1); mbar_init(accempty, 128);
+        for (int s = 0; s < LP_NS; ++s) {
+            mbar_init(full0 + 8 * s, 129);     // 128 row threads + the bulk-copy thread
+            mbar_init(empty0 + 8 * s, 1);      // tcgen05.commit
+        }
+        for (int h = 0; h < 2; ++h) { mbar_init(accfull0 + 8 * h, 1); mbar_init(accempty0 + 8 * h, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // shift by the largest finite b_k (a cluster with pi_k = 0 has b_k = -inf and simply never wins)
@@ -139,17 +137,13 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     const uint32_t acc = *tmem_slot;
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     bool ok = true;
-    long long g = 0;       // pipeline step counter of this CTA (all roles advance it identically)
+    long long g = 0;       // pipeline step counter of this CTA (the three pipeline roles advance it identically)
     int tile_it = 0;
 
     if (warp < 4) {
-        // ================= A producers, then epilogue =================
+        // ================= rows -> fp16 A stages =================
         const int t = tid;
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
-        const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
-        uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
             const long long i = tile * 128 + t;
             const bool valid = i < p.N_local;
             const uint32_t *xb = p.xbits + (size_t)(valid ? i : 0) * W;
@@ -165,18 +159,19 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                 }
                 return v;
             };
-            uint2 nxt = load_step(0);
+            uint2 nxt = load_step(0), nxt2 = load_step(1);
             for (int c = 0; c < nsteps && ok; ++c, ++g) {
                 const uint2 cur = nxt;
-                if (c + 1 < nsteps) nxt = load_step(c + 1);
+                nxt = nxt2;
+                if (c + 2 < nsteps) nxt2 = load_step(c + 2);
                 uint4 ex[8];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                     const uint32_t byte = (ch < 4 ? cur.x : cur.y) >> ((ch & 3) * 8);
-                    ex[ch] = make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
+                    ex[ch] = make_uint4(bits2_f16x2(byte), bits2_f16x2(byte >> 2), bits2_f16x2(byte >> 4), bits2_f16x2(byte >> 6));
                 }
-                const int s = (int)(g & 1);
-                const long long n = g >> 1;
+                const int s = (int)(g % LP_NS);
+                const long long n = g / LP_NS;
                 if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
                 if (!ok) break;
                 unsigned char *A = smem + s * LP_STAGE;
@@ -185,24 +180,76 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                 fence_async_smem();
                 mbar_arrive(full0 + 8 * s);
             }
-            if (!ok) break;
-            // ---- epilogue: this thread's observation = TMEM lane t ----
+        }
+    } else if (warp == 4) {
+      if (tid == 128) {
+        // ================= B stage streamer =================
+        const unsigned char *img = (const unsigned char *)p.lp_table;
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x)
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const int s = (int)(g % LP_NS);
+                const long long n = g / LP_NS;
+                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+                if (!ok) break;
+                const uint32_t dst = smem_u32(smem + s * LP_STAGE + LP_A_STAGE);
+                mbar_arrive_expect_tx(full0 + 8 * s, LP_B_STAGE);
+                bulk_g2s(dst, img + (size_t)c * LP_B_STAGE, LP_B_STAGE, full0 + 8 * s);
+            }
+      }
+      __syncwarp();
+    } else if (warp == 5) {
+      if (tid == 160) {
+        // ================= MMA issuer: M128 N256 K16, accumulator buffer = tile parity =================
+        constexpr uint32_t IDESC = umma_idesc_f16(128, LP_NCOL, 0, 0);
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
+            const int h = tile_it & 1, use = tile_it >> 1;
+            if (use > 0) ok = mbar_wait(accempty0 + 8 * h, (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const int s = (int)(g % LP_NS);
+                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g / LP_NS) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + kk * 2 * 2048, 2048, 128),
+                              umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);
+                if (c == nsteps - 1) umma_commit(accfull0 + 8 * h);
+            }
+        }
+      }
+      __syncwarp();
+    } else {
+        // ================= epilogue: this thread's observation = TMEM lane =================
+        const int q4 = warp & 3;                          // TMEM lane quadrant this warp may read
+        const int t = q4 * 32 + (tid & 31);
+        const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
+        const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+        uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
+        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
+            const long long i = tile * 128 + t;
+            const bool valid = i < p.N_local;
+            const int h = tile_it & 1, use = tile_it >> 1;
+            const uint32_t acch = acc + (uint32_t)(h * LP_NCOL);
             const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
             const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
             const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
-            ok = mbar_wait(accfull, (uint32_t)(tile_it & 1));
+            ok = mbar_wait(accfull0 + 8 * h, (uint32_t)(use & 1));
             if (!ok) break;
             tc_fence_after();
             float l[32];
             float mx = -INFINITY;
             for (int c0 = 0; c0 < LP_KC; c0 += 32) {
-                lp_logits32(acc, lane_sel, c0, bias, l);
+                lp_logits32(acch, lane_sel, c0, bias, l);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) mx = fmaxf(mx, l[q]);
             }
             float sum = 0.f;
             for (int c0 = 0; c0 < LP_KC; c0 += 32) {
-                lp_logits32(acc, lane_sel, c0, bias, l);
+                lp_logits32(acch, lane_sel, c0, bias, l);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) sum += ex2_ftz(l[q] - mx);
             }
@@ -211,7 +258,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
             float run = 0.f;
             int z = 0;
             for (int c0 = 0; c0 < LP_KC; c0 += 32) {
-                lp_logits32(acc, lane_sel, c0, bias, l);
+                lp_logits32(acch, lane_sel, c0, bias, l);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const float e = ex2_ftz(l[q] - mx);
@@ -223,51 +270,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                 }
             }
             tc_fence_before();
-            mbar_arrive(accempty);             // the accumulator may be overwritten by the next tile
+            mbar_arrive(accempty0 + 8 * h);    // this accumulator buffer may be overwritten
             z = min(z, K - 1);
             if (valid) zrow[i] = (uint8_t)(z + 1);
         }
-    } else if (warp == 4) {
-      if (tid == 128) {
-        // ================= B stage streamer =================
-        const unsigned char *img = (const unsigned char *)p.lp_table;
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x)
-            for (int c = 0; c < nsteps && ok; ++c, ++g) {
-                const int s = (int)(g & 1);
-                const long long n = g >> 1;
-                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
-                if (!ok) break;
-                const uint32_t dst = smem_u32(smem + s * LP_STAGE + LP_A_STAGE);
-                mbar_arrive_expect_tx(full0 + 8 * s, LP_B_STAGE);
-                bulk_g2s(dst, img + (size_t)c * LP_B_STAGE, LP_B_STAGE, full0 + 8 * s);
-            }
-      }
-      __syncwarp();
-    } else {
-      if (tid == 160) {
-        // ================= MMA issuer =================
-        constexpr uint32_t IDESC = umma_idesc(128, LP_NCOL / 2, 0, 0);
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
-            if (tile_it > 0) ok = mbar_wait(accempty, (uint32_t)((tile_it - 1) & 1));
-            for (int c = 0; c < nsteps && ok; ++c, ++g) {
-                const int s = (int)(g & 1);
-                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g >> 1) & 1));
-                if (!ok) break;
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        umma_bf16(acc + (uint32_t)(h * (LP_NCOL / 2)), umma_desc(a0 + kk * 2 * 2048, 2048, 128),
-                                  umma_desc(b0 + kk * 2 * (LP_NCOL * 16) + h * (LP_NCOL / 2) * 16, LP_NCOL * 16, 128),
-                                  IDESC, (c | kk) ? 1u : 0u);
-                umma_commit(empty0 + 8 * s);
-                if (c == nsteps - 1) umma_commit(accfull);
-            }
-        }
-      }
-      __syncwarp();
     }
     if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
     tc_fence_before();

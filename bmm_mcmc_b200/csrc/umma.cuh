@@ -20,6 +20,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn, int b_
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same instruction descriptor with fp16 operands (formats 0) and an fp32 accumulator
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -69,6 +74,11 @@ __device__ __forceinline__ uint32_t bits2_bf16x2(uint32_t t) {
     return (((t & 3u) * 0x8001u) & 0x00010001u) * 0x3F80u;
 }
 
+
+// two bits -> two fp16 0.0 / 1.0
+__device__ __forceinline__ uint32_t bits2_f16x2(uint32_t t) {
+    return (((t & 3u) * 0x8001u) & 0x00010001u) * 0x3C00u;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
