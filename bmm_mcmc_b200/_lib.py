@@ -53,7 +53,7 @@ class Out(C.Structure):
 
 EXPORTS = [
     "bmm_gibbs_full", "bmm_gibbs_stickbreaking", "bmm_gibbs_collapsed", "bmm_gibbs_dp", "bmm_stephens_batch",
-    "bmm_stephens_online", "bmm_assign", "bmm_assign_warp", "bmm_rdirichlet", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
+    "bmm_stephens_online", "bmm_assign", "bmm_assign_warp", "bmm_grid_cost", "bmm_rdirichlet", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
     "bmm_plan_sync", "bmm_plan_elapsed_ms", "bmm_plan_fetch", "bmm_plan_destroy", "bmm_dist_unique_id",
     "bmm_dist_init", "bmm_dist_finalize", "bmm_dist_p2p_local", "bmm_dist_p2p_attach", "bmm_dist_p2p_detach", "bmm_plan_kernel_ms", "bmm_host_alloc", "bmm_host_free", "bmm_release_cache", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_version",
 ]
@@ -86,6 +86,8 @@ def lib():
         L.bmm_plan_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.bmm_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
         L.bmm_host_free.argtypes = [C.c_void_p]
+        L.bmm_grid_cost.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_double)]
         _lib = L
     return _lib
 

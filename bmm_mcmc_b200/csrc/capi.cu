@@ -428,6 +428,7 @@ int run_big(bmm_plan *pl) {
     const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
     const long long N = b.N_local;
     const size_t NK = (size_t)N * K;
+    const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
     if (pl->relabel) CU(bmm::launch_grid_identity_perm(K, K, pl->perm_cur.as<int>(), pl->stream));
     for (int j = 1; j < ns; ++j) {
         bmm::BigParams bj = b;
@@ -459,7 +460,7 @@ int run_big(bmm_plan *pl) {
                 CU(cudaMemsetAsync(flag, 0, sizeof(int), pl->stream));
                 for (int t = 0; t < M; ++t) {
                     CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
-                                             pl->sm_count, pl->stream));
+                                             pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
                     if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
                         return fail(BMM_ERR_NCCL, bmm::dist_error());
                     CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
@@ -472,7 +473,7 @@ int run_big(bmm_plan *pl) {
             }
         } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
             CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), 0, pl->cost_acc.as<double>(),
-                                     pl->sm_count, pl->stream));
+                                     pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
             if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
                 return fail(BMM_ERR_NCCL, bmm::dist_error());
             CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
@@ -1069,6 +1070,26 @@ int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm) {
     CU(pd.alloc((size_t)K * 4)); CU(ws.alloc(bmm::assign_ws_bytes(K)));
     CU(bmm::launch_grid_assign(K, ad.as<double>(), ws.as<char>(), pd.as<int>(), nullptr, 1, 0));
     CU(cudaMemcpy(perm, pd.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+// Cost contraction of the grid path's relabelling on host matrices (row-major float N x K):
+// out[k + K*l] = sum_i log q_ik * p_il, out[K*K + l] = sum_i p_il^2 (or p log p when use_logp).
+int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t use_logp, int32_t tensor, double *out) {
+    if (!p || !q || !out || N < 1 || K < 1 || K > 128) return fail(BMM_ERR_INVALID, "bad grid_cost arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (tensor && !bmm::grid_cost_tc_supported(N, K)) return fail(BMM_ERR_INVALID, "tensor cost kernel needs 64 < K <= 128, K % 8 == 0");
+    DevBuf pd, qd, od, sd;
+    TRY(upload(pd, p, (size_t)N * K));
+    TRY(upload(qd, q, (size_t)N * K));
+    CU(od.alloc(((size_t)K * K + K) * 8)); CU(sd.alloc(16));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    CU(bmm::launch_grid_cost(N, K, pd.as<float>(), qd.as<float>(), use_logp, od.as<double>(), sms, 0, tensor, sd.as<int>()));
+    int st[2] = {0, 0};
+    CU(cudaMemcpy(st, sd.p, 8, cudaMemcpyDeviceToHost));
+    if (st[0]) return fail(st[0], "grid cost kernel failed");
+    CU(cudaMemcpy(out, od.p, ((size_t)K * K + K) * 8, cudaMemcpyDeviceToHost));
     return BMM_OK;
 }
 

@@ -1,0 +1,202 @@
+// Stephens cost matrix of the grid path on tcgen05 for 64 < K <= 128:
+//   G(k,l) = sum_i log q_ik * p_il,   s_l = sum_i p_il^2  (online)  or  sum_i p_il log p_il  (batch)
+// (/root/reference/src/stephens.cpp:45-53,76-84), a K x K contraction over the N observations of two
+// row-major fp32 matrices.  The CUDA-core version in kern_big_relabel.cu runs at a quarter of the FMA
+// peak (1.97 ms at N = 1e6, K = 128); here the contraction is a 128 x 128 x N GEMM whose operands are
+// produced on the fly: 8 warps stream 64 observations of P and Q per stage, take the logarithm, split
+// every value into fp16 hi + lo (22 significant bits) and store the MN-major operand image; one thread
+// issues hi*hi + hi*lo + lo*hi (12 MMAs M128 N128 K16 per stage) into one fp32 accumulator in TMEM.
+// The kernel is then bound by reading P and Q once (2 x N x K x 4 bytes).  Per-CTA partial sums go to
+// the fp64 cost buffer with atomics, like the CUDA-core kernel.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace bmm {
+namespace {
+
+constexpr int CT_ROWS = 64;                      // observations per stage
+constexpr int CT_MAT = 16 * CT_ROWS * 16;        // [16 column groups of 8][64 obs][16 B] = 16 KB
+constexpr int CT_STAGE = 4 * CT_MAT;             // LQ hi | LQ lo | P hi | P lo
+constexpr int CT_NS = 3;
+constexpr int CT_THREADS = 288;                  // warps 0-7 producers, warp 8 MMA issuer
+constexpr int CT_SMEM = CT_NS * CT_STAGE + 2 * CT_NS * 8 + 8 + 16;
+
+// 8 floats -> 8 fp16 hi (one 16-byte chunk) and 8 fp16 lo
+__device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+        h[q] = *(const uint32_t *)&hh;
+        l[q] = *(const uint32_t *)&ll;
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N, int K, const float *__restrict__ P,
+                                                                     const float *__restrict__ Q, int use_logp,
+                                                                     double *out, int *status) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bars = (uint64_t *)(smem + CT_NS * CT_STAGE);       // full[NS], empty[NS], done
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * CT_NS + 1);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[CT_NS]), done = smem_u32(&bars[2 * CT_NS]);
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < CT_NS; ++s) { mbar_init(full0 + 8 * s, 256); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t acc = *tmem_slot;
+    const long long nst = (N + CT_ROWS - 1) / CT_ROWS;
+    // contiguous range of stages per CTA
+    const long long per = (nst + gridDim.x - 1) / gridDim.x;
+    const long long st0 = (long long)blockIdx.x * per, st1 = min(st0 + per, nst);
+    bool ok = true;
+
+    if (warp < 8) {
+        // ---- producers: lane = (column group within a quad, row within an octet) so that every quarter-warp
+        //      store covers 128 contiguous bytes of one column group ----
+        const int cg = (warp & 3) * 4 + (lane >> 3);       // column group: columns [8 cg, 8 cg + 8)
+        const int rl = lane & 7, oct0 = warp >> 2;          // row octets oct0, oct0 + 2, oct0 + 4, oct0 + 6
+        const bool cols = cg * 8 < K;                       // K % 8 == 0
+        float sacc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sacc[q] = 0.f;
+        long long g = 0;
+        for (long long st = st0; st < st1 && ok; ++st, ++g) {
+            float4 pv[4][2], qv[4][2];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const long long i = st * CT_ROWS + (oct0 + 2 * m) * 8 + rl;
+                if (cols && i < N) {
+                    const float4 *pp = (const float4 *)(P + (size_t)i * K + cg * 8);
+                    const float4 *qq = (const float4 *)(Q + (size_t)i * K + cg * 8);
+                    pv[m][0] = __ldg(pp); pv[m][1] = __ldg(pp + 1);
+                    qv[m][0] = __ldg(qq); qv[m][1] = __ldg(qq + 1);
+                } else {
+                    pv[m][0] = pv[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[m][0] = qv[m][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+            }
+            const int s = (int)(g % CT_NS);
+            const long long n = g / CT_NS;
+            if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+            if (!ok) break;
+            unsigned char *stage = smem + s * CT_STAGE;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float p8[8] = {pv[m][0].x, pv[m][0].y, pv[m][0].z, pv[m][0].w, pv[m][1].x, pv[m][1].y, pv[m][1].z, pv[m][1].w};
+                const float q8[8] = {qv[m][0].x, qv[m][0].y, qv[m][0].z, qv[m][0].w, qv[m][1].x, qv[m][1].y, qv[m][1].z, qv[m][1].w};
+                float l8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    l8[q] = __logf(q8[q]);
+                    sacc[q] += use_logp ? (p8[q] > 0.f ? p8[q] * __logf(p8[q]) : 0.f) : p8[q] * p8[q];
+                }
+                uint4 hi, lo;
+                const int off = cg * (CT_ROWS * 16) + ((oct0 + 2 * m) * 8 + rl) * 16;
+                split8(l8, hi, lo);
+                *(uint4 *)(stage + 0 * CT_MAT + off) = hi;
+                *(uint4 *)(stage + 1 * CT_MAT + off) = lo;
+                split8(p8, hi, lo);
+                *(uint4 *)(stage + 2 * CT_MAT + off) = hi;
+                *(uint4 *)(stage + 3 * CT_MAT + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * s);
+        }
+        // column sums: the 8 lanes of an octet hold the same columns
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v = sacc[q];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (rl == 0 && cols) atomicAdd(&out[(size_t)K * K + cg * 8 + q], (double)v);
+        }
+    } else if (tid == 256) {
+        // ---- MMA issuer ----
+        constexpr uint32_t IDESC = umma_idesc_f16(128, 128, 1, 1);
+        long long g = 0;
+        for (long long st = st0; st < st1 && ok; ++st, ++g) {
+            const int s = (int)(g % CT_NS);
+            ok = mbar_wait(full0 + 8 * s, (uint32_t)((g / CT_NS) & 1));
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t b = smem_u32(smem + s * CT_STAGE);
+#pragma unroll
+            for (int kk = 0; kk < CT_ROWS / 16; ++kk) {
+                const uint64_t ah = umma_desc(b + 0 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
+                const uint64_t al = umma_desc(b + 1 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
+                const uint64_t bh = umma_desc(b + 2 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
+                const uint64_t bl = umma_desc(b + 3 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
+                umma_bf16(acc, ah, bh, IDESC, (g > 0 || kk > 0) ? 1u : 0u);
+                umma_bf16(acc, ah, bl, IDESC, 1u);
+                umma_bf16(acc, al, bh, IDESC, 1u);
+            }
+            umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(done);
+    }
+    __syncwarp();
+    // ---- epilogue: warps 0-3, TMEM lane = k, column = l ----
+    if (warp < 4 && st0 < st1) {
+        if (ok) ok = mbar_wait(done, 0u);
+        if (ok) {
+            tc_fence_after();
+            const int k = warp * 32 + lane;
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (k < K) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (c0 + q < K) atomicAdd(&out[k + (size_t)K * (c0 + q)], (double)__uint_as_float(v[q]));
+                }
+            }
+        }
+    }
+    if (!ok) *status = -10;  // BMM_ERR_TIMEOUT
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(acc), "r"(128) : "memory");
+    }
+}
+
+}  // namespace
+
+bool grid_cost_tc_supported(long long N, int K) { return K > 64 && K <= 128 && (K % 8) == 0 && N >= 1; }
+
+// acc must be zero on entry
+cudaError_t launch_grid_cost_tc(long long N, int K, const float *P, const float *Q, int use_logp, double *acc, int *status,
+                                int sm_count, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(grid_cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const long long nst = (N + CT_ROWS - 1) / CT_ROWS;
+    const int grid = (int)(nst < sm_count ? nst : sm_count);
+    grid_cost_tc_kernel<<<grid, CT_THREADS, CT_SMEM, st>>>(N, K, P, Q, use_logp, acc, status);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace bmm

@@ -20,7 +20,7 @@
 namespace bmm {
 namespace {
 
-constexpr int CNT_SLICE = 2048;   // sorted observations per block of cnt_accum_kernel
+constexpr int CNT_SLICE = 512;   // sorted observations per block of cnt_accum_kernel
 
 __global__ void cnt_hist_kernel(long long N, int K, const uint8_t *__restrict__ z, int *__restrict__ ck) {
     __shared__ int h[256];

@@ -11,6 +11,8 @@
 //     grid_qupdate_kernel Q' = j (Q + P[:, perm]) / (j + 1)   (quirks 3, 5)
 //   batch (stephens.cpp:6-64), once at j == burnin - 1 over the M stored sweeps: 100 x { Q = mean of the
 //     permuted slices; per slice C_t(k,l) = sum_i p (log p - log q); assignment } with the same kernels.
+#include <cstdlib>
+
 #include "assign.cuh"
 #include "kernels.h"
 
@@ -323,9 +325,12 @@ cudaError_t launch_grid_zfreq(long long N, int K, const uint8_t *z, const int *p
 }
 
 cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q, int use_logp, double *acc,
-                             int sm_count, cudaStream_t st) {
+                             int sm_count, cudaStream_t st, int tc, int *status) {
     cudaError_t e = cudaMemsetAsync(acc, 0, ((size_t)K * K + K) * sizeof(double), st);
     if (e != cudaSuccess) return e;
+    static const bool no_tc = getenv("BMM_NO_TC") != nullptr;  // A/B switch
+    if (tc && status && !no_tc && grid_cost_tc_supported(N, K))
+        return launch_grid_cost_tc(N, K, P, Q, use_logp, acc, status, sm_count, st);
     const long long ntiles = (N + GC_TP - 1) / GC_TP;
     const int grid = (int)(ntiles < 2LL * sm_count ? (ntiles < 1 ? 1 : ntiles) : 2LL * sm_count);
     const int T = (K + 15) / 16;

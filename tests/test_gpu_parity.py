@@ -501,6 +501,31 @@ def test_assign_warp_jv_matches_lpsolve(oracle):
         assert np.array_equal(perm, s_o.argmax(0)), K
 
 
+@pytest.mark.parametrize("N,K,use_logp", [(5000, 128, 0), (777, 72, 1), (64, 128, 0), (20011, 96, 1)])
+def test_grid_cost_kernels_match_float64(N, K, use_logp):
+    """Cost contraction of the grid path's relabelling (stephens.cpp:45-53,76-84): the tcgen05 kernel (fp16 hi/lo
+    split operands) and the CUDA-core kernel against numpy float64, tolerance 2e-5 of the largest entry."""
+    _need_gpu()
+    import ctypes as C
+    L = _lib.lib()
+    rng = np.random.default_rng(N + K)
+    p = rng.dirichlet(np.full(K, 0.3), N).astype(np.float32)
+    q = rng.dirichlet(np.full(K, 0.5), N).astype(np.float32)
+    q = np.maximum(q, np.float32(1e-6))
+    p[p < 1e-30] = 0.0
+    G = np.log(q.astype(np.float64)).T @ p.astype(np.float64)              # G[k, l]
+    pd = p.astype(np.float64)
+    s = np.where(pd > 0, pd * np.log(np.where(pd > 0, pd, 1.0)), 0.0).sum(0) if use_logp else (pd * pd).sum(0)
+    fp = C.POINTER(C.c_float)
+    for tensor in (1, 0):
+        out = np.zeros(K * K + K)
+        _lib.check(L.bmm_grid_cost(N, K, p.ctypes.data_as(fp), q.ctypes.data_as(fp), use_logp, tensor,
+                                   out.ctypes.data_as(C.POINTER(C.c_double))))
+        Gg = out[:K * K].reshape(K, K).T                                     # out[k + K*l]
+        assert np.abs(Gg - G).max() <= 2e-5 * np.abs(G).max(), (tensor, np.abs(Gg - G).max(), np.abs(G).max())
+        assert np.abs(out[K * K:] - s).max() <= 2e-5 * max(1.0, np.abs(s).max()), tensor
+
+
 # ---- edge cases ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,P,K", [(1, 1, 1), (2, 1, 2), (7, 33, 3), (50, 64, 5), (40, 70, 9)])
 def test_edge_shapes_replay_all_samplers(oracle, N, P, K):
