@@ -266,7 +266,19 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                     z += (run <= target) ? 1 : 0;
                     if (p.probs_out && valid && c0 + q < K)
                         p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * (c0 + q)] = (double)(e * inv);
-                    if (p.probs_f32 && valid && c0 + q < K) p.probs_f32[(size_t)i * K + c0 + q] = e * inv;
+                    l[q] = e * inv;
+                }
+                if (p.probs_f32 && valid) {        // this observation's row of P, 16 bytes at a time when aligned
+                    float *dst = p.probs_f32 + (size_t)i * K + c0;
+                    if ((K & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4)
+                            if (c0 + q < K) *(float4 *)(dst + q) = make_float4(l[q], l[q + 1], l[q + 2], l[q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (c0 + q < K) dst[q] = l[q];
+                    }
                 }
             }
             tc_fence_before();
