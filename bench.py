@@ -211,7 +211,11 @@ GRID_WORKLOADS = {
     "c4": dict(sampler="stickbreaking", N=10_000_000, P=64, K=32, nsamples=101, burnin=11, alpha=1.0,
                precision="fp32", cpu_N=60_000, cpu_ns=6,
                label="C4: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1"),
-    # BASELINE.json configs[4] (relabelling on the grid path is not built yet: relabel=FALSE here)
+    # the same with online Stephens relabelling after the burn-in ("relabel off and on")
+    "c4relabel": dict(sampler="stickbreaking", N=10_000_000, P=64, K=32, nsamples=41, burnin=5, alpha=1.0, relabel=True,
+                      burnrelabel=1, precision="fp32", cpu_N=60_000, cpu_ns=6,
+                      label="C4 + Stephens relabelling: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1"),
+    # BASELINE.json configs[4]
     "c5": dict(sampler="full", N=1_000_000, P=4096, K=128, nsamples=41, burnin=5, alpha=1.0, relabel=True, burnrelabel=1,
                precision="fp32", cpu_N=150, cpu_ns=3, stabilise=True,
                label="C5: gibbs_full synthetic N=1e6 P=4096 K=128 (large-P tcgen05 contraction) + Stephens relabelling (Hungarian)"),

@@ -1078,7 +1078,7 @@ int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm) {
 int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t use_logp, int32_t tensor, double *out) {
     if (!p || !q || !out || N < 1 || K < 1 || K > 128) return fail(BMM_ERR_INVALID, "bad grid_cost arguments");
     if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
-    if (tensor && !bmm::grid_cost_tc_supported(N, K)) return fail(BMM_ERR_INVALID, "tensor cost kernel needs 64 < K <= 128, K % 8 == 0");
+    if (tensor && !bmm::grid_cost_tc_supported(N, K)) return fail(BMM_ERR_INVALID, "tensor cost kernel needs 8 <= K <= 128, K % 8 == 0");
     DevBuf pd, qd, od, sd;
     TRY(upload(pd, p, (size_t)N * K));
     TRY(upload(qd, q, (size_t)N * K));

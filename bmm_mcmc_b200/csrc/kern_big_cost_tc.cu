@@ -1,4 +1,4 @@
-// Stephens cost matrix of the grid path on tcgen05 for 64 < K <= 128:
+// Stephens cost matrix of the grid path on tcgen05 for 8 <= K <= 128, K % 8 == 0:
 //   G(k,l) = sum_i log q_ik * p_il,   s_l = sum_i p_il^2  (online)  or  sum_i p_il log p_il  (batch)
 // (/root/reference/src/stephens.cpp:45-53,76-84), a K x K contraction over the N observations of two
 // row-major fp32 matrices.  The CUDA-core version in kern_big_relabel.cu runs at a quarter of the FMA
@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // column groups beyond K are never written: they stay zero (rows k >= K of the accumulator are unused)
+    for (int e = tid; e < CT_NS * CT_STAGE / 16; e += CT_THREADS) ((uint4 *)smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < CT_NS; ++s) { mbar_init(full0 + 8 * s, 256); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(done, 1);
@@ -60,30 +63,47 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
     __syncthreads();
     tc_fence_after();
     const uint32_t acc = *tmem_slot;
-    const long long nst = (N + CT_ROWS - 1) / CT_ROWS;
+    // K dividing 128: `fold` consecutive observations are read as one wide row of KW = 128 columns (the matrices
+    // are row-major and contiguous), which keeps every column group of the operand images busy; the wide
+    // contraction holds G in its `fold` diagonal K x K blocks, summed by the epilogue.
+    const int fold = (128 % K) == 0 ? 128 / K : 1, KW = K * fold;
+    const long long total = N * (long long)K, NWIDE = (N + fold - 1) / fold;
+    const long long nst = (NWIDE + CT_ROWS - 1) / CT_ROWS;
     // contiguous range of stages per CTA
     const long long per = (nst + gridDim.x - 1) / gridDim.x;
     const long long st0 = (long long)blockIdx.x * per, st1 = min(st0 + per, nst);
     bool ok = true;
 
+    const int ncg = KW >> 3;                                 // column groups of 8 (K % 8 == 0)
     if (warp < 8) {
-        // ---- producers: lane = (column group within a quad, row within an octet) so that every quarter-warp
-        //      store covers 128 contiguous bytes of one column group ----
-        const int cg = (warp & 3) * 4 + (lane >> 3);       // column group: columns [8 cg, 8 cg + 8)
-        const int rl = lane & 7, oct0 = warp >> 2;          // row octets oct0, oct0 + 2, oct0 + 4, oct0 + 6
-        const bool cols = cg * 8 < K;                       // K % 8 == 0
-        float sacc[8];
+        // ---- producers: work item = (row octet, column group); the 8 lanes of a quarter-warp phase take the 8
+        //      rows of one item, so every 16-byte store phase covers 128 contiguous bytes of one column group,
+        //      and consecutive items are consecutive column groups of the same rows (coalesced reads).
+        //      Slot m of a thread is item (tid >> 3) + 32 m in every stage, hence a fixed column group. ----
+        const int rl = lane & 7;
+        int cgm[4], octm[4];
+        bool act[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sacc[q] = 0.f;
+        for (int m = 0; m < 4; ++m) {
+            const int pi = (tid >> 3) + 32 * m;
+            act[m] = pi < 8 * ncg;
+            cgm[m] = pi % ncg; octm[m] = pi / ncg;
+        }
+        float sacc[4][8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sacc[m][q] = 0.f;
         long long g = 0;
         for (long long st = st0; st < st1 && ok; ++st, ++g) {
             float4 pv[4][2], qv[4][2];
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                const long long i = st * CT_ROWS + (oct0 + 2 * m) * 8 + rl;
-                if (cols && i < N) {
-                    const float4 *pp = (const float4 *)(P + (size_t)i * K + cg * 8);
-                    const float4 *qq = (const float4 *)(Q + (size_t)i * K + cg * 8);
+                const long long i = st * CT_ROWS + octm[m] * 8 + rl;        // wide row
+                const long long e = i * KW + cgm[m] * 8;                    // first element of the chunk
+                if (act[m] && e < total) {
+                    const float4 *pp = (const float4 *)(P + e);
+                    const float4 *qq = (const float4 *)(Q + e);
                     pv[m][0] = __ldg(pp); pv[m][1] = __ldg(pp + 1);
                     qv[m][0] = __ldg(qq); qv[m][1] = __ldg(qq + 1);
                 } else {
@@ -98,16 +118,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
             unsigned char *stage = smem + s * CT_STAGE;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
+                if (!act[m]) continue;
                 const float p8[8] = {pv[m][0].x, pv[m][0].y, pv[m][0].z, pv[m][0].w, pv[m][1].x, pv[m][1].y, pv[m][1].z, pv[m][1].w};
                 const float q8[8] = {qv[m][0].x, qv[m][0].y, qv[m][0].z, qv[m][0].w, qv[m][1].x, qv[m][1].y, qv[m][1].z, qv[m][1].w};
                 float l8[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     l8[q] = __logf(q8[q]);
-                    sacc[q] += use_logp ? (p8[q] > 0.f ? p8[q] * __logf(p8[q]) : 0.f) : p8[q] * p8[q];
+                    sacc[m][q] += use_logp ? (p8[q] > 0.f ? p8[q] * __logf(p8[q]) : 0.f) : p8[q] * p8[q];
                 }
                 uint4 hi, lo;
-                const int off = cg * (CT_ROWS * 16) + ((oct0 + 2 * m) * 8 + rl) * 16;
+                const int off = cgm[m] * (CT_ROWS * 16) + (octm[m] * 8 + rl) * 16;
                 split8(l8, hi, lo);
                 *(uint4 *)(stage + 0 * CT_MAT + off) = hi;
                 *(uint4 *)(stage + 1 * CT_MAT + off) = lo;
@@ -118,18 +139,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
             fence_async_smem();
             mbar_arrive(full0 + 8 * s);
         }
-        // column sums: the 8 lanes of an octet hold the same columns
+        // column sums: the 8 lanes of an item hold the same columns
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float v = sacc[q];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            if (rl == 0 && cols) atomicAdd(&out[(size_t)K * K + cg * 8 + q], (double)v);
-        }
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float v = sacc[m][q];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (rl == 0 && act[m]) atomicAdd(&out[(size_t)K * K + (cgm[m] * 8 + q) % K], (double)v);
+            }
     } else if (tid == 256) {
         // ---- MMA issuer ----
-        constexpr uint32_t IDESC = umma_idesc_f16(128, 128, 1, 1);
+        const uint32_t IDESC = umma_idesc_f16(128, (KW + 15) & ~15, 1, 1);   // N = width rounded up to the MMA granule
         long long g = 0;
         for (long long st = st0; st < st1 && ok; ++st, ++g) {
             const int s = (int)(g % CT_NS);
@@ -157,15 +180,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
         if (ok) ok = mbar_wait(done, 0u);
         if (ok) {
             tc_fence_after();
-            const int k = warp * 32 + lane;
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            const int kw = warp * 32 + lane;                 // wide row of G = TMEM lane
+            for (int c0 = 0; c0 < KW; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (k < K) {
+                if (kw < KW) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        if (c0 + q < K) atomicAdd(&out[k + (size_t)K * (c0 + q)], (double)__uint_as_float(v[q]));
+                    for (int q = 0; q < 32; ++q) {
+                        const int cw = c0 + q;
+                        if (cw < KW && cw / K == kw / K)     // diagonal blocks only
+                            atomicAdd(&out[(kw % K) + (size_t)K * (cw % K)], (double)__uint_as_float(v[q]));
+                    }
                 }
             }
         }
@@ -181,7 +207,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
 
 }  // namespace
 
-bool grid_cost_tc_supported(long long N, int K) { return K > 64 && K <= 128 && (K % 8) == 0 && N >= 1; }
+bool grid_cost_tc_supported(long long N, int K) { return K >= 8 && K <= 128 && (K % 8) == 0 && N >= 1; }
 
 // acc must be zero on entry
 cudaError_t launch_grid_cost_tc(long long N, int K, const float *P, const float *Q, int use_logp, double *acc, int *status,
@@ -192,7 +218,8 @@ cudaError_t launch_grid_cost_tc(long long N, int K, const float *P, const float 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const long long nst = (N + CT_ROWS - 1) / CT_ROWS;
+    const int fold = (128 % K) == 0 ? 128 / K : 1;
+    const long long nst = ((N + fold - 1) / fold + CT_ROWS - 1) / CT_ROWS;
     const int grid = (int)(nst < sm_count ? nst : sm_count);
     grid_cost_tc_kernel<<<grid, CT_THREADS, CT_SMEM, st>>>(N, K, P, Q, use_logp, acc, status);
     g_launches++;

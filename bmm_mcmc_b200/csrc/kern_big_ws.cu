@@ -246,10 +246,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                     for (int q = 0; q < WS_KC; ++q)
                         if (q < K) p.probs_out[(size_t)j * p.N_local * K + i + (size_t)p.N_local * q] = (double)(l[q] * inv);
                 }
-                if (valid && p.probs_f32) {
+                if (valid && p.probs_f32) {    // this observation's row of P, 16 bytes at a time when aligned
+                    float *dst = p.probs_f32 + (size_t)i * K;
+                    if ((K & 3) == 0) {
 #pragma unroll
-                    for (int q = 0; q < WS_KC; ++q)
-                        if (q < K) p.probs_f32[(size_t)i * K + q] = l[q] * inv;
+                        for (int q = 0; q < WS_KC; q += 4)
+                            if (q < K) *(float4 *)(dst + q) = make_float4(l[q] * inv, l[q + 1] * inv, l[q + 2] * inv, l[q + 3] * inv);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < WS_KC; ++q)
+                            if (q < K) dst[q] = l[q] * inv;
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < WS_KC; ++q) { run += l[q]; l[q] = run; }

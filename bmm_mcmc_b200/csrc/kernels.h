@@ -143,7 +143,7 @@ size_t big_lp_table_bytes(int P);
 cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st);
 
 // ---- relabelling on the grid path (kern_big_relabel.cu); P, Q row-major float [N][K] ----------
-// acc: K*K + K doubles; tc != 0 allows the tcgen05 kernel (kern_big_cost_tc.cu, 64 < K <= 128, K % 8 == 0),
+// acc: K*K + K doubles; tc != 0 allows the tcgen05 kernel (kern_big_cost_tc.cu, 8 <= K <= 128, K % 8 == 0),
 // which reports a pipeline timeout through *status
 cudaError_t launch_grid_cost(long long N, int K, const float *P, const float *Q, int use_logp, double *acc,
                              int sm_count, cudaStream_t st, int tc = 0, int *status = nullptr);

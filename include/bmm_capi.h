@@ -152,7 +152,7 @@ int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm);
 /* The K x K cost contraction of the grid path's relabelling (stephens.cpp:45-53,76-84) on host
  * matrices p, q (row-major float N x K): out[k + K*l] = sum_i log q_ik * p_il and
  * out[K*K + l] = sum_i p_il^2 (use_logp: p_il log p_il).  tensor != 0 forces the tcgen05 kernel
- * (64 < K <= 128, K % 8 == 0), 0 the CUDA-core kernel.  Test entry point.                         */
+ * (8 <= K <= 128, K % 8 == 0), 0 the CUDA-core kernel.  Test entry point.                         */
 int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t use_logp, int32_t tensor, double *out);
 /* _bmmmcmc_rdirichlet_cpp (full_gibbs.cpp:10-27) with an explicit Philox seed.                    */
 int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out);

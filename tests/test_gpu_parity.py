@@ -501,7 +501,7 @@ def test_assign_warp_jv_matches_lpsolve(oracle):
         assert np.array_equal(perm, s_o.argmax(0)), K
 
 
-@pytest.mark.parametrize("N,K,use_logp", [(5000, 128, 0), (777, 72, 1), (64, 128, 0), (20011, 96, 1)])
+@pytest.mark.parametrize("N,K,use_logp", [(5000, 128, 0), (777, 72, 1), (64, 128, 0), (20011, 96, 1), (3001, 32, 0), (1000, 24, 1), (4097, 64, 0), (1003, 8, 0), (50001, 16, 1)])
 def test_grid_cost_kernels_match_float64(N, K, use_logp):
     """Cost contraction of the grid path's relabelling (stephens.cpp:45-53,76-84): the tcgen05 kernel (fp16 hi/lo
     split operands) and the CUDA-core kernel against numpy float64, tolerance 2e-5 of the largest entry."""
