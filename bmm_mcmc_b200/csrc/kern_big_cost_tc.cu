@@ -3,9 +3,9 @@
 // (/root/reference/src/stephens.cpp:45-53,76-84), a K x K contraction over the N observations of two
 // row-major fp32 matrices.  The CUDA-core version in kern_big_relabel.cu runs at a quarter of the FMA
 // peak (1.97 ms at N = 1e6, K = 128); here the contraction is a 128 x 128 x N GEMM whose operands are
-// produced on the fly: 8 warps stream 64 observations of P and Q per stage, take the logarithm, split
+// produced on the fly: 8 warps stream 32 (wide) observations of P and Q per stage through a cp.async ring, take the logarithm, split
 // every value into fp16 hi + lo (22 significant bits) and store the MN-major operand image; one thread
-// issues hi*hi + hi*lo + lo*hi (12 MMAs M128 N128 K16 per stage) into one fp32 accumulator in TMEM.
+// issues hi*hi + hi*lo + lo*hi (6 MMAs M128 N128 K16 per stage) into one fp32 accumulator in TMEM.
 // The kernel is then bound by reading P and Q once (2 x N x K x 4 bytes).  Per-CTA partial sums go to
 // the fp64 cost buffer with atomics, like the CUDA-core kernel.
 #include <cuda_fp16.h>
@@ -17,12 +17,22 @@
 namespace bmm {
 namespace {
 
-constexpr int CT_ROWS = 64;                      // observations per stage
-constexpr int CT_MAT = 16 * CT_ROWS * 16;        // [16 column groups of 8][64 obs][16 B] = 16 KB
+constexpr int CT_ROWS = 32;                      // (wide) observations per stage
+constexpr int CT_MAT = 16 * CT_ROWS * 16;        // [16 column groups of 8][32 obs][16 B] = 8 KB
 constexpr int CT_STAGE = 4 * CT_MAT;             // LQ hi | LQ lo | P hi | P lo
-constexpr int CT_NS = 3;
+constexpr int CT_NS = 3;                         // operand stages
+constexpr int CT_NR = 3;                         // raw fp32 stages (cp.async ring)
+constexpr int CT_SL = 2;                         // work items per producer thread and stage
+constexpr int CT_RROW = 512 + 16;                // raw row pitch: 128 floats + 16 B so that 8 rows hit 32 distinct banks
+constexpr int CT_RAW = 2 * CT_ROWS * CT_RROW;    // [P | Q][32 rows][528 B] = 33 KB
+constexpr int CT_RAW_OFF = CT_NS * CT_STAGE;
+constexpr int CT_BAR_OFF = CT_RAW_OFF + CT_NR * CT_RAW;
 constexpr int CT_THREADS = 288;                  // warps 0-7 producers, warp 8 MMA issuer
-constexpr int CT_SMEM = CT_NS * CT_STAGE + 2 * CT_NS * 8 + 8 + 16;
+constexpr int CT_SMEM = CT_BAR_OFF + 2 * CT_NS * 8 + 8 + 16;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
 
 // 8 floats -> 8 fp16 hi (one 16-byte chunk) and 8 fp16 lo
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo) {
@@ -44,7 +54,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
                                                                      double *out, int *status) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t *bars = (uint64_t *)(smem + CT_NS * CT_STAGE);       // full[NS], empty[NS], done
+    uint64_t *bars = (uint64_t *)(smem + CT_BAR_OFF);             // full[NS], empty[NS], done
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * CT_NS + 1);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[CT_NS]), done = smem_u32(&bars[2 * CT_NS]);
     if (warp == 8) {
@@ -52,7 +62,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // column groups beyond K are never written: they stay zero (rows k >= K of the accumulator are unused)
-    for (int e = tid; e < CT_NS * CT_STAGE / 16; e += CT_THREADS) ((uint4 *)smem)[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = tid; e < CT_NS * CT_STAGE / 16; e += CT_THREADS)   // operand stages only ((uint4 *)smem)[e] = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < CT_NS; ++s) { mbar_init(full0 + 8 * s, 256); mbar_init(empty0 + 8 * s, 1); }
@@ -81,43 +91,73 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
         //      and consecutive items are consecutive column groups of the same rows (coalesced reads).
         //      Slot m of a thread is item (tid >> 3) + 32 m in every stage, hence a fixed column group. ----
         const int rl = lane & 7;
-        int cgm[4], octm[4];
-        bool act[4];
+        int cgm[CT_SL], octm[CT_SL];
+        bool act[CT_SL];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < CT_SL; ++m) {
             const int pi = (tid >> 3) + 32 * m;
-            act[m] = pi < 8 * ncg;
+            act[m] = pi < (CT_ROWS / 8) * ncg;
             cgm[m] = pi % ncg; octm[m] = pi / ncg;
         }
-        float sacc[4][8];
+        float sacc[CT_SL][8];
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < CT_SL; ++m)
 #pragma unroll
             for (int q = 0; q < 8; ++q) sacc[m][q] = 0.f;
-        long long g = 0;
-        for (long long st = st0; st < st1 && ok; ++st, ++g) {
-            float4 pv[4][2], qv[4][2];
+        // The rows travel global -> shared with cp.async, a warp instruction per 512-byte row (whole 32-byte
+        // sectors, once: 16-byte pieces of a sector fetched by different instructions doubled the L2 traffic
+        // and bound the first version), two stages ahead of their conversion; registers cannot hold that much
+        // data in flight (a register double buffer spilled and was slower).
+        const uint32_t raw0 = smem_u32(smem + CT_RAW_OFF);
+        auto issue = [&](long long st, int r) {
+            if (st < st1 && lane * 4 < KW) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const long long i = st * CT_ROWS + octm[m] * 8 + rl;        // wide row
-                const long long e = i * KW + cgm[m] * 8;                    // first element of the chunk
-                if (act[m] && e < total) {
-                    const float4 *pp = (const float4 *)(P + e);
-                    const float4 *qq = (const float4 *)(Q + e);
-                    pv[m][0] = __ldg(pp); pv[m][1] = __ldg(pp + 1);
-                    qv[m][0] = __ldg(qq); qv[m][1] = __ldg(qq + 1);
-                } else {
-                    pv[m][0] = pv[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    qv[m][0] = qv[m][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int rr = 0; rr < CT_ROWS / 8; ++rr) {
+                    const int row = warp + 8 * rr;
+                    const long long e = (st * CT_ROWS + row) * KW + lane * 4;
+                    if (e < total) {
+                        const uint32_t d = raw0 + r * CT_RAW + row * CT_RROW + lane * 16;
+                        cp_async16(d, P + e);
+                        cp_async16(d + CT_ROWS * CT_RROW, Q + e);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int r = 0; r < CT_NR - 1; ++r) issue(st0 + r, r);
+        long long g = 0;
+        for (long long st = st0; st < st1; ++st, ++g) {   // no early exit: every producer reaches every bar.sync
+            // own copies of stage g have landed; after the barrier everybody's have, and everybody has read
+            // stage g - 1 out of the slot that the next issue overwrites
+            asm volatile("cp.async.wait_group %0;" :: "n"(CT_NR - 2) : "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            issue(st + CT_NR - 1, (int)((g + CT_NR - 1) % CT_NR));
+            float4 pv[CT_SL][2], qv[CT_SL][2];
+            {
+                const unsigned char *rb = smem + CT_RAW_OFF + (int)(g % CT_NR) * CT_RAW;
+#pragma unroll
+                for (int m = 0; m < CT_SL; ++m) {
+                    const int row = octm[m] * 8 + rl;
+                    const long long e = (st * CT_ROWS + row) * KW + cgm[m] * 8;
+                    if (act[m] && e < total) {
+                        const unsigned char *src = rb + row * CT_RROW + cgm[m] * 32;
+                        pv[m][0] = *(const float4 *)(src);
+                        pv[m][1] = *(const float4 *)(src + 16);
+                        qv[m][0] = *(const float4 *)(src + CT_ROWS * CT_RROW);
+                        qv[m][1] = *(const float4 *)(src + CT_ROWS * CT_RROW + 16);
+                    } else {
+                        pv[m][0] = pv[m][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        qv[m][0] = qv[m][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    }
                 }
             }
             const int s = (int)(g % CT_NS);
             const long long n = g / CT_NS;
-            if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
-            if (!ok) break;
+            if (ok && n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));   // after a timeout: stop waiting
             unsigned char *stage = smem + s * CT_STAGE;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < CT_SL; ++m) {
                 if (!act[m]) continue;
                 const float p8[8] = {pv[m][0].x, pv[m][0].y, pv[m][0].z, pv[m][0].w, pv[m][1].x, pv[m][1].y, pv[m][1].z, pv[m][1].w};
                 const float q8[8] = {qv[m][0].x, qv[m][0].y, qv[m][0].z, qv[m][0].w, qv[m][1].x, qv[m][1].y, qv[m][1].z, qv[m][1].w};
@@ -141,7 +181,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
         }
         // column sums: the 8 lanes of an item hold the same columns
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < CT_SL; ++m)
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float v = sacc[m][q];
