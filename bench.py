@@ -406,7 +406,7 @@ def run_grid(a):
         tf = flops / dur_s / 1e12
         roof.update(bound="tensor", achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=tf / pk["bf16_tflops_sustained"],
-                    kernel="%s (%d rows, %d algorithmic flop/update; issued flops are 4x: 3-term bf16 split + counts GEMM)"
+                    kernel="%s (%d rows, %d algorithmic flop/update; the kernel issues 2x that: D = hi + lo in fp16)"
                            % (kname, n_local, 2 * K * P))
     line = {
         "metric": METRIC, "value": total_updates / tm[0], "unit": "allocation updates/s", "n_gpus": world,

@@ -5,14 +5,14 @@
 // (the ncu profile of the single-role kernel showed its four warpgroups convoying: ALU phase and
 // tensor phase of a round did not overlap).
 //
-//   warps 0-3    producers: packed row -> bf16 A stage (ring of NS stages) -> arrive full_A
+//   warps 0-3    producers: packed row -> fp16 A stage (ring of NS stages) -> arrive full_A
 //   warp  4      one thread issues GEMM1(k) into accumulator k % NA, tcgen05.commit publishes it
 //   warp  5      one thread issues GEMM2(k) from A stage + one-hot stage; its commits free both stages
 //   warps 8-19   three epilogue warpgroups (tile k goes to warpgroup k % 3): TMEM lane = observation,
 //                softmax, Philox inverse-CDF draw, 1-byte allocation, one-hot row -> B2 stage
 //
 // Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -23,17 +23,18 @@ namespace {
 
 constexpr int WS_KC = 32;
 constexpr int WS_NS = 5;      // A stages
-constexpr int WS_NA = 4;      // GEMM1 accumulators (96 TMEM columns each)
+constexpr int WS_PARTS = 2;   // D = hi + lo in fp16 (22 significant bits; the 0/1 rows are exact)
+constexpr int WS_NA = 4;      // GEMM1 accumulators (64 TMEM columns each)
 constexpr int WS_NB = 4;      // one-hot stages
 constexpr int WS_NEPI = 3;    // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
 constexpr int WS_CHUNK = 2048;
 constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
-constexpr int WS_B1_ROW = 3 * WS_KC * 16;
+constexpr int WS_B1_ROW = WS_PARTS * WS_KC * 16;
 
 // shared memory: [A ring][B2 ring][B1 table][bias][barriers][tmem slot].  GEMM2 reads 16 chunks (M = 128)
 // from an A stage that only holds NCH + 1: the rows beyond are whatever follows (other stages, one-hot
-// rows, the weight table -- all finite bf16) and land in accumulator lanes that are never read.
+// rows, the weight table -- all finite fp16) and land in accumulator lanes that are never read.
 template <int NCH>
 struct WsLayout {
     static constexpr int A_STAGE = (NCH + 1) * WS_CHUNK;
@@ -43,7 +44,7 @@ struct WsLayout {
     static constexpr int BAR_OFF = BIAS_OFF + WS_KC * 4;
     static constexpr int NBAR = 2 * WS_NS + 2 * WS_NA + 2 * WS_NB + 1;
     static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16;
-    static_assert(B1_OFF + NCH * WS_B1_ROW - (WS_NS - 1) * A_STAGE >= 16 * WS_CHUNK, "GEMM2 over-read must stay inside finite bf16 data");
+    static_assert(B1_OFF + NCH * WS_B1_ROW - (WS_NS - 1) * A_STAGE >= 16 * WS_CHUNK, "GEMM2 over-read must stay inside the operand data");
 };
 
 template <int NCH>
@@ -81,14 +82,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (k < K && d < P) D = (p.w1[k + K * d] - p.w0[k + K * d]) * 1.4426950408889634;
         D = fmin(fmax(D, -1.0e4), 1.0e4);     // theta exactly 0 / 1: log 0 = -inf would make 0 * inf = NaN in the contraction
         if (D != D) D = 0.0;
-        const __nv_bfloat16 hi = __double2bfloat16(D);
-        const double r1 = D - (double)__bfloat162float(hi);
-        const __nv_bfloat16 mid = __double2bfloat16(r1);
-        const __nv_bfloat16 lo = __double2bfloat16(r1 - (double)__bfloat162float(mid));
+        const __half hi = __double2half(D);
+        const __half lo = __double2half(D - (double)__half2float(hi));
         unsigned char *cell = B1 + (d >> 3) * WS_B1_ROW + k * 16 + (d & 7) * 2;
-        *(__nv_bfloat16 *)(cell + 0 * WS_KC * 16) = hi;
-        *(__nv_bfloat16 *)(cell + 1 * WS_KC * 16) = mid;
-        *(__nv_bfloat16 *)(cell + 2 * WS_KC * 16) = lo;
+        *(__half *)(cell + 0 * WS_KC * 16) = hi;
+        *(__half *)(cell + 1 * WS_KC * 16) = lo;
     }
     for (int k = tid; k < WS_KC; k += WS_THREADS) {
         float b = -INFINITY;
@@ -102,14 +100,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     }
     // the ones column of [X | 1] (chunk NCH of every A stage) and zeroed one-hot stages
     for (int e = tid; e < WS_NS * 128; e += WS_THREADS)
-        *(uint4 *)(smem + (e / 128) * L::A_STAGE + NCH * WS_CHUNK + (e % 128) * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);
+        *(uint4 *)(smem + (e / 128) * L::A_STAGE + NCH * WS_CHUNK + (e % 128) * 16) = make_uint4(0x3C00u, 0u, 0u, 0u);
     for (int e = tid; e < WS_NB * WS_B2_BYTES / 16; e += WS_THREADS) *(uint4 *)(smem + L::B2_OFF + e * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc2 = tmem_base + WS_NA * 3 * WS_KC;
+    const uint32_t acc2 = tmem_base + WS_NA * WS_PARTS * WS_KC;
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     const long long T = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
     bool ok = true;
@@ -144,7 +142,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t byte = ring[d][c >> 2] >> ((c & 3) * 8);
-                    ex[c] = make_uint4(bits2_bf16x2(byte), bits2_bf16x2(byte >> 2), bits2_bf16x2(byte >> 4), bits2_bf16x2(byte >> 6));
+                    ex[c] = make_uint4(bits2_f16x2(byte), bits2_f16x2(byte >> 2), bits2_f16x2(byte >> 4), bits2_f16x2(byte >> 6));
                 }
                 load_row(k + PF, ring[d]);
                 const int s = (int)(k % WS_NS);
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         // (one thread per GEMM: a single thread issuing both was the bottleneck -- ~300 dependent
         //  instructions per tile; descriptors are base + constant offset in the 16-byte address field)
         if (tid == 128) {
-            constexpr uint32_t IDESC1 = umma_idesc(128, 3 * WS_KC, 0, 0);
+            constexpr uint32_t IDESC1 = umma_idesc_f16(128, WS_PARTS * WS_KC, 0, 0);
             const uint64_t da0 = umma_desc(smem_u32(smem), WS_CHUNK, 128), db0 = umma_desc(smem_u32(B1), WS_B1_ROW, 128);
             for (long long k = 0; k < T && ok; ++k) {
                 const int s = (int)(k % WS_NS), a = (int)(k % WS_NA);
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                 const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < NCH / 2; ++kk)
-                    umma_bf16(tmem_base + (uint32_t)(a * 3 * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
+                    umma_bf16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
                               db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
                 umma_commit(acc_full + 8 * a);
             }
@@ -184,7 +182,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     } else if (warp == 5) {
         // ================= GEMM2 issuer =================
         if (tid == 160) {
-            constexpr uint32_t IDESC2 = umma_idesc(128, WS_KC, 1, 1);
+            constexpr uint32_t IDESC2 = umma_idesc_f16(128, WS_KC, 1, 1);
             const uint64_t da0 = umma_desc(smem_u32(smem), 128, WS_CHUNK), db0 = umma_desc(smem_u32(smem + L::B2_OFF), 128, WS_CHUNK);
             for (long long q = 0; q < T && ok; ++q) {
                 const int s = (int)(q % WS_NS), b = (int)(q % WS_NB);
@@ -220,9 +218,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             tc_fence_after();
             float l[WS_KC];
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
+            for (int part = 0; part < WS_PARTS; ++part) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * 3 * WS_KC + part * WS_KC), v);
+                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * WS_PARTS * WS_KC + part * WS_KC), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 32; ++q) l[q] = part == 0 ? __uint_as_float(v[q]) + bias[q] : l[q] + __uint_as_float(v[q]);
@@ -273,7 +271,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             if (!ok) break;
             {
                 unsigned char *B2 = smem + L::B2_OFF + b * WS_B2_BYTES;
-                const uint32_t h = valid ? ((z & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+                const uint32_t h = valid ? ((z & 1) ? 0x3C000000u : 0x3C00u) : 0u;
                 const int wsel = (z & 7) >> 1, csel = z >> 3;
                 const uint4 hot = make_uint4(wsel == 0 ? h : 0u, wsel == 1 ? h : 0u, wsel == 2 ? h : 0u, wsel == 3 ? h : 0u);
 #pragma unroll
