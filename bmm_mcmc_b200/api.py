@@ -109,7 +109,7 @@ def _chain_cm(C_, shape, dtype, pinned=False):
 def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
                 compact_z=False, stable_softmax=False, chain_offset=0, grid_path=False, no_z_history=False,
-                n_global=0, row_offset=0, no_tensor=False):
+                n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
     """ctypes bmm_args / bmm_init for one call; returns (args, init, keepalive)."""
     N, P = X.shape
     args = _lib.Args()
@@ -122,7 +122,7 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     args.device = int(device)
     args.flags = ((_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0) |
                   (_lib.FLAG_GRID_PATH if grid_path else 0) | (_lib.FLAG_NO_Z_HISTORY if no_z_history else 0) |
-                  (_lib.FLAG_NO_TENSOR if no_tensor else 0))
+                  (_lib.FLAG_NO_TENSOR if no_tensor else 0) | (_lib.FLAG_STEPHENS_FIXED if stephens_fixed else 0))
     if isinstance(X, PackedX):
         args.flags |= _lib.FLAG_X_PACKED
     args.n_global, args.row_offset = int(n_global), int(row_offset)
@@ -208,7 +208,7 @@ class Plan:
     def __init__(self, sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                  chains=1, seed=0, device=0, precision="fp64", init_pi=None, init_theta=None, init_z=None,
                  compact_z=False, chain_offset=0, probes=(), stable_softmax=False, grid_path=False,
-                 no_z_history=False, n_global=0, row_offset=0, no_tensor=False):
+                 no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
         self.L = _lib.lib()
         self.X = _as_X(X)
         self.meta = dict(sampler=sampler, Cn=int(chains), N=self.X.shape[0], P=self.X.shape[1], K=int(K),
@@ -217,7 +217,7 @@ class Plan:
         args, init, self._keep = _build_args(sampler, self.X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel,
                                              burnrelabel, False, chains, seed, device, precision, init_pi, init_theta,
                                              init_z, None, compact_z, stable_softmax, chain_offset, grid_path,
-                                             no_z_history, n_global, row_offset, no_tensor)
+                                             no_z_history, n_global, row_offset, no_tensor, stephens_fixed)
         if "probs" in probes:
             args.flags |= 0x100
         if "loglik" in probes:
@@ -275,14 +275,14 @@ class Plan:
 def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
          chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
          compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
-         grid_path=False, no_z_history=False, n_global=0, row_offset=0, no_tensor=False):
+         grid_path=False, no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
     L = _lib.lib()
     N, P = X.shape
     Cn = int(chains)
     args, init, keep = _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                                    debug, chains, seed, device, precision, init_pi, init_theta, init_z, replay,
                                    compact_z, stable_softmax, chain_offset, grid_path, no_z_history, n_global,
-                                   row_offset, no_tensor)
+                                   row_offset, no_tensor, stephens_fixed)
     res, out, status = out_bufs if out_bufs is not None else _alloc_out(
         sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=no_z_history)
     if sampler == _lib.SAMPLER_DP:
@@ -311,8 +311,11 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                initial_pi=None, initial_theta=None, replay=None, compact_z=False, stable_softmax=False,
                probes=(), chain_offset=0, pinned=False, out_bufs=None, grid_path=False, no_z_history=False,
-               n_global=0, row_offset=0, no_tensor=False, _sampler=None):
-    """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32)."""
+               n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, _sampler=None):
+    """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32).
+
+    `stephens_fixed=True` (BMM_FLAG_STEPHENS_FIXED, not the reference's behaviour) relabels with the corrected
+    Stephens steps: inverse permutation for the column re-ordering, log p in the online cost, running-mean Q."""
     X = _as_X(data)
     N, P = X.shape
     burnin, burnrelabel, alpha = _defaults(nsamples, burnin, burnrelabel, alpha, clamp=_sampler is None)
@@ -333,7 +336,7 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                 device, precision, init_pi=np.ascontiguousarray(initial_pi), init_theta=np.ascontiguousarray(initial_theta),
                 replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset,
                 pinned=pinned, out_bufs=out_bufs, grid_path=grid_path, no_z_history=no_z_history, n_global=n_global,
-                row_offset=row_offset, no_tensor=no_tensor)
+                row_offset=row_offset, no_tensor=no_tensor, stephens_fixed=stephens_fixed)
 
 
 def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None,
@@ -347,7 +350,8 @@ def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a
 
 def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None, relabel=False,
                     burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
-                    initial_K=None, replay=None, compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
+                    initial_K=None, replay=None, compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
+                    stephens_fixed=False):
     """Collapsed Gibbs sampler for a finite mixture (R/utils.R:37-47 -> collapsed_gibbs.cpp:24)."""
     X = _as_X(data)
     N, P = X.shape
@@ -358,15 +362,15 @@ def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1
     initial_K = np.ascontiguousarray(np.asarray(initial_K, dtype=np.int32).reshape(chains, N))
     return _run(_lib.SAMPLER_COLLAPSED, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_z=initial_K, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed)
 
 
 def gibbs_dp(data, nsamples, alpha=None, a=1, b=1, beta=0.5, gamma=0.5, burnin=None, relabel=False,
              burnrelabel=50, maxK=30, debug=False, *, chains=1, seed=0, device=0, precision="fp64", replay=None,
-             compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None):
+             compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None, stephens_fixed=False):
     """Collapsed Gibbs sampler for the DP (CRP) infinite mixture (R/utils.R:23-30 -> collapsed_gibbs_dp.cpp:27)."""
     X = _as_X(data)
     burnin, burnrelabel, alpha = _defaults(nsamples, burnin, burnrelabel, alpha)
     return _run(_lib.SAMPLER_DP, X, nsamples, maxK, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed)

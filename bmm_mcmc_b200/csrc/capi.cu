@@ -155,7 +155,7 @@ struct bmm_plan {
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
     // state
     DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status, cost_g;
-    DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws;
+    DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws, perm_inv;
     // histories
     DevBuf zhist, theta_out, theta_rel_out, pi_out, alpha_out, perm_out, probs_out, loglik_out, kactive;
     DevBuf z_orig, z_rel, Qexp;
@@ -369,6 +369,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
         CU(pl->cost_acc.alloc(((size_t)K * K + K) * 8));
         CU(pl->perm_cur.alloc((size_t)K * 4));
         CU(pl->sb_perm.alloc((size_t)a.burnrelabel * K * 4));
+        CU(pl->perm_inv.alloc((size_t)(a.burnrelabel > 1 ? a.burnrelabel : 1) * K * 4));   // BMM_FLAG_STEPHENS_FIXED
         CU(pl->perm_out.alloc((size_t)S * K * 4));
         CU(pl->theta_rel_out.alloc(KP * S * 8));
         CU(pl->assign_ws.alloc(bmm::assign_ws_bytes(K)));
@@ -428,6 +429,7 @@ int run_big(bmm_plan *pl) {
     const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
     const long long N = b.N_local;
     const size_t NK = (size_t)N * K;
+    const int st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0;
     const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
     if (pl->relabel) CU(bmm::launch_grid_identity_perm(K, K, pl->perm_cur.as<int>(), pl->stream));
     for (int j = 1; j < ns; ++j) {
@@ -456,7 +458,9 @@ int run_big(bmm_plan *pl) {
             // assignments, so stopping there returns exactly what the 100th iteration would.
             int *flag = pl->status.as<int>() + 1;
             for (int iter = 0; iter < 100; ++iter) {
-                CU(bmm::launch_grid_qmean(N, K, M, cube, sbp, pl->Qf.as<float>(), pl->sm_count, pl->stream));
+                if (st_fixed) CU(bmm::launch_grid_invert_perm(M, K, sbp, pl->perm_inv.as<int>(), pl->stream));
+                CU(bmm::launch_grid_qmean(N, K, M, cube, st_fixed ? pl->perm_inv.as<int>() : sbp, pl->Qf.as<float>(), pl->sm_count,
+                                          pl->stream));
                 CU(cudaMemsetAsync(flag, 0, sizeof(int), pl->stream));
                 for (int t = 0; t < M; ++t) {
                     CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
@@ -472,14 +476,15 @@ int run_big(bmm_plan *pl) {
                 if (!changed) break;
             }
         } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
-            CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), 0, pl->cost_acc.as<double>(),
+            CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), st_fixed, pl->cost_acc.as<double>(),
                                      pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
             if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
                 return fail(BMM_ERR_NCCL, bmm::dist_error());
             CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
                                        pl->perm_out.as<int>() + (j - burnin), pl->S, pl->stream));
-            CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(), pl->perm_cur.as<int>(), j,
-                                        pl->sm_count, pl->stream));
+            if (st_fixed) CU(bmm::launch_grid_invert_perm(1, K, pl->perm_cur.as<int>(), pl->perm_inv.as<int>(), pl->stream));
+            CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(),
+                                        st_fixed ? pl->perm_inv.as<int>() : pl->perm_cur.as<int>(), j, pl->sm_count, pl->stream, st_fixed));
         }
         if (pl->zfreq.p && j >= burnin)
             CU(bmm::launch_grid_zfreq(N, K, pl->zhist.as<uint8_t>() + (size_t)(b.keep_history ? j : 0) * N,
@@ -746,7 +751,7 @@ int bmm_plan_run(bmm_plan *pl) {
         CU(bmm::launch_stephens_batch(pl->C, pl->U, pl->K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
                                       pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(),
                                       pl->logQ.as<double>(), pl->sb_perm.as<int>(), pl->sb_cost.as<double>(),
-                                      pl->sb_ws.as<char>(), pl->stream));
+                                      pl->sb_ws.as<char>(), pl->stream, (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
         CU(cudaEventRecord(pl->evs[2], pl->stream));
         TRY(run_segment(pl, burnin, ns));
     } else {
@@ -928,7 +933,8 @@ static int run_fetch_pipelined(bmm_plan *pl, bmm_out *out) {
     if (pl->relabel)
         CU(bmm::launch_stephens_batch(pl->C, pl->U, K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
                                       pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(), pl->logQ.as<double>(),
-                                      pl->sb_perm.as<int>(), pl->sb_cost.as<double>(), pl->sb_ws.as<char>(), pl->stream));
+                                      pl->sb_perm.as<int>(), pl->sb_cost.as<double>(), pl->sb_ws.as<char>(), pl->stream,
+                                      (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
     const int nck = (S + CH - 1) / CH;
     auto enqueue = [&](int k) -> int {
         const int j0 = burnin + k * CH, cs = std::min(CH, ns - j0), b = k & 1;
@@ -1016,6 +1022,10 @@ int bmm_gibbs_dp(const bmm_args *args, bmm_out *out) { return run_once(BMM_SAMPL
 
 // ---- helpers --------------------------------------------------------------------------------------
 int bmm_stephens_batch(int32_t N, int32_t K, int32_t M, const double *p, double *q, int32_t *perm_MxK) {
+    return bmm_stephens_batch_ex(N, K, M, p, q, perm_MxK, 0);
+}
+
+int bmm_stephens_batch_ex(int32_t N, int32_t K, int32_t M, const double *p, double *q, int32_t *perm_MxK, uint32_t flags) {
     if (!p || !q || N < 1 || K < 1 || K > 255 || M < 1) return fail(BMM_ERR_INVALID, "bad stephens_batch arguments");
     if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
     const size_t NK = (size_t)N * K;
@@ -1024,7 +1034,8 @@ int bmm_stephens_batch(int32_t N, int32_t K, int32_t M, const double *p, double 
     CU(logp.alloc(NK * M * 8)); CU(Q.alloc(NK * 8)); CU(logQ.alloc(NK * 8));
     CU(perm.alloc((size_t)M * K * 4)); CU(cost.alloc((size_t)M * K * K * 8)); CU(ws.alloc((size_t)M * bmm::assign_ws_bytes(K)));
     CU(bmm::launch_stephens_batch(1, N, K, M, nullptr, cube.as<double>(), logp.as<double>(), Q.as<double>(),
-                                  logQ.as<double>(), perm.as<int>(), cost.as<double>(), ws.as<char>(), 0));
+                                  logQ.as<double>(), perm.as<int>(), cost.as<double>(), ws.as<char>(), 0,
+                                  (flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
     CU(cudaMemcpy(q, Q.p, NK * 8, cudaMemcpyDeviceToHost));
     if (perm_MxK) CU(cudaMemcpy(perm_MxK, perm.p, (size_t)M * K * 4, cudaMemcpyDeviceToHost));
     return BMM_OK;
@@ -1032,6 +1043,11 @@ int bmm_stephens_batch(int32_t N, int32_t K, int32_t M, const double *p, double 
 
 int bmm_stephens_online(int32_t N, int32_t K, const double *q, const double *p, int32_t sample_num,
                         int32_t *perm, double *q_new, double *cost) {
+    return bmm_stephens_online_ex(N, K, q, p, sample_num, perm, q_new, cost, 0);
+}
+
+int bmm_stephens_online_ex(int32_t N, int32_t K, const double *q, const double *p, int32_t sample_num,
+                           int32_t *perm, double *q_new, double *cost, uint32_t flags) {
     if (!p || !q || !perm || !q_new || N < 1 || K < 1 || K > 255) return fail(BMM_ERR_INVALID, "bad stephens_online arguments");
     if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
     const size_t NK = (size_t)N * K;
@@ -1039,7 +1055,7 @@ int bmm_stephens_online(int32_t N, int32_t K, const double *q, const double *p, 
     TRY(upload(Q, q, NK)); TRY(upload(pd, p, NK));
     CU(logQ.alloc(NK * 8)); CU(cd.alloc((size_t)K * K * 8)); CU(pm.alloc((size_t)K * 4)); CU(ws.alloc(bmm::assign_ws_bytes(K)));
     CU(bmm::launch_stephens_online(N, K, Q.as<double>(), logQ.as<double>(), pd.as<double>(), sample_num,
-                                   cd.as<double>(), pm.as<int>(), ws.as<char>(), 0));
+                                   cd.as<double>(), pm.as<int>(), ws.as<char>(), 0, (flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
     CU(cudaMemcpy(q_new, Q.p, NK * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(perm, pm.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
     if (cost) CU(cudaMemcpy(cost, cd.p, (size_t)K * K * 8, cudaMemcpyDeviceToHost));

@@ -276,14 +276,22 @@ __global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *pe
     }
 }
 
+// fixed (BMM_FLAG_STEPHENS_FIXED): perm is the inverse permutation and Q' the running mean (j Q + p) / (j + 1)
 __global__ void grid_qupdate_kernel(long long N, int K, float *__restrict__ Q, const float *__restrict__ P,
-                                    const int *__restrict__ perm, int sample_num) {
+                                    const int *__restrict__ perm, int sample_num, int fixed) {
     const float sn = (float)sample_num, inv = 1.f / (float)(sample_num + 1);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N * K; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / K;
         const int k = (int)(e % K);
-        Q[e] = sn * (Q[e] + P[i * K + perm[k]]) * inv;   // (stephens.cpp:87-92)
+        const float pr = P[i * K + perm[k]];
+        Q[e] = fixed ? (sn * Q[e] + pr) * inv : sn * (Q[e] + pr) * inv;   // (stephens.cpp:87-92)
     }
+}
+
+// inv[t][perm[t][l]] = l for n = M permutations of K
+__global__ void grid_invert_perm_kernel(int n, int K, const int *__restrict__ perm, int *__restrict__ inv) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * K; e += gridDim.x * blockDim.x)
+        inv[(e / K) * K + perm[e]] = e % K;
 }
 
 // batch: p.replace(0, 1e-6) (stephens.cpp:30-31)
@@ -360,9 +368,15 @@ cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int 
     return cudaGetLastError();
 }
 
+cudaError_t launch_grid_invert_perm(int n, int K, const int *perm, int *inv, cudaStream_t st) {
+    grid_invert_perm_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(n, K, perm, inv);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_grid_qupdate(long long N, int K, float *Q, const float *P, const int *perm, int sample_num,
-                                int sm_count, cudaStream_t st) {
-    grid_qupdate_kernel<<<sm_count * 8, 256, 0, st>>>(N, K, Q, P, perm, sample_num);
+                                int sm_count, cudaStream_t st, int fixed) {
+    grid_qupdate_kernel<<<sm_count * 8, 256, 0, st>>>(N, K, Q, P, perm, sample_num, fixed);
     g_launches++;
     return cudaGetLastError();
 }

@@ -76,7 +76,7 @@ __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s,
         if (j >= p.burnin) {
             stephens_online_block(N, K, nullptr, p.Q + (size_t)c * NK, p.logQ + (size_t)c * NK,
                                   p.probs_sample + (size_t)c * NK, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm,
-                                  p.assign_ws + (size_t)c * assign_ws_bytes(K));
+                                  p.assign_ws + (size_t)c * assign_ws_bytes(K), (p.flags & 64u) != 0);  // BMM_FLAG_STEPHENS_FIXED
         }
     }
     if (j >= p.burnin) {

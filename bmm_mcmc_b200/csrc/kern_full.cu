@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                 double *dst = p.cube + ((size_t)c * p.burnrelabel + (j - p.burnin + p.burnrelabel)) * UK;
                 for (size_t e = tid; e < UK; e += nthr) dst[e] = prob[e];
             } else if (j >= p.burnin) {
-                stephens_online_block(U, K, p.wt, Q, logQ, prob, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm, aws);
+                stephens_online_block(U, K, p.wt, Q, logQ, prob, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm, aws,
+                                      (p.flags & 64u) != 0);  // BMM_FLAG_STEPHENS_FIXED
             }
         }
         // ---- F: parameter draws

@@ -15,6 +15,7 @@ struct StephensBatchParams {
     int *perm;         // [chain][M*K cm]   scratch / out (perm[t + M*k])
     double *cost;      // [chain][M][K*K]   scratch
     char *assign_ws;   // [chain][M][assign_ws_bytes(K)]
+    int fixed;         // BMM_FLAG_STEPHENS_FIXED: store the inverse permutation (reference label -> sample column)
 };
 
 // One block per chain.  my_stephens_batch (stephens.cpp:6-64).
@@ -60,7 +61,11 @@ __global__ void stephens_batch_kernel(StephensBatchParams sp) {
             int c2r[256];
             int *out = c2r;
             assign_thread(K, cost + (size_t)t * K * K, ws + (size_t)t * wsb, out);
-            for (int k = 0; k < K; ++k) { changed |= perm[t + M * k] != out[k]; perm[t + M * k] = out[k]; }
+            if (sp.fixed) {   // what `perm.row(iter) <- sort_index(...)` (:56) was meant to do
+                for (int l = 0; l < K; ++l) { changed |= perm[t + M * out[l]] != l; perm[t + M * out[l]] = l; }
+            } else {
+                for (int k = 0; k < K; ++k) { changed |= perm[t + M * k] != out[k]; perm[t + M * k] = out[k]; }
+            }
         }
         // Fixed point: with unchanged permutations the next iteration recomputes the same Q, the same costs
         // and the same assignments, so the remaining iterations of the reference's fixed 100 are no-ops
@@ -72,13 +77,13 @@ __global__ void stephens_batch_kernel(StephensBatchParams sp) {
 
 
 __global__ void stephens_online_kernel(int U, int K, double *Q, double *logQ, const double *p, int sample_num,
-                                       double *cost_out, int *perm_out, char *ws) {
+                                       double *cost_out, int *perm_out, char *ws, int fixed) {
     extern __shared__ __align__(16) char sm[];
     double *cost = (double *)sm;
     int *perm = (int *)(cost + K * K);
     for (size_t e = threadIdx.x; e < (size_t)U * K; e += blockDim.x) logQ[e] = log(Q[e]);
     __syncthreads();
-    stephens_online_block(U, K, nullptr, Q, logQ, p, sample_num, cost, perm, ws);
+    stephens_online_block(U, K, nullptr, Q, logQ, p, sample_num, cost, perm, ws, fixed != 0);
     for (int e = threadIdx.x; e < K * K; e += blockDim.x) if (cost_out) cost_out[e] = cost[e];
     for (int e = threadIdx.x; e < K; e += blockDim.x) perm_out[e] = perm[e];
 }
@@ -113,19 +118,19 @@ __global__ void rdirichlet_kernel(int K, const double *alpha_m, unsigned long lo
 
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,
                                   double *Q, double *logQ, int *perm, double *cost, char *assign_ws,
-                                  cudaStream_t st) {
-    StephensBatchParams sp{U, K, M, wt, cube, logp, Q, logQ, perm, cost, assign_ws};
+                                  cudaStream_t st, int fixed) {
+    StephensBatchParams sp{U, K, M, wt, cube, logp, Q, logQ, perm, cost, assign_ws, fixed};
     stephens_batch_kernel<<<n_chains, 128, 0, st>>>(sp);
     g_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_stephens_online(int U, int K, double *Q, double *logQ, const double *p, int sample_num,
-                                   double *cost, int *perm, char *assign_ws, cudaStream_t st) {
+                                   double *cost, int *perm, char *assign_ws, cudaStream_t st, int fixed) {
     size_t smem = (size_t)K * K * 8 + (size_t)K * 4 + 16;
     cudaError_t e = cudaFuncSetAttribute(stephens_online_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    stephens_online_kernel<<<1, 256, smem, st>>>(U, K, Q, logQ, p, sample_num, cost, perm, assign_ws);
+    stephens_online_kernel<<<1, 256, smem, st>>>(U, K, Q, logQ, p, sample_num, cost, perm, assign_ws, fixed);
     g_launches++;
     return cudaGetLastError();
 }

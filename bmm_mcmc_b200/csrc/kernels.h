@@ -154,7 +154,8 @@ cudaError_t launch_grid_cost_tc(long long N, int K, const float *P, const float 
 cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int *perm_dst, int perm_stride, cudaStream_t st,
                                int *changed = nullptr);
 cudaError_t launch_grid_qupdate(long long N, int K, float *Q, const float *P, const int *perm, int sample_num,
-                                int sm_count, cudaStream_t st);
+                                int sm_count, cudaStream_t st, int fixed = 0);
+cudaError_t launch_grid_invert_perm(int n, int K, const int *perm, int *inv, cudaStream_t st);
 cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t st);
 cudaError_t launch_grid_qmean(long long N, int K, int M, const float *cube, const int *perm, float *Q, int sm_count,
                               cudaStream_t st);
@@ -165,9 +166,9 @@ cudaError_t launch_grid_zfreq(long long N, int K, const uint8_t *z, const int *p
 // ---- Stephens batch (kern_stephens.cu) -------------------------------------------------------
 cudaError_t launch_stephens_batch(int n_chains, int U, int K, int M, const int *wt, double *cube, double *logp,
                                   double *Q, double *logQ, int *perm, double *cost, char *assign_ws,
-                                  cudaStream_t st);
+                                  cudaStream_t st, int fixed = 0);
 cudaError_t launch_stephens_online(int U, int K, double *Q, double *logQ, const double *p, int sample_num,
-                                   double *cost, int *perm, char *assign_ws, cudaStream_t st);
+                                   double *cost, int *perm, char *assign_ws, cudaStream_t st, int fixed = 0);
 cudaError_t launch_assign(int K, int batch, const double *cost, int *solution, char *ws, cudaStream_t st);
 cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long seed, double *out, cudaStream_t st);
 

@@ -2,7 +2,8 @@
 // called once per sweep from inside the sampler kernels) and the batch initialisation kernel.
 // Restates /root/reference/src/stephens.cpp:6-94 *with its quirks* (SURVEY.md Appendix D 1-6):
 // 100 fixed batch iterations, permutations never inverted, online cost uses p*(p - log q),
-// Q' = j*(Q + p_reordered)/(j+1), zero->1e-6 clamping only in batch.
+// Q' = j*(Q + p_reordered)/(j+1), zero->1e-6 clamping only in batch.  `fixed` (BMM_FLAG_STEPHENS_FIXED)
+// selects the corrected variant of the online step instead; the default is the reference's.
 //
 // "Rows" are either observations (U = N, wt == nullptr) or unique data rows with multiplicities
 // (the uncollapsed samplers, where every observation with the same x shares one probability row);
@@ -15,8 +16,34 @@ namespace bmm {
 // cost (K x K, cm) and perm (K) live in shared memory; Q / logQ / p are U x K column-major.
 __device__ inline void stephens_online_block(int U, int K, const int *__restrict__ wt, double *Q, double *logQ,
                                              const double *p, int sample_num, double *cost, int *perm,
-                                             void *assign_ws) {
+                                             void *assign_ws, bool fixed = false) {
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (fixed) {   // BMM_FLAG_STEPHENS_FIXED: log p in the cost, inverse permutation and running mean in the update
+        for (int t = tid; t < K * K; t += nthr) {
+            const int k = t % K, l = t / K;
+            const double *pl = p + (size_t)U * l, *lq = logQ + (size_t)U * k;
+            double acc = 0.0;
+            for (int u = 0; u < U; ++u) {
+                const double pv = pl[u], term = pv > 0.0 ? pv * (log(pv) - lq[u]) : 0.0;
+                acc += wt ? wt[u] * term : term;
+            }
+            cost[k + K * l] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) assign_thread(K, cost, assign_ws, perm);
+        __syncthreads();
+        const double sn = (double)sample_num, sn1 = (double)(sample_num + 1);
+        for (int e = tid; e < U * K; e += nthr) {
+            const int u = e % U, k = e / U;
+            int inv = 0;
+            for (int l = 0; l < K; ++l) if (perm[l] == k) inv = l;   // sample column assigned to reference label k
+            const double qn = (sn * Q[e] + p[u + (size_t)U * inv]) / sn1;
+            Q[e] = qn;
+            logQ[e] = log(qn);
+        }
+        __syncthreads();
+        return;
+    }
     for (int t = tid; t < K * K; t += nthr) {
         const int k = t % K, l = t / K;
         const double *pl = p + (size_t)U * l, *lq = logQ + (size_t)U * k;

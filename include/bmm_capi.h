@@ -52,6 +52,14 @@ extern "C" {
                                         path only; 8 B per row at P = 64 instead of 256 B)         */
 #define BMM_FLAG_NO_TENSOR 32u        /* grid path, BMM_FP32: use the CUDA-core float kernel instead of
                                         the tcgen05 contraction (A/B testing)                      */
+#define BMM_FLAG_STEPHENS_FIXED 64u   /* correctness-fixed relabelling (NOT the reference): the batch
+                                      * initialisation and the online Q update re-order columns with the
+                                      * inverse of index_max(solution.col(.)) -- what the no-op
+                                      * `perm <- sort_index(perm)` (stephens.cpp:56,85) was meant to do --,
+                                      * the online cost uses log p like the batch cost (:79), and
+                                      * Q' = (j Q + p_reordered) / (j + 1) is a running mean (:92).  The
+                                      * batch loop's real threshold (1e-6, :24) needs no switch: it stops
+                                      * at the same fixed point the 100 iterations reach.                  */
 #define BMM_FLAG_GRID_PATH 8u        /* force the one-chain-over-the-whole-GPU kernels (default:
                                         chosen when n_chains <= 1 and N >= 32768, or when K*P is
                                         too large for the chain-per-block kernel)                  */
@@ -143,6 +151,11 @@ int bmm_stephens_batch(int32_t N, int32_t K, int32_t M, const double *p, double 
 /* my_stephens_online (stephens.cpp:66-94): perm[K], q_new N x K, optional cost K x K.             */
 int bmm_stephens_online(int32_t N, int32_t K, const double *q, const double *p, int32_t sample_num,
                         int32_t *perm, double *q_new, double *cost);
+/* The same two helpers with a flags word: BMM_FLAG_STEPHENS_FIXED selects the corrected variant
+ * (batch: perm_MxK then holds the inverse permutations, reference label -> sample column).          */
+int bmm_stephens_batch_ex(int32_t N, int32_t K, int32_t M, const double *p, double *q, int32_t *perm_MxK, uint32_t flags);
+int bmm_stephens_online_ex(int32_t N, int32_t K, const double *q, const double *p, int32_t sample_num,
+                           int32_t *perm, double *q_new, double *cost, uint32_t flags);
 /* _bmmmcmc_my_lpsolve (my_lpsolve.cpp:6-31): K x K cost (cm) -> K x K 0/1 solution (cm).
  * `batch` independent problems, consecutive in memory.                                            */
 int bmm_assign(int32_t K, int32_t batch, const double *cost, int32_t *solution);

@@ -122,6 +122,15 @@ int index_max_col(int K, const int *sol, int col) {  // arma::index_max: first m
     return best;
 }
 
+// Correctness-fixed Stephens mode (NOT the reference's behaviour, off by default):
+//   * threshold = 1e-6 instead of 10 ^ (-6) == -16, criterion on the total cost over the M slices (:24,58-59)
+//   * the permutation used to re-order columns is the inverse of index_max(solution.col(.)), which is what
+//     the no-op `perm <- sort_index(perm)` was meant to compute (:56,85)
+//   * online cost with log p, like the batch cost (:79)
+//   * Q' = (j Q + p_reordered) / (j + 1), a running mean (:92)
+// The permutation handed back to the samplers (sample label -> reference label) is unchanged.
+static int g_stephens_fixed = 0;
+
 // my_stephens_batch (stephens.cpp:6-64).  p: N x K x M cube (by value in the reference).
 int stephens_batch(int N, int K, int M, const double *p_in, double *q, int use_ref, int *perm_out) {
     std::vector<double> p(p_in, p_in + (size_t)N * K * M);
@@ -130,12 +139,14 @@ int stephens_batch(int N, int K, int M, const double *p_in, double *q, int use_r
     for (int k = 0; k < K; ++k)
         for (int t = 0; t < M; ++t) perm[t + (size_t)M * k] = k;
     // threshold = 10^(-6) is integer XOR = -16 (:24): the loop always runs maxiter = 100 times.
-    double previous = -99, current, criterion = 99, threshold = (double)(10 ^ (-6));
+    double previous = -99, current, criterion = 99, threshold = g_stephens_fixed ? 1e-6 : (double)(10 ^ (-6));
+    std::vector<int> a(K);
     int maxiter = 100, t = 0;
     const double min_prob = 0.000001;
     for (auto &v : p) if (v == 0.0) v = min_prob;  // p.replace(0, min_prob) :31
     while ((criterion > threshold) && (t < maxiter)) {
         t++;
+        double total = 0;
         std::fill(q, q + (size_t)N * K, 0.0);
         for (int k = 0; k < K; ++k)
             for (int it = 0; it < M; ++it) {
@@ -157,9 +168,15 @@ int stephens_batch(int N, int K, int M, const double *p_in, double *q, int use_r
             if (my_lpsolve(K, cost.data(), solution.data(), use_ref)) return 1;
             for (int k = 0; k < K; ++k) perm[it + (size_t)M * k] = index_max_col(K, solution.data(), k);
             // perm.row(iter) <- sort_index(...) (:56) is `perm.row(iter) < -sort_index(...)`: a no-op.
+            if (g_stephens_fixed) {
+                for (int k = 0; k < K; ++k) a[k] = perm[it + (size_t)M * k];
+                for (int l = 0; l < K; ++l) perm[it + (size_t)M * a[l]] = l;
+                for (size_t e = 0; e < (size_t)K * K; ++e) total += cost[e] * solution[e];
+            }
         }
         current = 0;
         for (size_t e = 0; e < (size_t)K * K; ++e) current += cost[e] * solution[e];
+        if (g_stephens_fixed) current = total;
         criterion = std::fabs(previous - current);
         previous = current;
     }
@@ -178,7 +195,8 @@ int stephens_online(int N, int K, const double *q, const double *p, int sample_n
             double acc = 0;
             for (int i = 0; i < N; ++i) {
                 double pv = p[i + (size_t)N * l];
-                acc += pv * (pv - logq[i]);  // p, not log p (:79)
+                if (g_stephens_fixed) acc += pv > 0 ? pv * (std::log(pv) - logq[i]) : 0.0;
+                else acc += pv * (pv - logq[i]);  // p, not log p (:79)
             }
             cost[k + (size_t)K * l] = acc;
         }
@@ -187,6 +205,14 @@ int stephens_online(int N, int K, const double *q, const double *p, int sample_n
     if (my_lpsolve(K, cost.data(), solution.data(), use_ref)) return 1;
     for (int k = 0; k < K; ++k) perm[k] = index_max_col(K, solution.data(), k);
     // perm <- sort_index(perm) (:85): no-op.
+    if (g_stephens_fixed) {
+        std::vector<int> inv(K);
+        for (int l = 0; l < K; ++l) inv[perm[l]] = l;
+        for (int k = 0; k < K; ++k)
+            for (int i = 0; i < N; ++i)
+                q_new[i + (size_t)N * k] = (sample_num * q[i + (size_t)N * k] + p[i + (size_t)N * inv[k]]) / (double)(sample_num + 1);
+        return 0;
+    }
     for (int k = 0; k < K; ++k)
         for (int i = 0; i < N; ++i)
             q_new[i + (size_t)N * k] =
@@ -250,6 +276,8 @@ struct oracle_out {
 };
 
 int oracle_has_lpsolve_ref() { return load_lp() != nullptr; }
+
+void oracle_set_stephens_fixed(int on) { g_stephens_fixed = on; }
 
 int oracle_assign(int K, const double *cost_cm, int *sol_cm, int use_ref) { return my_lpsolve(K, cost_cm, sol_cm, use_ref); }
 

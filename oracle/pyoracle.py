@@ -68,6 +68,13 @@ def assign(cost, use_ref=True):
     return sol
 
 
+def set_stephens_fixed(on):
+    """Correctness-fixed Stephens mode: real threshold, inverse permutation for the column
+    re-ordering, log p in the online cost, running-mean Q.  Process-wide switch; the default (off) is the
+    reference's behaviour."""
+    lib().oracle_set_stephens_fixed(int(bool(on)))
+
+
 def stephens_batch(p, use_ref=True):
     p = np.asfortranarray(p, dtype=np.float64)
     N, K, M = p.shape

@@ -21,7 +21,8 @@ struct RunSpec {
 };
 
 // chains / seed / device are taken from R options so the exported signatures stay the reference's:
-//   options(bmm.chains = 1L, bmm.seed = NULL, bmm.device = 0L)
+//   options(bmm.chains = 1L, bmm.seed = NULL, bmm.device = 0L, bmm.stephens_fixed = FALSE)
+// bmm.stephens_fixed = TRUE selects BMM_FLAG_STEPHENS_FIXED (corrected relabelling, not the reference's).
 // bmm.seed = NULL draws the Philox key from R's RNG, so set.seed() keeps runs reproducible.
 unsigned long long philox_seed() {
     SEXP s = Rf_GetOption1(Rf_install("bmm.seed"));
@@ -47,6 +48,7 @@ List run(const RunSpec &spec, IntegerMatrix df, const double *init_pi, const dou
     args.burnin = burnin; args.relabel = relabel; args.burnrelabel = burnrelabel; args.debug = debug;
     args.n_chains = 1; args.seed = philox_seed(); args.precision = BMM_FP64;
     args.device = int_option("bmm.device", 0);
+    if (int_option("bmm.stephens_fixed", 0)) args.flags |= BMM_FLAG_STEPHENS_FIXED;
     bmm_init init = {init_pi, init_theta, init_z};
 
     NumericMatrix pi(spec.has_pi ? S : 0, spec.has_pi ? K : 0);

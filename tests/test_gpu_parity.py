@@ -220,6 +220,70 @@ def test_stephens_helpers(oracle):
     _close(qn_g, qn_o, rtol=1e-12)
 
 
+def test_stephens_fixed_mode_helpers(oracle):
+    """BMM_FLAG_STEPHENS_FIXED through the helper entry points against the oracle's fixed mode (inverse permutation,
+    log p online cost, running-mean Q): same permutations, Q and cost to rounding."""
+    _need_gpu()
+    import ctypes as C
+    L = _lib.lib()
+    rng = np.random.default_rng(8)
+    N, K, M = 150, 4, 6
+    base = rng.dirichlet(np.ones(K) * 0.3, N)
+    sig = [rng.permutation(K) for _ in range(M)]
+    p = np.stack([0.9 * base[:, sg] + 0.1 * rng.dirichlet(np.ones(K), N) for sg in sig], axis=2)
+    p[5, 2, 1] = 0.0
+    pf = np.asfortranarray(p)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    try:
+        oracle.set_stephens_fixed(True)
+        q_o, perm_o = oracle.stephens_batch(pf, use_ref=oracle.has_ref())
+        ps = np.asfortranarray(base[:, sig[0]])
+        ps[7, 1] = 0.0
+        perm2_o, qn_o, cost_o = oracle.stephens_online(q_o, ps, 17, use_ref=oracle.has_ref())
+    finally:
+        oracle.set_stephens_fixed(False)
+    q_g = np.zeros((N, K), order="F")
+    perm_g = np.zeros((M, K), dtype=np.int32, order="F")
+    _lib.check(L.bmm_stephens_batch_ex(N, K, M, dp(pf), dp(q_g), ip(perm_g), _lib.FLAG_STEPHENS_FIXED))
+    assert np.array_equal(perm_g, perm_o)
+    _close(q_g, q_o, rtol=1e-12)
+    perm2_g = np.zeros(K, dtype=np.int32)
+    qn_g = np.zeros((N, K), order="F")
+    cost_g = np.zeros((K, K), order="F")
+    _lib.check(L.bmm_stephens_online_ex(N, K, dp(np.asfortranarray(q_o)), dp(ps), 17, ip(perm2_g), dp(qn_g), dp(cost_g),
+                                        _lib.FLAG_STEPHENS_FIXED))
+    _close(cost_g, cost_o, rtol=1e-9)
+    assert np.array_equal(perm2_g, perm2_o)
+    _close(qn_g, qn_o, rtol=1e-12)
+
+
+@pytest.mark.parametrize("grid", [False, True])
+def test_full_replay_stephens_fixed(oracle, datasets, grid):
+    """gibbs_full with relabelling in the correctness-fixed Stephens mode, replayed against the oracle in the same
+    mode, on the chain-per-block path (fp64) and the streaming grid path (float P / Q)."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    N, P = X.shape
+    K, ns, burnin, br = 3, 50, 20, 6
+    ip, th = _init_full(K, P, 5)
+    try:
+        oracle.set_stephens_fixed(True)
+        r = oracle.gibbs_full(X, ip, th, ns, K, burnin=burnin, relabel=True, burnrelabel=br, seed=11)
+    finally:
+        oracle.set_stephens_fixed(False)
+    r0 = oracle.gibbs_full(X, ip, th, ns, K, burnin=burnin, relabel=True, burnrelabel=br, seed=11)
+    g = B.gibbs_full(X, ns, K, burnin=burnin, relabel=True, burnrelabel=br, initial_pi=ip, initial_theta=th,
+                     replay=_replay_of(r), probes=("Q_final",), grid_path=grid, stephens_fixed=True)
+    t = r.tail()
+    assert np.array_equal(g["z_original"], t["z_original"])
+    assert np.array_equal(g["permutations"], t["permutations"])
+    assert np.array_equal(g["z"], t["z"])
+    _close(g["theta"], t["theta"], rtol=0)
+    _close(g["Q_final"], r["Q_final"], rtol=2e-4 if grid else 1e-9)
+    assert not np.allclose(r["Q_final"], r0["Q_final"])      # the mode does change the reference Q (running mean)
+
+
 def test_chain_split_invariance(datasets):
     """Chains are keyed by their global index: running chains 2..3 alone equals rows 2..3 of a 4-chain run."""
     _need_gpu()

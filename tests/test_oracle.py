@@ -103,6 +103,36 @@ def test_stephens_batch_identity_when_consistent(oracle):
     np.testing.assert_allclose(q, base, rtol=1e-12)
 
 
+def test_stephens_fixed_mode_undoes_a_three_cycle(oracle):
+    """Correctness-fixed mode: with the sample's columns a 3-cycle of the reference's, the online
+    step returns that cycle, re-orders with its inverse and keeps Q a running mean; the reference's own step
+    (quirks 3-5) re-orders with the forward permutation, which is wrong for a 3-cycle."""
+    rng = np.random.default_rng(5)
+    N, K, j = 60, 3, 7
+    base = rng.dirichlet(np.ones(K) * 0.3, N)
+    sigma = np.array([1, 2, 0])
+    p = base[:, sigma]                                   # sample column l shows reference label sigma[l]
+    try:
+        oracle.set_stephens_fixed(True)
+        perm, qn, cost = oracle.stephens_online(base, p, j, use_ref=oracle.has_ref())
+        want = np.array([[np.sum(p[:, l] * (np.log(p[:, l]) - np.log(base[:, k]))) for l in range(K)] for k in range(K)])
+        np.testing.assert_allclose(cost, want, rtol=1e-12)
+        assert np.array_equal(perm, sigma)
+        np.testing.assert_allclose(qn, (j * base + base) / (j + 1), rtol=1e-14)     # running mean of consistent labels
+        # batch: slices that are column permutations of one matrix come back to it
+        sig = [np.array([0, 1, 2]), sigma, np.array([2, 0, 1]), np.array([0, 1, 2])]
+        cube = np.stack([base[:, sg] for sg in sig], axis=2)
+        q, inv = oracle.stephens_batch(cube, use_ref=oracle.has_ref())
+        for t, sg in enumerate(sig):
+            assert np.array_equal(inv[t], np.argsort(sg)), t      # reference label -> sample column
+        np.testing.assert_allclose(q, np.maximum(base, 0), rtol=1e-12)
+    finally:
+        oracle.set_stephens_fixed(False)
+    perm_q, qn_q, _ = oracle.stephens_online(base, p, j, use_ref=oracle.has_ref())
+    assert np.array_equal(perm_q, sigma)
+    assert not np.allclose(qn_q, j * (base + base) / (j + 1))       # forward re-ordering: columns stay mixed up
+
+
 def test_full_posterior_recovers_truth(oracle, datasets):
     X = datasets["K3_N1000_P5"]
     ip, th = _init_full(3, 5, 1)
