@@ -6,14 +6,17 @@
 //   lp_table_kernel    per sweep: D (log2 units) split into fp16 hi|lo (22 significant bits; the 0/1 rows are
 //                      exact in fp16), written to global memory already in the shared-memory operand image
 //                      ([64-feature step][16-B chunk][2*128 rows][16 B]), so a stage is one contiguous 32 KB block.
-//   lp_sweep_kernel    persistent, one 128-observation tile at a time per CTA, 4-stage mbarrier pipeline:
-//                        warps 0-3  expand 64 bits per observation and step into the fp16 A stage;
-//                        warp 4     one thread streams the B stage with cp.async.bulk (mbarrier tx count);
-//                        warp 5     one thread issues 4 tcgen05.mma (M128 N256 K16) per step into one of two
-//                                   128 x 256 fp32 accumulators in TMEM and commits stage-empty / accumulator-full;
-//                        warps 6-9  epilogue of the previous tile while the next one is being multiplied:
-//                                   three passes over TMEM (max, sum, inverse-CDF walk) because 128 logits
-//                                   do not fit the register file; 1-byte allocation to HBM.
+//   lp_sweep_kernel    persistent, a 256-observation super-tile (two 128-row tiles) at a time per CTA, 3-stage
+//                      mbarrier pipeline of 64 features:
+//                        warps 0-7  expand 64 bits per observation and step into the two fp16 A tiles of the
+//                                   stage; after a super-tile's last step they run its epilogue: three passes
+//                                   over TMEM (max, sum, inverse-CDF walk; 128 logits do not fit the register
+//                                   file), 1-byte allocation to HBM;
+//                        warp 8     one thread streams the B stage with cp.async.bulk (mbarrier tx count);
+//                        warp 9     one thread issues 8 tcgen05.mma (M128 N256 K16) per step: both tiles
+//                                   against the SAME B stage, into two 128 x 256 fp32 accumulators (all of TMEM).
+//                      Sharing a B stage between two tiles halves the table traffic out of L2, which bounded
+//                      the one-tile version (every tile re-reads the 2 MB table: 9.3 TB/s at 1.77 ms).
 //   (counts)           V_kd, c_k from the allocations: kern_big_counts.cu (counting sort + bit-sliced counters
 //                      on the packed rows; a tcgen05 [X]^T onehot(z) kernel used to sit here and was 10x slower).
 //
@@ -29,13 +32,16 @@ namespace bmm {
 namespace {
 
 constexpr int LP_KC = 128;                  // clusters, padded
-constexpr int LP_NCOL = 2 * LP_KC;          // accumulator columns: hi | lo
+constexpr int LP_NCOL = 2 * LP_KC;          // accumulator columns per tile: hi | lo
 constexpr int LP_DK = 64;                   // features per pipeline step
-constexpr int LP_A_STAGE = 8 * 2048;        // [8 chunks][128 rows][16 B]
+constexpr int LP_TM = 2;                    // 128-observation tiles sharing one B stage (a 256-row super-tile)
+constexpr int LP_A_TILE = 8 * 2048;         // [8 chunks][128 rows][16 B]
+constexpr int LP_A_STAGE = LP_TM * LP_A_TILE;
 constexpr int LP_B_STAGE = 8 * LP_NCOL * 16;  // [8 chunks][256 rows][16 B]
 constexpr int LP_STAGE = LP_A_STAGE + LP_B_STAGE;
-constexpr int LP_NS = 4;                    // pipeline stages (48 KB each)
-constexpr int LP_THREADS = 320;             // warps 0-3 rows -> A stage, 4 B streamer, 5 MMA issuer, 6-9 epilogue
+constexpr int LP_NS = 3;                    // pipeline stages (64 KB each)
+constexpr int LP_ROWT = LP_TM * 128;        // row threads: warps 0-7 write A stages, then run the epilogue
+constexpr int LP_THREADS = LP_ROWT + 64;    // + warp 8 B streamer, warp 9 MMA issuer
 constexpr double LOG2E_D = 1.4426950408889634;
 
 // ---- per-sweep tables -----------------------------------------------------------------------------
@@ -86,7 +92,7 @@ __global__ void lp_bias_kernel(const BigParams p) {
 struct LpSmem {
     static constexpr int BIAS_OFF = LP_STAGE * LP_NS;
     static constexpr int BAR_OFF = BIAS_OFF + LP_KC * 4;
-    static constexpr int TOTAL = BAR_OFF + (2 * LP_NS + 4) * 8 + 16;
+    static constexpr int TOTAL = BAR_OFF + (2 * LP_NS + 2) * 8 + 16;
 };
 
 // logits of 32 clusters [c0, c0+32) of this thread's observation: hi + lo + bias
@@ -105,21 +111,22 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     const int K = p.K, W = p.W;
     const int nsteps = (p.P + LP_DK - 1) / LP_DK;   // the last step may be partial: missing words read as zero bits
     float *bias = (float *)(smem + LpSmem::BIAS_OFF);
-    uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[NS], empty[NS], accfull[2], accempty[2]
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * LP_NS + 4);
+    uint64_t *bars = (uint64_t *)(smem + LpSmem::BAR_OFF);   // full[NS], empty[NS], accfull, accempty
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * LP_NS + 2);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[LP_NS]);
-    const uint32_t accfull0 = smem_u32(&bars[2 * LP_NS]), accempty0 = smem_u32(&bars[2 * LP_NS + 2]);
+    const uint32_t accfull = smem_u32(&bars[2 * LP_NS]), accempty = smem_u32(&bars[2 * LP_NS + 1]);
+    constexpr int BW = LP_ROWT / 32, MW = BW + 1;   // B-streamer warp, MMA warp
 
-    if (warp == 4) {
+    if (warp == BW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 160) {
+    if (tid == MW * 32) {
         for (int s = 0; s < LP_NS; ++s) {
-            mbar_init(full0 + 8 * s, 129);     // 128 row threads + the bulk-copy thread
-            mbar_init(empty0 + 8 * s, 1);      // tcgen05.commit
+            mbar_init(full0 + 8 * s, LP_ROWT + 1);   // row threads + the bulk-copy thread
+            mbar_init(empty0 + 8 * s, 1);            // tcgen05.commit
         }
-        for (int h = 0; h < 2; ++h) { mbar_init(accfull0 + 8 * h, 1); mbar_init(accempty0 + 8 * h, 128); }
+        mbar_init(accfull, 1); mbar_init(accempty, LP_ROWT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // shift by the largest finite b_k (a cluster with pi_k = 0 has b_k = -inf and simply never wins)
@@ -135,110 +142,40 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
     __syncthreads();
     tc_fence_after();
     const uint32_t acc = *tmem_slot;
-    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    const long long nsuper = ((long long)p.N_local + LP_ROWT - 1) / LP_ROWT;   // super-tiles of 256 observations
+    const long long mine = blockIdx.x < nsuper ? (nsuper - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // of this CTA
     bool ok = true;
-    long long g = 0;       // pipeline step counter of this CTA (the three pipeline roles advance it identically)
-    int tile_it = 0;
 
-    if (warp < 4) {
-        // ================= rows -> fp16 A stages =================
-        const int t = tid;
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-            const long long i = tile * 128 + t;
-            const bool valid = i < p.N_local;
-            const uint32_t *xb = p.xbits + (size_t)(valid ? i : 0) * W;
-            // two 32-bit words per step; rows are only 4-byte aligned when W is odd, so the words are read singly
-            auto load_step = [&](int c) {
-                uint2 v = make_uint2(0u, 0u);
-                if (valid) {
-                    if ((W & 1) == 0) { if (2 * c < W) v = *(const uint2 *)(xb + 2 * c); }   // 8-byte aligned rows
-                    else {
-                        if (2 * c < W) v.x = xb[2 * c];
-                        if (2 * c + 1 < W) v.y = xb[2 * c + 1];
-                    }
-                }
-                return v;
-            };
-            uint2 nxt = load_step(0), nxt2 = load_step(1);
-            for (int c = 0; c < nsteps && ok; ++c, ++g) {
-                const uint2 cur = nxt;
-                nxt = nxt2;
-                if (c + 2 < nsteps) nxt2 = load_step(c + 2);
-                uint4 ex[8];
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const uint32_t byte = (ch < 4 ? cur.x : cur.y) >> ((ch & 3) * 8);
-                    ex[ch] = make_uint4(bits2_f16x2(byte), bits2_f16x2(byte >> 2), bits2_f16x2(byte >> 4), bits2_f16x2(byte >> 6));
-                }
-                const int s = (int)(g % LP_NS);
-                const long long n = g / LP_NS;
-                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
-                if (!ok) break;
-                unsigned char *A = smem + s * LP_STAGE;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) *(uint4 *)(A + ch * 2048 + t * 16) = ex[ch];
-                fence_async_smem();
-                mbar_arrive(full0 + 8 * s);
-            }
-        }
-    } else if (warp == 4) {
-      if (tid == 128) {
-        // ================= B stage streamer =================
-        const unsigned char *img = (const unsigned char *)p.lp_table;
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x)
-            for (int c = 0; c < nsteps && ok; ++c, ++g) {
-                const int s = (int)(g % LP_NS);
-                const long long n = g / LP_NS;
-                if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
-                if (!ok) break;
-                const uint32_t dst = smem_u32(smem + s * LP_STAGE + LP_A_STAGE);
-                mbar_arrive_expect_tx(full0 + 8 * s, LP_B_STAGE);
-                bulk_g2s(dst, img + (size_t)c * LP_B_STAGE, LP_B_STAGE, full0 + 8 * s);
-            }
-      }
-      __syncwarp();
-    } else if (warp == 5) {
-      if (tid == 160) {
-        // ================= MMA issuer: M128 N256 K16, accumulator buffer = tile parity =================
-        constexpr uint32_t IDESC = umma_idesc_f16(128, LP_NCOL, 0, 0);
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
-            const int h = tile_it & 1, use = tile_it >> 1;
-            if (use > 0) ok = mbar_wait(accempty0 + 8 * h, (uint32_t)((use - 1) & 1));
-            tc_fence_after();
-            for (int c = 0; c < nsteps && ok; ++c, ++g) {
-                const int s = (int)(g % LP_NS);
-                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g / LP_NS) & 1));
-                if (!ok) break;
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + kk * 2 * 2048, 2048, 128),
-                              umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
-                umma_commit(empty0 + 8 * s);
-                if (c == nsteps - 1) umma_commit(accfull0 + 8 * h);
-            }
-        }
-      }
-      __syncwarp();
-    } else {
-        // ================= epilogue: this thread's observation = TMEM lane =================
-        const int q4 = warp & 3;                          // TMEM lane quadrant this warp may read
-        const int t = q4 * 32 + (tid & 31);
-        const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    if (warp < BW) {
+        // ================= rows -> fp16 A stages, and the epilogue of the finished super-tile =================
+        const int h = tid >> 7, r = tid & 127;            // tile within the super-tile, row = TMEM lane
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16, acch = acc + (uint32_t)(h * LP_NCOL);
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
         const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
         uint8_t *zrow = p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local;
-        for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tile_it) {
-            const long long i = tile * 128 + t;
+        auto row_of = [&](long long it) { return ((long long)blockIdx.x + it * gridDim.x) * LP_ROWT + tid; };
+        // two 32-bit words per step; rows are only 4-byte aligned when W is odd, so the words are read singly
+        auto load_step = [&](long long it, int c) {
+            uint2 v = make_uint2(0u, 0u);
+            const long long i = row_of(it);
+            if (it < mine && i < p.N_local) {
+                const uint32_t *xb = p.xbits + (size_t)i * W;
+                if ((W & 1) == 0) { if (2 * c < W) v = *(const uint2 *)(xb + 2 * c); }   // 8-byte aligned rows
+                else {
+                    if (2 * c < W) v.x = xb[2 * c];
+                    if (2 * c + 1 < W) v.y = xb[2 * c + 1];
+                }
+            }
+            return v;
+        };
+        auto epilogue = [&](long long it) {
+            const long long i = row_of(it);
             const bool valid = i < p.N_local;
-            const int h = tile_it & 1, use = tile_it >> 1;
-            const uint32_t acch = acc + (uint32_t)(h * LP_NCOL);
             const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
             const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
             const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
-            ok = mbar_wait(accfull0 + 8 * h, (uint32_t)(use & 1));
-            if (!ok) break;
+            ok = mbar_wait(accfull, (uint32_t)(it & 1));
+            if (!ok) return;
             tc_fence_after();
             float l[32];
             float mx = -INFINITY;
@@ -282,15 +219,95 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                 }
             }
             tc_fence_before();
-            mbar_arrive(accempty0 + 8 * h);    // this accumulator buffer may be overwritten
+            mbar_arrive(accempty);             // the accumulators may be overwritten by the next super-tile
             z = min(z, K - 1);
             if (valid) zrow[i] = (uint8_t)(z + 1);
+        };
+        // Stages are produced in one flat sequence over (super-tile, step).  The epilogue of a super-tile runs after
+        // the first `pre` stages of the next one are in the ring, so the MMAs restart as soon as the accumulators
+        // are released (those stages only wait for MMAs of the finished super-tile: no cycle through accempty).
+        const int pre = nsteps < LP_NS ? nsteps : LP_NS;
+        const long long nstage = mine * nsteps;
+        long long it = 0, itp = 0;             // super-tile of stage g / of the stage being prefetched (g + 2)
+        int c = 0, cp = 0;                     // step within it
+        auto advance = [&](long long &t, int &k) { if (++k == nsteps) { k = 0; ++t; } };
+        uint2 nxt = load_step(itp, cp);
+        advance(itp, cp);
+        uint2 nxt2 = load_step(itp, cp);
+        advance(itp, cp);
+        for (long long g = 0; g < nstage && ok; ++g) {
+            const uint2 cur = nxt;
+            nxt = nxt2;
+            nxt2 = load_step(itp, cp);
+            advance(itp, cp);
+            uint4 ex[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint32_t byte = (ch < 4 ? cur.x : cur.y) >> ((ch & 3) * 8);
+                ex[ch] = make_uint4(bits2_f16x2(byte), bits2_f16x2(byte >> 2), bits2_f16x2(byte >> 4), bits2_f16x2(byte >> 6));
+            }
+            const int s = (int)(g % LP_NS);
+            const long long n = g / LP_NS;
+            if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+            if (!ok) break;
+            unsigned char *A = smem + s * LP_STAGE + h * LP_A_TILE;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) *(uint4 *)(A + ch * 2048 + r * 16) = ex[ch];
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * s);
+            if (it > 0 && c == pre - 1) epilogue(it - 1);
+            advance(it, c);
         }
+        if (ok && mine > 0) epilogue(mine - 1);
+    } else if (warp == BW) {
+      if (tid == BW * 32) {
+        // ================= B stage streamer =================
+        const unsigned char *img = (const unsigned char *)p.lp_table;
+        const long long nstage = mine * nsteps;
+        int c = 0;
+        for (long long g = 0; g < nstage && ok; ++g) {
+            const int s = (int)(g % LP_NS);
+            const long long n = g / LP_NS;
+            if (n > 0) ok = mbar_wait(empty0 + 8 * s, (uint32_t)((n - 1) & 1));
+            if (!ok) break;
+            const uint32_t dst = smem_u32(smem + s * LP_STAGE + LP_A_STAGE);
+            mbar_arrive_expect_tx(full0 + 8 * s, LP_B_STAGE);
+            bulk_g2s(dst, img + (size_t)c * LP_B_STAGE, LP_B_STAGE, full0 + 8 * s);
+            if (++c == nsteps) c = 0;
+        }
+      }
+      __syncwarp();
+    } else {
+      if (tid == MW * 32) {
+        // ================= MMA issuer: per step 4 x K16 for each of the two tiles against the same B stage =================
+        constexpr uint32_t IDESC = umma_idesc_f16(128, LP_NCOL, 0, 0);
+        long long g = 0;
+        for (long long it = 0; it < mine && ok; ++it) {
+            if (it > 0) ok = mbar_wait(accempty, (uint32_t)((it - 1) & 1));
+            tc_fence_after();
+            for (int c = 0; c < nsteps && ok; ++c, ++g) {
+                const int s = (int)(g % LP_NS);
+                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g / LP_NS) & 1));
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int h = 0; h < LP_TM; ++h)
+                        umma_bf16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + h * LP_A_TILE + kk * 2 * 2048, 2048, 128),
+                                  umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
+                umma_commit(empty0 + 8 * s);
+                if (c == nsteps - 1) umma_commit(accfull);
+            }
+        }
+      }
+      __syncwarp();
     }
     if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == BW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(acc), "r"(512) : "memory");
     }
@@ -315,7 +332,7 @@ cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStr
     }
     lp_table_kernel<<<(p.P + 63) / 64, 64, 0, st>>>(p);   // one thread per (padded) feature
     lp_bias_kernel<<<LP_KC, 128, 0, st>>>(p);
-    const long long ntiles = ((long long)p.N_local + 127) / 128;
+    const long long ntiles = ((long long)p.N_local + LP_ROWT - 1) / LP_ROWT;
     const int ctas = (int)(ntiles < sm_count ? ntiles : sm_count);
     lp_sweep_kernel<<<ctas, LP_THREADS, LpSmem::TOTAL, st>>>(p, j);
     g_launches += 3;
