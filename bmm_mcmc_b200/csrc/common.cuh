@@ -107,6 +107,22 @@ __device__ __forceinline__ double update_alpha_dev(Stream &s, double alpha_old, 
     return pi * g1 + (1 - pi) * g2;
 }
 
+// The same update with its four Gamma draws on independent substreams (index q of ST_ALPHA), used by the
+// uncollapsed samplers: the chain kernel draws them on four lanes next to the theta / pi draws instead of one
+// lane drawing them in turn after everybody else (that serial tail was a third of a C2 sweep), the grid
+// kernel draws the same four substreams so both paths keep producing the same chain.
+//   q = 0, 1: x ~ G(alpha + 1), y ~ G(N)   -> rbeta(alpha + 1, N) = x / (x + y)   (utils.cpp:8)
+//   q = 2, 3: G(a + K), G(a + K - 1)                                               (utils.cpp:12)
+__device__ __forceinline__ double alpha_gamma_shape(int q, double alpha_old, double a, int N, int K) {
+    return q == 0 ? alpha_old + 1.0 : (q == 1 ? (double)N : (q == 2 ? a + K : a + K - 1));
+}
+__device__ __forceinline__ double alpha_combine(const double *g, double a, double b, int N, int K) {
+    const double sb = g[0] + g[1], bt = sb > 0.0 ? g[0] / sb : 0.5;
+    const double b_eps = b - log(bt);
+    const double pi1 = a + K - 1, pi2 = N * b_eps, pi = pi1 / (pi1 + pi2);
+    return pi * (g[2] / b_eps) + (1 - pi) * (g[3] / b_eps);
+}
+
 // rmultinom(1, prob, K) replay rule (R nmath rmultinom.c / rbinom.c inversion branch, SURVEY App. A
 // items 3-4): sequential conditional binomials; one recorded uniform per non-zero category visited.
 // `getp(k)` returns prob[k]; u points at this draw's recorded uniforms.  Returns the 0-based label.

@@ -198,6 +198,7 @@ __global__ void big_param_kernel(const BigParams p, const int j) {
 // One block: pi, alpha, log pi, history rows; zero the next sweep's count buffer.
 __global__ void big_finish_kernel(const BigParams p, const int j) {
     __shared__ double red[32];
+    __shared__ double ag[4];
     const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = ns - p.burnin, tid = threadIdx.x;
     const bool replay = p.rtheta != nullptr;
     const double alpha_prev = *p.alpha_cur;
@@ -220,9 +221,13 @@ __global__ void big_finish_kernel(const BigParams p, const int j) {
         double sum = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
         for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.gsc[k] / sum;
-        if (tid == 0 && p.alpha0 == 0.0) {
-            Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, 0u);
-            *p.alpha_cur = update_alpha_dev(st, alpha_prev, p.a, p.b, (int)p.N_global, K);
+        if (p.alpha0 == 0.0) {          // the four Gamma substreams of the alpha update, one thread each
+            if (tid < 4) {
+                Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, (uint32_t)tid);
+                ag[tid] = st.gamma(alpha_gamma_shape(tid, alpha_prev, p.a, (int)p.N_global, K));
+            }
+            __syncthreads();
+            if (tid == 0) *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, K);
         }
     } else if (tid == 0) {           // stick-breaking weights (stickbreaking.cpp:195-214)
         p.gsc[K - 1] = 1.0;
@@ -235,8 +240,11 @@ __global__ void big_finish_kernel(const BigParams p, const int j) {
             cumprod *= (1 - p.gsc[k]);
         }
         if (p.alpha0 == 0.0) {
-            Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, 0u);
-            *p.alpha_cur = update_alpha_dev(st, alpha_prev, p.a, p.b, (int)p.N_global, K_viable);
+            for (int q = 0; q < 4; ++q) {
+                Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, (uint32_t)q);
+                ag[q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, (int)p.N_global, K_viable));
+            }
+            *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, K_viable);
         }
     }
     __syncthreads();

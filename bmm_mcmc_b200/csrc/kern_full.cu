@@ -34,7 +34,7 @@ __host__ __device__ inline size_t full_layout(const FullParams &p, char *base, F
     auto takeD = [&](size_t n) { double *r = (double *)(base + off); off += n * sizeof(double); return r; };
     auto takeI = [&](size_t n) { int *r = (int *)(base + off); off += n * sizeof(int); return r; };
     double *theta = takeD(KP), *w1 = takeD(KP), *w0 = takeD(KP), *pi = takeD(K), *lpi = takeD(K), *gsc = takeD(K);
-    double *cost = takeD(K * K <= (size_t)COST_SMEM_MAX ? K * K : 0), *scal = takeD(4);
+    double *cost = takeD(K * K <= (size_t)COST_SMEM_MAX ? K * K : 0), *scal = takeD(8);   // [0] alpha, [4..7] the Gamma draws of its update
     double *prob = nullptr, *Q = nullptr, *logQ = nullptr;
     if (p.use_hist) { prob = takeD(UK); if (p.relabel) { Q = takeD(UK); logQ = takeD(UK); } }
     int *ck = takeI(K), *Vkd = takeI(KP), *perm = takeI(K), *hist = nullptr;
@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
             __syncthreads();
             if (tid == 0) s.scal[0] = p.ralpha[(size_t)c * ns + j];
         } else {
-            for (int t = tid; t < K + KP; t += nthr) {
+            // alpha update: its Gamma draws ride along on spare lanes (substream q of ST_ALPHA); the two whose
+            // shape needs K_viable (stick-breaking) are drawn after the sticks
+            const int nalpha = p.alpha0 == 0.0 ? (p.stickbreaking ? 2 : 4) : 0;
+            for (int t = tid; t < K + KP + nalpha; t += nthr) {
                 if (t < K) {
                     if (!p.stickbreaking) {  // Dirichlet via K Gamma(alpha/K + c_k, 1) (full_gibbs.cpp:202-210)
                         Stream st(p.seed, chain, (uint32_t)j, ST_PI, (uint32_t)t);
@@ -207,10 +210,14 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                         Stream st(p.seed, chain, (uint32_t)j, ST_STICK, (uint32_t)t);
                         s.gsc[t] = st.beta(1.0 + s.ck[t], alpha_prev + later);
                     }
-                } else {                     // theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) (:213-225)
+                } else if (t < K + KP) {     // theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) (:213-225)
                     const int e = t - K, k = e % K, d = e / K;
                     Stream st(p.seed, chain, (uint32_t)j, ST_THETA, (uint32_t)(k * P + d));
                     s.theta[e] = st.beta(p.beta + s.Vkd[e], p.gamma + s.ck[k] - s.Vkd[e]);
+                } else {
+                    const int q = t - K - KP;
+                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)q);
+                    s.scal[4 + q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, N, K));
                 }
             }
             __syncthreads();
@@ -220,24 +227,30 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                     for (int k = 0; k < K; ++k) sum += s.gsc[k];
                     s.pi[t] = s.gsc[t] / sum;
                 }
-                if (tid == 0 && p.alpha0 == 0.0) {
-                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, 0u);
-                    s.scal[0] = update_alpha_dev(st, alpha_prev, p.a, p.b, N, K);
+                if (tid == 0 && p.alpha0 == 0.0) s.scal[0] = alpha_combine(s.scal + 4, p.a, p.b, N, K);
+            } else {                         // stick-breaking weights (stickbreaking.cpp:195-214)
+                if (tid == 0) {
+                    s.gsc[K - 1] = 1.0;
+                    int K_viable = 0;
+                    s.pi[0] = s.gsc[0];
+                    if (s.pi[0] > 0.01) K_viable++;
+                    double cumprod = 1 - s.gsc[0];
+                    for (int k = 1; k < K; ++k) {
+                        s.pi[k] = cumprod * s.gsc[k];
+                        if (s.pi[k] > 0.01) K_viable++;
+                        cumprod *= (1 - s.gsc[k]);
+                    }
+                    s.scal[1] = (double)K_viable;
                 }
-            } else if (tid == 0) {           // stick-breaking weights (stickbreaking.cpp:195-214)
-                s.gsc[K - 1] = 1.0;
-                int K_viable = 0;
-                s.pi[0] = s.gsc[0];
-                if (s.pi[0] > 0.01) K_viable++;
-                double cumprod = 1 - s.gsc[0];
-                for (int k = 1; k < K; ++k) {
-                    s.pi[k] = cumprod * s.gsc[k];
-                    if (s.pi[k] > 0.01) K_viable++;
-                    cumprod *= (1 - s.gsc[k]);
-                }
-                if (p.alpha0 == 0.0) {
-                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, 0u);
-                    s.scal[0] = update_alpha_dev(st, alpha_prev, p.a, p.b, N, K_viable);
+                if (p.alpha0 == 0.0) {       // the two draws whose shape is a + K_viable (- 1), side by side
+                    __syncthreads();
+                    const int K_viable = (int)s.scal[1];
+                    for (int q = 2 + tid; q < 4; q += nthr) {
+                        Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)q);
+                        s.scal[4 + q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, N, K_viable));
+                    }
+                    __syncthreads();
+                    if (tid == 0) s.scal[0] = alpha_combine(s.scal + 4, p.a, p.b, N, K_viable);
                 }
             }
         }
