@@ -587,15 +587,18 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     return BMM_OK;
 }
 
-// Threads per chain block of the uncollapsed chain-per-block kernel: 128 registers/thread cap the SM
-// at 512 resident threads, so smaller blocks keep more chains resident (one wave for 1024 chains at
-// 64 threads; measured on C2: 32 threads 9.5 ms, 64: 9.9 ms, 128: 14.4 ms per 300 sweeps).  BMM_FULL_THREADS overrides (tuning).
+// Threads per chain block of the uncollapsed chain-per-block kernel.  The per-sweep work of one chain is
+// narrow (32 unique rows, 18 parameters), so the block size is about latency hiding: two warps let the
+// relabelling step run beside the parameter draws, and the 64-thread entry point is capped at 144
+// registers so that seven blocks (1024 chains on 148 SMs) stay resident.  Measured on C2 per step:
+// 32 threads 28.0 ms, 64 threads 23.3 ms (before the two-warp split: 9.5 / 9.9 / 14.4 ms per 300 sweeps for
+// 32 / 64 / 128).  BMM_FULL_THREADS overrides (tuning).
 int full_threads(int n_chains) {
     if (const char *e = getenv("BMM_FULL_THREADS")) {
         int t = atoi(e);
         if (t == 32 || t == 64 || t == 128) return t;
     }
-    return n_chains >= 1024 ? 32 : (n_chains >= 512 ? 64 : 128);
+    return n_chains >= 512 ? 64 : 128;
 }
 
 int run_segment(bmm_plan *pl, int j0, int j1) {

@@ -44,7 +44,7 @@ __host__ __device__ inline size_t full_layout(const FullParams &p, char *base, F
     return (off + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
+__device__ __forceinline__ void full_chain_body(const FullParams &p) {
     extern __shared__ __align__(16) char smem_raw[];
     FullSmem s;
     full_layout(p, smem_raw, &s);
@@ -178,24 +178,23 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
             }
             __syncthreads();
         }
-        // ---- E: Stephens relabelling hooks (full_gibbs.cpp:146-176)
-        if (p.relabel) {
-            if (j < p.burnin && j >= p.burnin - p.burnrelabel) {
-                double *dst = p.cube + ((size_t)c * p.burnrelabel + (j - p.burnin + p.burnrelabel)) * UK;
-                for (size_t e = tid; e < UK; e += nthr) dst[e] = prob[e];
-            } else if (j >= p.burnin) {
-                stephens_online_block(U, K, p.wt, Q, logQ, prob, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm, aws,
-                                      (p.flags & 64u) != 0);  // BMM_FLAG_STEPHENS_FIXED
-            }
-        }
-        // ---- F: parameter draws
+        // ---- E: Stephens relabelling hooks (full_gibbs.cpp:146-176)   F: parameter draws
+        // E (reads prob, Q; writes Q, perm) and F (reads the counts; writes theta, pi, alpha) are independent.  Both
+        // are narrow -- K*K costs, K + K*P + 4 draws -- so with two or more warps per chain warp 1 relabels
+        // while warp 0 draws, each synchronising with __syncwarp; a one-warp block runs them in turn.
         const double alpha_prev = s.scal[0];
-        if (replay) {
-            for (int t = tid; t < KP; t += nthr) s.theta[t] = p.rtheta[(size_t)c * KP * ns + (size_t)KP * j + t];
-            for (int t = tid; t < K; t += nthr) s.pi[t] = p.rpi[(size_t)c * ns * K + j + (size_t)ns * t];
-            __syncthreads();
-            if (tid == 0) s.scal[0] = p.ralpha[(size_t)c * ns + j];
-        } else {
+        auto phase_e = [&](const int tid, const int nthr, auto sync) {
+            if (p.relabel && j >= p.burnin)
+                stephens_online_group(U, K, p.wt, Q, logQ, prob, j, p.cost_g ? p.cost_g + (size_t)c * K * K : s.cost, s.perm, aws,
+                                      (p.flags & 64u) != 0 /* BMM_FLAG_STEPHENS_FIXED */, tid, nthr, sync);
+        };
+        auto phase_f = [&](const int tid, const int nthr, auto sync) {
+            if (replay) {
+                for (int t = tid; t < KP; t += nthr) s.theta[t] = p.rtheta[(size_t)c * KP * ns + (size_t)KP * j + t];
+                for (int t = tid; t < K; t += nthr) s.pi[t] = p.rpi[(size_t)c * ns * K + j + (size_t)ns * t];
+                if (tid == 0) s.scal[0] = p.ralpha[(size_t)c * ns + j];
+                return;
+            }
             // alpha update: its Gamma draws ride along on spare lanes (substream q of ST_ALPHA); the two whose
             // shape needs K_viable (stick-breaking) are drawn after the sticks
             const int nalpha = p.alpha0 == 0.0 ? (p.stickbreaking ? 2 : 4) : 0;
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                     s.scal[4 + q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, N, K));
                 }
             }
-            __syncthreads();
+            sync();
             if (!p.stickbreaking) {
                 for (int t = tid; t < K; t += nthr) {
                     double sum = 0.0;
@@ -243,16 +242,28 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
                     s.scal[1] = (double)K_viable;
                 }
                 if (p.alpha0 == 0.0) {       // the two draws whose shape is a + K_viable (- 1), side by side
-                    __syncthreads();
+                    sync();
                     const int K_viable = (int)s.scal[1];
                     for (int q = 2 + tid; q < 4; q += nthr) {
                         Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)q);
                         s.scal[4 + q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, N, K_viable));
                     }
-                    __syncthreads();
+                    sync();
                     if (tid == 0) s.scal[0] = alpha_combine(s.scal + 4, p.a, p.b, N, K_viable);
                 }
             }
+        };
+        if (p.relabel && j < p.burnin && j >= p.burnin - p.burnrelabel) {
+            double *dst = p.cube + ((size_t)c * p.burnrelabel + (j - p.burnin + p.burnrelabel)) * UK;
+            for (size_t e = tid; e < UK; e += nthr) dst[e] = prob[e];
+        }
+        if (nthr >= 64) {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w == 0) phase_f(lane, 32, [] { __syncwarp(); });
+            else if (w == 1) phase_e(lane, 32, [] { __syncwarp(); });
+        } else {
+            phase_e(tid, nthr, [] { __syncthreads(); });
+            phase_f(tid, nthr, [] { __syncthreads(); });
         }
         __syncthreads();
         if (j >= p.burnin) {
@@ -280,15 +291,21 @@ __global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) {
         for (size_t e = tid; e < UK; e += nthr) { p.Q[(size_t)c * UK + e] = s.Q[e]; p.logQ[(size_t)c * UK + e] = s.logQ[e]; }
 }
 
+// Two entry points over one body: blocks of 64 threads are capped at 144 registers so that seven of them fit
+// an SM (1024 chains resident on 148 SMs); the 32- and 128-thread launches use the uncapped one.
+__global__ void __launch_bounds__(128) full_chain_kernel(const FullParams p) { full_chain_body(p); }
+__global__ void __launch_bounds__(64, 7) full_chain_kernel_64(const FullParams p) { full_chain_body(p); }
+
 }  // namespace
 
 size_t full_smem_bytes(const FullParams &p, int) { return full_layout(p, nullptr, nullptr); }
 
 cudaError_t launch_full(const FullParams &p, int n_chains, int threads, cudaStream_t st) {
     size_t smem = full_smem_bytes(p, threads);
-    cudaError_t e = cudaFuncSetAttribute(full_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = threads == 64 ? full_chain_kernel_64 : full_chain_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    full_chain_kernel<<<n_chains, threads, smem, st>>>(p);
+    kern<<<n_chains, threads, smem, st>>>(p);
     g_launches++;
     return cudaGetLastError();
 }

@@ -14,10 +14,13 @@
 namespace bmm {
 
 // cost (K x K, cm) and perm (K) live in shared memory; Q / logQ / p are U x K column-major.
-__device__ inline void stephens_online_block(int U, int K, const int *__restrict__ wt, double *Q, double *logQ,
+// The cooperating threads are `nthr` threads with ranks `tid` that `sync()` synchronises: the whole block with
+// __syncthreads, or one warp with __syncwarp when the sampler kernel relabels on one warp while another
+// draws the parameters.
+template <class Sync>
+__device__ inline void stephens_online_group(int U, int K, const int *__restrict__ wt, double *Q, double *logQ,
                                              const double *p, int sample_num, double *cost, int *perm,
-                                             void *assign_ws, bool fixed = false) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+                                             void *assign_ws, bool fixed, const int tid, const int nthr, Sync sync) {
     if (fixed) {   // BMM_FLAG_STEPHENS_FIXED: log p in the cost, inverse permutation and running mean in the update
         for (int t = tid; t < K * K; t += nthr) {
             const int k = t % K, l = t / K;
@@ -29,9 +32,9 @@ __device__ inline void stephens_online_block(int U, int K, const int *__restrict
             }
             cost[k + K * l] = acc;
         }
-        __syncthreads();
+        sync();
         if (tid == 0) assign_thread(K, cost, assign_ws, perm);
-        __syncthreads();
+        sync();
         const double sn = (double)sample_num, sn1 = (double)(sample_num + 1);
         for (int e = tid; e < U * K; e += nthr) {
             const int u = e % U, k = e / U;
@@ -41,7 +44,7 @@ __device__ inline void stephens_online_block(int U, int K, const int *__restrict
             Q[e] = qn;
             logQ[e] = log(qn);
         }
-        __syncthreads();
+        sync();
         return;
     }
     for (int t = tid; t < K * K; t += nthr) {
@@ -55,9 +58,9 @@ __device__ inline void stephens_online_block(int U, int K, const int *__restrict
         }
         cost[k + K * l] = acc;
     }
-    __syncthreads();
+    sync();
     if (tid == 0) assign_thread(K, cost, assign_ws, perm);  // perm[l] = index_max(solution.col(l)) (:82-84)
-    __syncthreads();
+    sync();
     const double sn = (double)sample_num, sn1 = (double)(sample_num + 1);
     for (int e = tid; e < U * K; e += nthr) {
         const int u = e % U, k = e / U;
@@ -65,7 +68,14 @@ __device__ inline void stephens_online_block(int U, int K, const int *__restrict
         Q[e] = qn;
         logQ[e] = log(qn);
     }
-    __syncthreads();
+    sync();
+}
+
+__device__ inline void stephens_online_block(int U, int K, const int *__restrict__ wt, double *Q, double *logQ,
+                                             const double *p, int sample_num, double *cost, int *perm,
+                                             void *assign_ws, bool fixed = false) {
+    stephens_online_group(U, K, wt, Q, logQ, p, sample_num, cost, perm, assign_ws, fixed, (int)threadIdx.x, (int)blockDim.x,
+                          [] { __syncthreads(); });
 }
 
 }  // namespace bmm
