@@ -71,32 +71,44 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def launch(self):
+        """Start nvidia-smi (it needs a few hundred ms to come up: call before the warm-up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def start(self):
+        """Open the timed window; only samples that arrive inside it are reported."""
+        if self.proc is None:
+            self.launch()
+        self.t0 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
+        self.t1 = time.perf_counter()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if self.t0 <= t <= self.t1 + 0.03]
+        if not inside and self.lines:      # a timed region shorter than one sampling period: the nearest sample
+            inside = [min(self.lines, key=lambda x: abs(x[0] - self.t1))[1]]
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -346,9 +358,10 @@ def run_grid(a):
 
     plan = api.Plan(sid, X, ns, K, chains=1, seed=2026, device=local, init_pi=ip, init_theta=th,
                     precision=w["precision"], compact_z=True, grid_path=True, **shard, **kw)
+    clocks = ClockSampler(local)
+    clocks.launch()
     for _ in range(a.warmup):
         plan.run(); plan.sync()
-    clocks = ClockSampler(local)
     barrier(); plan.sync()
     clocks.start()
     l0 = L.bmm_launch_count()
@@ -512,9 +525,10 @@ def main():
 
     # ---- device-resident arm (value) --------------------------------------------------------
     plan = api.Plan(sid, X, ns, K, chains=C_, seed=2026, device=local, chain_offset=rank * C_, **init_kw, **kw)
+    clocks = ClockSampler(local)
+    clocks.launch()
     for _ in range(a.warmup):
         plan.run(); plan.sync()
-    clocks = ClockSampler(local)
     barrier(); plan.sync()
     clocks.start()
     l0 = L.bmm_launch_count()
@@ -625,5 +639,31 @@ def main():
     return 0
 
 
+def _guarded_main():
+    """Exactly one JSON line reaches stdout: everything else a library prints there while the bench runs (the
+    NCCL version banner, for one) is sent to stderr by pointing fd 1 at fd 2 until the line is ready."""
+    import io
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, buf
+    try:
+        rc = main()
+    finally:
+        sys.stdout = py_stdout
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+    lines = buf.getvalue().splitlines()
+    js = [ln for ln in lines if ln.startswith("{")]
+    for ln in lines:
+        if ln not in js[-1:]:
+            print(ln, file=sys.stderr)
+    if js:
+        print(js[-1], flush=True)
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_guarded_main())
