@@ -347,7 +347,8 @@ def run_grid(a):
     X = synth_rows(lo, hi, P, K)
     ip, th = grid_init(K, P)
     sid = _lib.SAMPLER_STICKBREAKING if w["sampler"] == "stickbreaking" else _lib.SAMPLER_FULL
-    kname = "big_sweep_ws_kernel" if (K <= 32 and P <= 112) else "lp_table+lp_sweep+lp_counts kernels"
+    kname = "big_sweep_ws_kernel" if (K <= 32 and P <= 112) else "lp_table + lp_sweep + cnt_* kernels"
+    tkey = "big_sweep_ws_kernel" if (K <= 32 and P <= 112) else "lp_sweep_kernel"
     shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
     relabel, br = bool(w.get("relabel")), int(w.get("burnrelabel", 0))
     kw = dict(alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=relabel, burnrelabel=br)
@@ -409,8 +410,16 @@ def run_grid(a):
     bytes_per_update = (P + 7) // 8 + 1
     dur_s = kern[0] / a.steps / (ns - 1) / 1e3
     achieved = n_local * bytes_per_update / dur_s / 1e9
+    traffic = None   # dram bytes of the dominant kernel's launch from the committed ncu --set full capture (same rows per GPU)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(tkey, {})
+        if tr.get("n") == n_local and tr.get("dram_bytes_read") is not None:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+            "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
             "kernel": "%s (%d rows, %d B/update)" % (kname, n_local, bytes_per_update),
             "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))}
     if 2 * K * P / bytes_per_update > 1e3 * pk["bf16_tflops_sustained"] / pk["hbm_gbs"]:
