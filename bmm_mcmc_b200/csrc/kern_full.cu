@@ -198,26 +198,39 @@ __device__ __forceinline__ void full_chain_body(const FullParams &p) {
             // alpha update: its Gamma draws ride along on spare lanes (substream q of ST_ALPHA); the two whose
             // shape needs K_viable (stick-breaking) are drawn after the sticks
             const int nalpha = p.alpha0 == 0.0 ? (p.stickbreaking ? 2 : 4) : 0;
+            // Every lane describes its draw (substream, shapes) and then all of them run ONE copy of the sampler:
+            // with a separate inlined Gamma/Beta call per kind of parameter the diverged lanes executed the
+            // rejection sampler four times in turn (pi, theta x, theta y, alpha) instead of twice.
             for (int t = tid; t < K + KP + nalpha; t += nthr) {
+                uint32_t sid, idx;
+                double sa, sb = 0.0;
+                bool is_beta = false;
+                double *dst;
                 if (t < K) {
+                    idx = (uint32_t)t; dst = &s.gsc[t];
                     if (!p.stickbreaking) {  // Dirichlet via K Gamma(alpha/K + c_k, 1) (full_gibbs.cpp:202-210)
-                        Stream st(p.seed, chain, (uint32_t)j, ST_PI, (uint32_t)t);
-                        s.gsc[t] = st.gamma(alpha_prev / K + s.ck[t]);
+                        sid = ST_PI; sa = alpha_prev / K + s.ck[t];
                     } else {                 // v_k ~ Beta(1 + c_k, alpha + sum_{l>k} c_l) (stickbreaking.cpp:187-193)
                         int later = 0;
                         for (int l = t + 1; l < K; ++l) later += s.ck[l];
-                        Stream st(p.seed, chain, (uint32_t)j, ST_STICK, (uint32_t)t);
-                        s.gsc[t] = st.beta(1.0 + s.ck[t], alpha_prev + later);
+                        sid = ST_STICK; sa = 1.0 + s.ck[t]; sb = alpha_prev + later; is_beta = true;
                     }
                 } else if (t < K + KP) {     // theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) (:213-225)
                     const int e = t - K, k = e % K, d = e / K;
-                    Stream st(p.seed, chain, (uint32_t)j, ST_THETA, (uint32_t)(k * P + d));
-                    s.theta[e] = st.beta(p.beta + s.Vkd[e], p.gamma + s.ck[k] - s.Vkd[e]);
+                    sid = ST_THETA; idx = (uint32_t)(k * P + d); dst = &s.theta[e];
+                    sa = p.beta + s.Vkd[e]; sb = p.gamma + s.ck[k] - s.Vkd[e]; is_beta = true;
                 } else {
                     const int q = t - K - KP;
-                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)q);
-                    s.scal[4 + q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, N, K));
+                    sid = ST_ALPHA; idx = (uint32_t)q; dst = &s.scal[4 + q];
+                    sa = alpha_gamma_shape(q, alpha_prev, p.a, N, K);
                 }
+                Stream st(p.seed, chain, (uint32_t)j, sid, idx);
+                double val = st.gamma(sa);
+                if (is_beta) {               // Stream::beta: x / (x + y), 0.5 when both vanish
+                    const double y = st.gamma(sb), sum = val + y;
+                    val = sum > 0.0 ? val / sum : 0.5;
+                }
+                *dst = val;
             }
             sync();
             if (!p.stickbreaking) {
