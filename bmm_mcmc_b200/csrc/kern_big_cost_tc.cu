@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) grid_cost_tc_kernel(long long N
                 const uint64_t al = umma_desc(b + 1 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
                 const uint64_t bh = umma_desc(b + 2 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
                 const uint64_t bl = umma_desc(b + 3 * CT_MAT + kk * 256, 128, CT_ROWS * 16);
-                umma_bf16(acc, ah, bh, IDESC, (g > 0 || kk > 0) ? 1u : 0u);
-                umma_bf16(acc, ah, bl, IDESC, 1u);
-                umma_bf16(acc, al, bh, IDESC, 1u);
+                umma_f16(acc, ah, bh, IDESC, (g > 0 || kk > 0) ? 1u : 0u);
+                umma_f16(acc, ah, bl, IDESC, 1u);
+                umma_f16(acc, al, bh, IDESC, 1u);
             }
             umma_commit(empty0 + 8 * s);
         }

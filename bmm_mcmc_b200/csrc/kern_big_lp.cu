@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
                 for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
                     for (int h = 0; h < LP_TM; ++h)
-                        umma_bf16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + h * LP_A_TILE + kk * 2 * 2048, 2048, 128),
+                        umma_f16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + h * LP_A_TILE + kk * 2 * 2048, 2048, 128),
                                   umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
                 umma_commit(empty0 + 8 * s);
                 if (c == nsteps - 1) umma_commit(accfull);

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) big_sweep_tc_kernel(const BigPar
             // tcgen05.mma costs ~50 cycles whatever N is, so 3 x fewer instructions beat 3 x narrower ones)
 #pragma unroll
             for (int kk = 0; kk < NCH / 2; ++kk)
-                umma_bf16(acc1, umma_desc(a0 + kk * 2 * TC_CHUNK, TC_CHUNK, 128),
+                umma_f16(acc1, umma_desc(a0 + kk * 2 * TC_CHUNK, TC_CHUNK, 128),
                           umma_desc(b0 + kk * 2 * L::B1_ROW, L::B1_ROW, 128), IDESC1, kk ? 1u : 0u);
             umma_commit(bar1);
         }
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) big_sweep_tc_kernel(const BigPar
             const uint32_t a0 = smem_u32(A), b0 = smem_u32(B2);
 #pragma unroll
             for (int kk = 0; kk < TC_TILE / 16; ++kk)
-                umma_bf16(acc2, umma_desc(a0 + kk * 256, 128, TC_CHUNK), umma_desc(b0 + kk * 256, 128, TC_CHUNK),
+                umma_f16(acc2, umma_desc(a0 + kk * 256, 128, TC_CHUNK), umma_desc(b0 + kk * 256, 128, TC_CHUNK),
                           IDESC2, (it > 0 || kk > 0) ? 1u : 0u);
             umma_commit(bar2);
         }

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                 const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < NCH / 2; ++kk)
-                    umma_bf16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
+                    umma_f16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
                               db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
                 umma_commit(acc_full + 8 * a);
             }
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                 const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4), db = db0 + (uint64_t)((b * WS_B2_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
-                    umma_bf16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
+                    umma_f16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(free_a + 8 * s);
                 umma_commit(b2_free + 8 * b);
             }
