@@ -42,6 +42,10 @@ for prec in ("fp64", "fp32"):
     g = B.gibbs_stickbreaking(X[lo:hi], 8, K, alpha=1.0, burnin=1, seed=5, device=rank, precision=prec,
                               grid_path=True, n_global=N, row_offset=lo, probes=("counts",))
     out[prec] = g
+# the same chain with relabelling: K x K cost partial sums of the two row blocks are all-reduced (fp64)
+g = B.gibbs_full(X[lo:hi], 14, K, alpha=1.0, burnin=6, relabel=True, burnrelabel=3, seed=9, device=rank, precision="fp32",
+                 grid_path=True, n_global=N, row_offset=lo)
+out["rel"] = {k: g[k] for k in ("z", "z_original", "permutations", "theta")}
 np.savez(os.path.join(os.environ["BMM_OUT"], "rank%d.npz" % rank), lo=lo, hi=hi,
          **{p + "_" + k: v for p, g in out.items() for k, v in g.items()})
 bdist.finalize()
@@ -72,3 +76,13 @@ def test_n_sharded_equals_unsharded(tmp_path, p2p):
         assert np.array_equal(z, g["z"]), prec
         for k in ("theta", "pi", "alpha", "counts"):
             assert np.array_equal(r[0][prec + "_" + k], g[k]) and np.array_equal(r[1][prec + "_" + k], g[k]), (prec, k)
+    # relabelling on the sharded chain: the sweeps are bit-identical; the permutations come from all-reduced
+    # costs whose float partial sums are grouped differently, so they agree wherever the optimum is not a
+    # near-tie -- on this well-separated data everywhere -- and both ranks must hold the same ones
+    g = B.gibbs_full(X, 14, K, alpha=1.0, burnin=6, relabel=True, burnrelabel=3, seed=9, precision="fp32", grid_path=True)
+    z0 = np.concatenate([r[0]["rel_z_original"], r[1]["rel_z_original"]], axis=1)
+    assert np.array_equal(z0, g["z_original"])
+    assert np.array_equal(r[0]["rel_permutations"], r[1]["rel_permutations"])
+    assert np.array_equal(r[0]["rel_permutations"], g["permutations"])
+    assert np.array_equal(np.concatenate([r[0]["rel_z"], r[1]["rel_z"]], axis=1), g["z"])
+    assert np.array_equal(r[0]["rel_theta"], g["theta"])
