@@ -1,6 +1,13 @@
 # User-facing samplers.  Argument lists, defaults and the returned list are those of bmmmcmc 1.0
 # (reference R/utils.R:23-107); the initial state is drawn here with R's RNG exactly as the reference
 # does, then handed to the CUDA back end through the Rcpp host (src/host.cpp).
+#
+# Back-end settings that have no place in the reference's argument lists are R options:
+#   options(bmm.seed = NULL)              Philox key; NULL draws it from R's RNG (set.seed() reproducible)
+#   options(bmm.device = 0L)              CUDA device
+#   options(bmm.stephens_fixed = FALSE)   TRUE: corrected Stephens relabelling (inverse permutation for the
+#                                         column re-ordering, log p in the online cost, running-mean Q)
+#                                         instead of the reference's (stephens.cpp:56,79,85,92)
 
 .bmm_defaults <- function(nsamples, burnin, burnrelabel, alpha, clamp = TRUE) {
     if (is.null(burnin)) burnin <- round(0.1 * nsamples)
