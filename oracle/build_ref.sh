@@ -31,3 +31,25 @@ done
 wait
 gcc -shared -o "$OUT/liblpsolve_ref.so" $OBJS -lm -ldl
 echo "build_ref: built $OUT/liblpsolve_ref.so"
+
+# The reference's own samplers: every first-party C++ file of /root/reference/src, UNMODIFIED and compiled
+# where it lies, against the header-only Rcpp/Armadillo stand-in in oracle/shim/ (R, Rcpp and Armadillo are
+# not in this image).  -O2 is R's default optimisation level.  Linked with the lp_solve objects above.
+mkdir -p "$OUT/objcpp"
+COBJS=""
+for f in full_gibbs stickbreaking collapsed_gibbs collapsed_gibbs_dp stephens utils my_lpsolve RcppExports; do
+  o="$OUT/objcpp/$f.o"
+  if [ ! -f "$o" ] || [ "$S/$f.cpp" -nt "$o" ] || [ "$HERE/shim/RcppArmadillo.h" -nt "$o" ] || [ "$HERE/rrng.h" -nt "$o" ]; then
+    g++ -O2 -std=gnu++17 -fPIC -w -I"$HERE/shim" -I"$S" $INC -c "$S/$f.cpp" -o "$o" &
+  fi
+  COBJS="$COBJS $o"
+done
+g++ -O2 -std=gnu++17 -fPIC -Wall -I"$HERE/shim" -I"$S" $INC -c "$HERE/shim/ref_capi.cpp" -o "$OUT/objcpp/ref_capi.o" &
+wait
+for o in $COBJS "$OUT/objcpp/ref_capi.o"; do
+  [ -f "$o" ] || { echo "build_ref: $o did not compile"; exit 1; }
+done
+LPOBJS=""
+for f in "$S"/*.c; do LPOBJS="$LPOBJS $OUT/obj/$(basename "$f" .c).o"; done
+g++ -shared -o "$OUT/libbmm_ref.so" $COBJS "$OUT/objcpp/ref_capi.o" $LPOBJS -lm -ldl
+echo "build_ref: built $OUT/libbmm_ref.so"

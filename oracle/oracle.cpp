@@ -130,6 +130,7 @@ int index_max_col(int K, const int *sol, int col) {  // arma::index_max: first m
 //   * Q' = (j Q + p_reordered) / (j + 1), a running mean (:92)
 // The permutation handed back to the samplers (sample label -> reference label) is unchanged.
 static int g_stephens_fixed = 0;
+static int g_sample_stable = 0;
 
 // my_stephens_batch (stephens.cpp:6-64).  p: N x K x M cube (by value in the reference).
 int stephens_batch(int N, int K, int M, const double *p_in, double *q, int use_ref, int *perm_out) {
@@ -160,9 +161,15 @@ int stephens_batch(int N, int K, int M, const double *p_in, double *q, int use_r
                 for (size_t e = 0; e < (size_t)N * K; ++e) sub[e] = std::log(ps[e]);  // recomputed K times :49
                 for (int i = 0; i < N; ++i) logq[i] = std::log(q[i + (size_t)N * k]);
                 for (int l = 0; l < K; ++l) {
-                    double acc = 0;
-                    for (int i = 0; i < N; ++i) acc += ps[i + (size_t)N * l] * (sub[i + (size_t)N * l] - logq[i]);
-                    cost[k + (size_t)K * l] = acc;
+                    // arma::sum(expr, 0): two running sums over even / odd rows (op_sum::apply_noalias_proxy)
+                    double acc1 = 0, acc2 = 0;
+                    int i = 0;
+                    for (; i + 1 < N; i += 2) {
+                        acc1 += ps[i + (size_t)N * l] * (sub[i + (size_t)N * l] - logq[i]);
+                        acc2 += ps[i + 1 + (size_t)N * l] * (sub[i + 1 + (size_t)N * l] - logq[i + 1]);
+                    }
+                    if (i < N) acc1 += ps[i + (size_t)N * l] * (sub[i + (size_t)N * l] - logq[i]);
+                    cost[k + (size_t)K * l] = acc1 + acc2;
                 }
             }
             if (my_lpsolve(K, cost.data(), solution.data(), use_ref)) return 1;
@@ -192,13 +199,13 @@ int stephens_online(int N, int K, const double *q, const double *p, int sample_n
     for (int k = 0; k < K; ++k) {
         for (int i = 0; i < N; ++i) logq[i] = std::log(q[i + (size_t)N * k]);
         for (int l = 0; l < K; ++l) {
-            double acc = 0;
+            double acc[2] = {0, 0};  // arma::sum(expr, 0): even / odd rows accumulate separately
             for (int i = 0; i < N; ++i) {
                 double pv = p[i + (size_t)N * l];
-                if (g_stephens_fixed) acc += pv > 0 ? pv * (std::log(pv) - logq[i]) : 0.0;
-                else acc += pv * (pv - logq[i]);  // p, not log p (:79)
+                if (g_stephens_fixed) acc[i & 1] += pv > 0 ? pv * (std::log(pv) - logq[i]) : 0.0;
+                else acc[i & 1] += pv * (pv - logq[i]);  // p, not log p (:79)
             }
-            cost[k + (size_t)K * l] = acc;
+            cost[k + (size_t)K * l] = acc[0] + acc[1];
         }
     }
     if (cost_out) std::copy(cost.begin(), cost.end(), cost_out);
@@ -278,6 +285,10 @@ struct oracle_out {
 int oracle_has_lpsolve_ref() { return load_lp() != nullptr; }
 
 void oracle_set_stephens_fixed(int on) { g_stephens_fixed = on; }
+
+// Tie order of RcppArmadillo::sample()'s descending sort in the DP sampler: 0 (default) = std::sort like the
+// reference build, 1 = stable for every candidate count (see rrng.h::sample1).
+void oracle_set_sample_stable(int on) { g_sample_stable = on; }
 
 int oracle_assign(int K, const double *cost_cm, int *sol_cm, int use_ref) { return my_lpsolve(K, cost_cm, sol_cm, use_ref); }
 
@@ -576,6 +587,7 @@ int oracle_gibbs_dp(const int *df, int N, int P, int nsamples, double alpha, dou
                     oracle_out *o) {
     if (beta != gamma) return -4;
     RRng R; R.set_seed(seed);
+    R.stable_ties = g_sample_stable != 0;
     int K = 0;
     Relabel rl(N, maxK, burnin, relabel ? burnrelabel : 0, use_ref);
     std::vector<std::vector<int>> clusters(maxK);

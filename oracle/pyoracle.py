@@ -32,7 +32,12 @@ def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("oracle.cpp", "rrng.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(_HERE, "_ref", "liblpsolve_ref.so")):
+    ref_out = [os.path.join(_HERE, "_ref", f) for f in ("liblpsolve_ref.so", "libbmm_ref.so")]
+    ref_src = [os.path.join(_HERE, "build_ref.sh"), os.path.join(_HERE, "rrng.h")] + \
+        [os.path.join(_HERE, "shim", f) for f in ("RcppArmadillo.h", "ref_capi.cpp", "RcppArmadilloExtensions/sample.h")]
+    if os.path.isdir("/root/reference/src") and (
+            force or not all(os.path.exists(f) for f in ref_out)
+            or any(os.path.getmtime(s) > min(os.path.getmtime(f) for f in ref_out) for s in ref_src)):
         subprocess.check_call(["sh", os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
     return so
 
@@ -73,6 +78,12 @@ def set_stephens_fixed(on):
     re-ordering, log p in the online cost, running-mean Q.  Process-wide switch; the default (off) is the
     reference's behaviour."""
     lib().oracle_set_stephens_fixed(int(bool(on)))
+
+
+def set_sample_stable(on):
+    """DP sampler: tie order of sample()'s descending sort.  Off (default) = std::sort like the reference build
+    (stable up to 16 candidates); on = stable for every candidate count.  Process-wide switch."""
+    lib().oracle_set_sample_stable(int(bool(on)))
 
 
 def stephens_batch(p, use_ref=True):

@@ -13,16 +13,18 @@
 //   * rmultinom(1,..) (sequential conditional binomials, long double running total) and
 //     RcppArmadillo::sample(x,1,false,prob) (descending sort + cumulative walk): restated
 //     from the published algorithms; parity unpinned beyond the rbinom/unif_rand core.
-//     Tie rule for equal probabilities in sample(): stable (lower index first) -- this is
-//     the oracle's contract (std::sort on <=16 elements is an insertion sort, i.e. stable).
+//     Tie rule for equal probabilities in sample(): std::sort on (value, index) packets, as
+//     Armadillo's sort_index does (libstdc++: stable up to 16 candidates, introsort above).
 //   * rgamma / rbeta: NOT R's Ahrens-Dieter / Cheng generators.  Any exact sampler has the
 //     same law, so the oracle uses Marsaglia-Tsang + Box-Muller on the same uniform stream.
 //     Consequence: theta/pi/alpha draws agree with R only in distribution ("parity
 //     unpinned" for the parameter-draw values; pinned for everything deterministic).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <vector>
 
 namespace oracle {
 
@@ -130,17 +132,26 @@ struct RRng {
     }
 
     // RcppArmadillo::sample(x, 1, false, prob)(0): index into x of the drawn element.
-    // prob is normalised (FixProb), sorted descending (stable), walked cumulatively.
+    // prob is normalised (FixProb), sorted descending, walked cumulatively.  Armadillo's sort_index is
+    // std::sort over (value, index) packets with the comparator a.val > b.val: NOT a stable sort.  With
+    // libstdc++ it is an insertion sort (ties keep index order) up to 16 candidates and an introsort above;
+    // the compiled reference (oracle/_ref/libbmm_ref.so) shows the difference from sweep to sweep once a
+    // DP chain holds 16+ clusters with tied probabilities.  stable_ties = true selects the stable order for
+    // every n (the documented contract of the GPU's Philox path, where the order is immaterial in law).
+    bool stable_ties = false;
+    struct SortPacket { double val; int index; };
     int sample1(const double *prob_in, int n, double *scratch_p, int *scratch_perm) {
         double sum = 0.0;
         for (int i = 0; i < n; ++i) sum += prob_in[i];
-        for (int i = 0; i < n; ++i) { scratch_p[i] = prob_in[i] / sum; scratch_perm[i] = i; }
-        // stable insertion sort, descending
-        for (int i = 1; i < n; ++i) {
-            double v = scratch_p[i]; int pi_ = scratch_perm[i]; int j = i - 1;
-            while (j >= 0 && scratch_p[j] < v) { scratch_p[j + 1] = scratch_p[j]; scratch_perm[j + 1] = scratch_perm[j]; --j; }
-            scratch_p[j + 1] = v; scratch_perm[j + 1] = pi_;
-        }
+        SortPacket pk_small[64];
+        std::vector<SortPacket> pk_big;
+        SortPacket *pk = pk_small;
+        if (n > 64) { pk_big.resize(n); pk = pk_big.data(); }
+        for (int i = 0; i < n; ++i) { pk[i].val = prob_in[i] / sum; pk[i].index = i; }
+        auto cmp = [](const SortPacket &a, const SortPacket &b) { return a.val > b.val; };
+        if (stable_ties) std::stable_sort(pk, pk + n, cmp);
+        else std::sort(pk, pk + n, cmp);
+        for (int i = 0; i < n; ++i) { scratch_p[i] = pk[i].val; scratch_perm[i] = pk[i].index; }
         double rT = 1.0 * unif_rand(), mass = 0.0;
         int jj;
         for (jj = 0; jj < n - 1; ++jj) {
