@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -24,13 +25,11 @@
 #define BMM_FLAG_PROBE_LOGLIK 0x200u
 #define BMM_FLAG_PROBE_COUNTS 0x400u
 #define BMM_FLAG_PROBE_ZFREQ 0x1000u
-#define BMM_FLAG_PIPELINE 0x800u       // internal: run_once overlaps sampling with the z download (chunks of sweeps)
 
 namespace bmm {
 bool full_rows_fit_smem(int U, int K);
 }
 extern "C" void bmm_widen_u8_i32(const uint8_t *src, int32_t *dst, size_t n, int threads);  // host_widen.cpp
-extern "C" void bmm_widen_rows_u8_i32(const uint8_t *src, int32_t *dst, size_t rows, size_t cs, size_t stride, size_t off, int threads);
 
 namespace {
 
@@ -141,14 +140,16 @@ struct bmm_plan {
     bmm::CollapsedParams cp{};
     bmm::BigParams bp{};
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
-    bool pipelined = false;       // z is delivered chunk by chunk while later sweeps still run (run_once only)
-    int CH = 0;                   // sweeps per chunk
-    DevBuf zc_orig[2], zc_rel[2]; // chunk buffers [chain][observation][CH] bytes
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ck_done[2] = {nullptr, nullptr}, ck_copied[2] = {nullptr, nullptr};
     int deb = 4;                  // bytes per allocation of the device-side R-layout z (1: widened on the host)
     int sm_count = 148;
-    std::vector<cudaEvent_t> sweep_ev;   // start/stop of every sweep kernel of the last run (grid path)
+    std::vector<cudaEvent_t> sweep_ev;   // start/stop of the timed sweep kernels of the last run (grid path)
+    int ev_stride = 1;            // every ev_stride-th sweep kernel is bracketed by events (0: none)
+    bool sharded = false;         // rows of one chain block-partitioned over the ranks of bmm_dist_init
+    bool x_p2p = false;           // counts exchanged over peer memory (else NCCL)
+    bool use_graph = true, capturing = false;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    unsigned long long glaunches[2] = {0, 0};
+    DevBuf ws_b1, ws_s0, x_done;
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias, cnt_ws;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
     DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
@@ -163,6 +164,12 @@ struct bmm_plan {
     // replay
     DevBuf ru, rpi, rtheta, ralpha;
     bool ran = false;
+    // Chain state as bmm_plan_create left it, restored at the start of every bmm_plan_run so that a plan can be
+    // run any number of times (each run is the same chain from the same initial state).
+    struct Snap { DevBuf *live; DevBuf copy; };
+    std::vector<std::unique_ptr<Snap>> snaps;
+    std::vector<DevBuf *> zero_at_run;   // buffers the reference starts from zero (arma::fill::zeros) and only partly writes
+    int runs = 0;
     ~bmm_plan() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -170,8 +177,7 @@ struct bmm_plan {
         if (evk1) cudaEventDestroy(evk1);
         for (auto &e : evs) if (e) cudaEventDestroy(e);
         for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
-        for (int b = 0; b < 2; ++b) { if (ck_done[b]) cudaEventDestroy(ck_done[b]); if (ck_copied[b]) cudaEventDestroy(ck_copied[b]); }
-        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto &g : gexec) if (g) cudaGraphExecDestroy(g);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -187,8 +193,11 @@ int check_args(int sampler, const bmm_args *a, const bmm_init *init) {
     if (a->relabel) {
         // the reference's behaviour is undefined otherwise
         if (a->burnin < 2) return fail(BMM_ERR_INVALID, "relabel needs burnin >= 2 (Q is initialised at sweep burnin-1)");
-        if (a->burnrelabel < 1 || a->burnrelabel > a->burnin)
-            return fail(BMM_ERR_INVALID, "relabel needs 1 <= burnrelabel <= burnin");
+        // burnrelabel > burnin is legal at this level, as at the reference's .Call level: only the R wrappers clamp
+        // it, and gibbs_stickbreaking's does not (R/utils.R:95-107).  The slices of probs_out before sweep 1 stay
+        // zero and become 1e-6 in my_stephens_batch (stephens.cpp:30-31).
+        if (a->burnrelabel < 1) return fail(BMM_ERR_INVALID, "relabel needs burnrelabel >= 1");
+        if (a->burnrelabel > 100000) return fail(BMM_ERR_INVALID, "burnrelabel too large");
     }
     if (!(a->beta > 0) || !(a->gamma > 0)) return fail(BMM_ERR_INVALID, "beta and gamma must be > 0");
     if (a->alpha < 0) return fail(BMM_ERR_INVALID, "alpha must be >= 0 (0 = sample it)");
@@ -409,90 +418,193 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.lp_table = pl->lp_table.p; b.lp_bias = pl->lp_bias.as<double>(); b.cnt_ws = pl->cnt_ws.as<int>();
     b.ru = pl->ru.as<double>(); b.ru_slots = a.replay ? a.replay->u_slots : 0;
     b.rpi = pl->rpi.as<double>(); b.rtheta = pl->rtheta.as<double>(); b.ralpha = pl->ralpha.as<double>();
+    const bool tensor_ws = !(a.flags & BMM_FLAG_NO_TENSOR) && !getenv("BMM_NO_TC") && bmm::big_tc_supported(b);
+    if (tensor_ws) {
+        CU(pl->ws_b1.alloc(bmm::ws_b1_bytes(P)));     // zero: rows k >= K and columns d >= P stay zero
+        CU(pl->ws_s0.alloc(32 * 8));
+        b.ws_b1 = pl->ws_b1.as<unsigned char>(); b.ws_s0 = pl->ws_s0.as<double>();
+    }
+    pl->sharded = n_global > N;
+    if (pl->sharded) {
+        if (bmm::dist_world() < 2) return fail(BMM_ERR_NCCL, "N-sharded run needs bmm_dist_init with world > 1");
+        const size_t ncnt = (size_t)K + KP;
+        pl->x_p2p = bmm::dist_p2p_ready(ncnt);
+        if (pl->x_p2p) {
+            const bmm::P2PView v = bmm::dist_p2p_view();
+            CU(pl->x_done.alloc(sizeof(unsigned)));
+            b.x_world = v.world; b.x_rank = v.rank; b.x_cap = v.cap; b.x_peer = v.peer; b.x_local = v.local; b.x_seq = v.seq;
+            b.x_done = pl->x_done.as<unsigned>();
+            b.x_fused = tensor_ws ? 1 : 0;
+        }
+    }
+    {   // sweep-kernel timing: every sweep for short runs, every 8th otherwise (BMM_SWEEP_EVENTS = stride, 0 = none)
+        const char *e = getenv("BMM_SWEEP_EVENTS");
+        pl->ev_stride = e ? atoi(e) : (ns <= 24 ? 1 : 8);
+        if (const char *g = getenv("BMM_GRAPH")) pl->use_graph = g[0] != '0';
+    }
     return BMM_OK;
+}
+
+// ---- the grid path's sweep loop -------------------------------------------------------------------------
+// One sweep = front (z-sweep kernel, count exchange) + back (online relabelling, parameter update).  The batch
+// initialisation of the relabelling sits between the front and the back of sweep burnin-1 and needs the host
+// (its early exit reads a flag), so a run is: segment A = everything up to and including front(burnin-1),
+// the batch step, segment B = the rest.  Each segment is captured once into a CUDA graph and replayed by later
+// runs: per sweep the host would otherwise issue 3-8 launches, and at 8 GPUs a sweep kernel lasts ~45 us.
+int sweep_front(bmm_plan *pl, int j) {
+    const bmm::BigParams &b = pl->bp;
+    const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
+    const size_t NK = (size_t)b.N_local * K, ncnt = (size_t)K + (size_t)K * b.P;
+    bmm::BigParams bj = b;
+    if (pl->relabel) {   // where this sweep's probabilities go (full_gibbs.cpp:146-156)
+        if (j < burnin && j >= burnin - M) bj.probs_f32 = pl->cube_f.as<float>() + (size_t)(j - burnin + M) * NK;
+        else if (j >= burnin) bj.probs_f32 = pl->probs_f32.as<float>();
+    }
+    if (b.ru) CU(bmm::launch_big_replay_load(bj, j, pl->stream));
+    const bool timed = pl->ev_stride > 0 && (j % pl->ev_stride) == 0;
+    if (timed) CU(cudaEventRecordWithFlags(pl->sweep_ev[2 * j], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
+    CU(bmm::launch_big_sweep(bj, j, pl->sm_count, pl->stream));
+    if (timed) CU(cudaEventRecordWithFlags(pl->sweep_ev[2 * j + 1], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
+    if (pl->sharded) {   // counts of all ranks: pushed over peer memory when attached (consumed by the update kernel), else NCCL
+        int *cj = pl->counts.as<int>() + (size_t)(j & 1) * ncnt;
+        if (pl->x_p2p) {
+            if (!b.x_fused && bmm::dist_p2p_publish(cj, ncnt, j, pl->stream)) return fail(BMM_ERR_NCCL, bmm::dist_error());
+        } else if (bmm::dist_allreduce_i32(cj, ncnt, pl->stream)) return fail(BMM_ERR_NCCL, bmm::dist_error());
+    }
+    return BMM_OK;
+}
+
+int sweep_back(bmm_plan *pl, int j) {
+    const bmm::BigParams &b = pl->bp;
+    const int burnin = pl->a.burnin, K = b.K;
+    const long long N = b.N_local;
+    const int st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0;
+    const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
+    if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
+        CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), st_fixed, pl->cost_acc.as<double>(),
+                                 pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
+        if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
+            return fail(BMM_ERR_NCCL, bmm::dist_error());
+        CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
+                                   pl->perm_out.as<int>() + (j - burnin), pl->S, pl->stream));
+        if (st_fixed) CU(bmm::launch_grid_invert_perm(1, K, pl->perm_cur.as<int>(), pl->perm_inv.as<int>(), pl->stream));
+        CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(),
+                                    st_fixed ? pl->perm_inv.as<int>() : pl->perm_cur.as<int>(), j, pl->sm_count, pl->stream, st_fixed));
+    }
+    if (pl->zfreq.p && j >= burnin)
+        CU(bmm::launch_grid_zfreq(N, K, pl->zhist.as<uint8_t>() + (size_t)(b.keep_history ? j : 0) * N,
+                                  pl->relabel ? pl->perm_cur.as<int>() : nullptr, pl->zfreq.as<unsigned>(), pl->sm_count, pl->stream));
+    CU(bmm::launch_big_params(b, j, pl->stream));
+    return BMM_OK;
+}
+
+// my_stephens_batch on the grid path (full_gibbs.cpp:163-165), after front(burnin - 1); host-synchronised
+int batch_relabel_big(bmm_plan *pl) {
+    const bmm::BigParams &b = pl->bp;
+    const int M = pl->a.burnrelabel, K = b.K;
+    const long long N = b.N_local;
+    const size_t NK = (size_t)N * K;
+    const int st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0;
+    const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
+    float *cube = pl->cube_f.as<float>();
+    int *sbp = pl->sb_perm.as<int>();
+    CU(bmm::launch_grid_clamp((long long)M * (long long)NK, cube, pl->sm_count, pl->stream));
+    CU(bmm::launch_grid_identity_perm(M * K, K, sbp, pl->stream));
+    // The reference always runs 100 iterations (threshold 10^(-6) == -16, quirk 1).  Once an iteration
+    // leaves every permutation unchanged the following ones recompute the same Q, costs and
+    // assignments, so stopping there returns exactly what the 100th iteration would.
+    int *flag = pl->status.as<int>() + 1;
+    for (int iter = 0; iter < 100; ++iter) {
+        if (st_fixed) CU(bmm::launch_grid_invert_perm(M, K, sbp, pl->perm_inv.as<int>(), pl->stream));
+        CU(bmm::launch_grid_qmean(N, K, M, cube, st_fixed ? pl->perm_inv.as<int>() : sbp, pl->Qf.as<float>(), pl->sm_count,
+                                  pl->stream));
+        CU(cudaMemsetAsync(flag, 0, sizeof(int), pl->stream));
+        for (int t = 0; t < M; ++t) {
+            CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
+                                     pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
+            if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
+                return fail(BMM_ERR_NCCL, bmm::dist_error());
+            CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
+                                       pl->stream, flag));
+        }
+        int changed = 1;   // every rank sees the same all-reduced costs, hence the same flag
+        CU(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+        CU(cudaStreamSynchronize(pl->stream));
+        if (!changed) break;
+    }
+    return BMM_OK;
+}
+
+// Segment 0: run prologue, sweeps [1, jsplit) in full, front(jsplit).  Segment 1: back(jsplit), sweeps (jsplit, ns).
+// Without relabelling there is only segment 0 with jsplit = ns (no trailing front).
+int enqueue_segment(bmm_plan *pl, int seg, int jsplit) {
+    const bmm::BigParams &b = pl->bp;
+    const int ns = pl->ns;
+    if (seg == 0) {
+        CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
+        if (pl->zfreq.p) CU(cudaMemsetAsync(pl->zfreq.p, 0, pl->zfreq.bytes, pl->stream));
+        if (pl->x_done.p) CU(cudaMemsetAsync(pl->x_done.p, 0, pl->x_done.bytes, pl->stream));
+        if (pl->x_p2p && bmm::dist_p2p_begin_run(ns, pl->stream)) return fail(BMM_ERR_NCCL, bmm::dist_error());
+        CU(bmm::launch_big_init(b, pl->stream));
+        CU(bmm::launch_ws_table(b, pl->stream));
+        if (pl->relabel) CU(bmm::launch_grid_identity_perm(b.K, b.K, pl->perm_cur.as<int>(), pl->stream));
+        for (int j = 1; j < jsplit; ++j) { TRY(sweep_front(pl, j)); TRY(sweep_back(pl, j)); }
+        if (jsplit < ns) TRY(sweep_front(pl, jsplit));
+    } else {
+        TRY(sweep_back(pl, jsplit));
+        for (int j = jsplit + 1; j < ns; ++j) { TRY(sweep_front(pl, j)); TRY(sweep_back(pl, j)); }
+    }
+    return BMM_OK;
+}
+
+// Run one segment through its CUDA graph (captured on first use).  Falls back to plain launches if the capture
+// or the instantiation is refused.
+int run_segment_big(bmm_plan *pl, int seg, int jsplit) {
+    if (pl->use_graph && !pl->gexec[seg]) {
+        const unsigned long long l0 = bmm::g_launches;
+        cudaError_t e = cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
+            pl->capturing = true;
+            const int rc = enqueue_segment(pl, seg, jsplit);
+            pl->capturing = false;
+            cudaGraph_t g = nullptr;
+            e = cudaStreamEndCapture(pl->stream, &g);
+            if (rc == BMM_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&pl->gexec[seg], g, 0);
+            else if (e == cudaSuccess) e = cudaErrorUnknown;
+            if (g) cudaGraphDestroy(g);
+            if (rc != BMM_OK && rc != BMM_ERR_CUDA) return rc;     // a real (non-capture) error: report it
+        }
+        if (e != cudaSuccess || !pl->gexec[seg]) {
+            cudaGetLastError();
+            pl->gexec[seg] = nullptr;
+            pl->use_graph = false;
+            bmm::g_launches = l0;
+        } else {
+            pl->glaunches[seg] = bmm::g_launches - l0;
+            bmm::g_launches = l0;
+        }
+    }
+    if (pl->use_graph && pl->gexec[seg]) {
+        CU(cudaGraphLaunch(pl->gexec[seg], pl->stream));
+        bmm::g_launches += pl->glaunches[seg];
+        return BMM_OK;
+    }
+    return enqueue_segment(pl, seg, jsplit);
 }
 
 // All sweeps of the grid path on the plan's stream.
 int run_big(bmm_plan *pl) {
-    const bmm::BigParams &b = pl->bp;
-    const int ns = pl->ns;
-    const size_t ncnt = (size_t)b.K + (size_t)b.K * b.P;
-    const bool sharded = b.N_global > b.N_local;
-    if (sharded && bmm::dist_world() < 2) return fail(BMM_ERR_NCCL, "N-sharded run needs bmm_dist_init with world > 1");
+    const int ns = pl->ns, burnin = pl->a.burnin;
+    if (pl->sharded && bmm::dist_world() < 2) return fail(BMM_ERR_NCCL, "N-sharded run needs bmm_dist_init with world > 1");
     while (pl->sweep_ev.size() < (size_t)2 * ns) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         pl->sweep_ev.push_back(e);
     }
-    CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
-    if (pl->zfreq.p) CU(cudaMemsetAsync(pl->zfreq.p, 0, pl->zfreq.bytes, pl->stream));
-    CU(bmm::launch_big_init(b, pl->stream));
-    const int burnin = pl->a.burnin, M = pl->a.burnrelabel, K = b.K;
-    const long long N = b.N_local;
-    const size_t NK = (size_t)N * K;
-    const int st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0;
-    const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
-    if (pl->relabel) CU(bmm::launch_grid_identity_perm(K, K, pl->perm_cur.as<int>(), pl->stream));
-    for (int j = 1; j < ns; ++j) {
-        bmm::BigParams bj = b;
-        if (pl->relabel) {   // where this sweep's probabilities go (full_gibbs.cpp:146-156)
-            if (j < burnin && j >= burnin - M) bj.probs_f32 = pl->cube_f.as<float>() + (size_t)(j - burnin + M) * NK;
-            else if (j >= burnin) bj.probs_f32 = pl->probs_f32.as<float>();
-        }
-        if (b.ru) CU(bmm::launch_big_replay_load(bj, j, pl->stream));
-        CU(cudaEventRecord(pl->sweep_ev[2 * j], pl->stream));
-        CU(bmm::launch_big_sweep(bj, j, pl->sm_count, pl->stream));
-        CU(cudaEventRecord(pl->sweep_ev[2 * j + 1], pl->stream));
-        if (sharded) {   // counts of all ranks: one-shot push over peer memory when attached, else NCCL
-            int *cj = pl->counts.as<int>() + (size_t)(j & 1) * ncnt;
-            const int rc_ar = bmm::dist_p2p_ready(ncnt) ? bmm::dist_p2p_allreduce_i32(cj, ncnt, pl->status.as<int>(), pl->stream)
-                                                         : bmm::dist_allreduce_i32(cj, ncnt, pl->stream);
-            if (rc_ar) return fail(BMM_ERR_NCCL, bmm::dist_error());
-        }
-        if (pl->relabel && j == burnin - 1) {          // my_stephens_batch (full_gibbs.cpp:163-165)
-            float *cube = pl->cube_f.as<float>();
-            int *sbp = pl->sb_perm.as<int>();
-            CU(bmm::launch_grid_clamp((long long)M * (long long)NK, cube, pl->sm_count, pl->stream));
-            CU(bmm::launch_grid_identity_perm(M * K, K, sbp, pl->stream));
-            // The reference always runs 100 iterations (threshold 10^(-6) == -16, quirk 1).  Once an iteration
-            // leaves every permutation unchanged the following ones recompute the same Q, costs and
-            // assignments, so stopping there returns exactly what the 100th iteration would.
-            int *flag = pl->status.as<int>() + 1;
-            for (int iter = 0; iter < 100; ++iter) {
-                if (st_fixed) CU(bmm::launch_grid_invert_perm(M, K, sbp, pl->perm_inv.as<int>(), pl->stream));
-                CU(bmm::launch_grid_qmean(N, K, M, cube, st_fixed ? pl->perm_inv.as<int>() : sbp, pl->Qf.as<float>(), pl->sm_count,
-                                          pl->stream));
-                CU(cudaMemsetAsync(flag, 0, sizeof(int), pl->stream));
-                for (int t = 0; t < M; ++t) {
-                    CU(bmm::launch_grid_cost(N, K, cube + (size_t)t * NK, pl->Qf.as<float>(), 1, pl->cost_acc.as<double>(),
-                                             pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
-                    if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
-                        return fail(BMM_ERR_NCCL, bmm::dist_error());
-                    CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
-                                               pl->stream, flag));
-                }
-                int changed = 1;   // every rank sees the same all-reduced costs, hence the same flag
-                CU(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
-                CU(cudaStreamSynchronize(pl->stream));
-                if (!changed) break;
-            }
-        } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
-            CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), st_fixed, pl->cost_acc.as<double>(),
-                                     pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
-            if (sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
-                return fail(BMM_ERR_NCCL, bmm::dist_error());
-            CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
-                                       pl->perm_out.as<int>() + (j - burnin), pl->S, pl->stream));
-            if (st_fixed) CU(bmm::launch_grid_invert_perm(1, K, pl->perm_cur.as<int>(), pl->perm_inv.as<int>(), pl->stream));
-            CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(),
-                                        st_fixed ? pl->perm_inv.as<int>() : pl->perm_cur.as<int>(), j, pl->sm_count, pl->stream, st_fixed));
-        }
-        if (pl->zfreq.p && j >= burnin)
-            CU(bmm::launch_grid_zfreq(N, K, pl->zhist.as<uint8_t>() + (size_t)(b.keep_history ? j : 0) * N,
-                                      pl->relabel ? pl->perm_cur.as<int>() : nullptr, pl->zfreq.as<unsigned>(), pl->sm_count, pl->stream));
-        CU(bmm::launch_big_params(bj, j, pl->stream));
-    }
-    return BMM_OK;
+    if (!pl->relabel) return run_segment_big(pl, 0, ns);
+    TRY(run_segment_big(pl, 0, burnin - 1));
+    TRY(batch_relabel_big(pl));
+    return run_segment_big(pl, 1, burnin - 1);
 }
 
 int create_collapsed(bmm_plan *pl, const bmm_init *init) {
@@ -620,11 +732,15 @@ struct Staging {
     uint8_t *buf[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     size_t bytes = 0;
-} g_stage;
+};
+std::mutex g_stage_m;                 // one download at a time per process: the staging buffers are shared
+std::map<int, Staging> g_stages;      // per device (events belong to the device they were created on)
 
 int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
     if (!dst || !src.p || n == 0) return BMM_OK;
     const size_t CH = (size_t)32 << 20;
+    std::lock_guard<std::mutex> lock(g_stage_m);
+    Staging &g_stage = g_stages[pl->a.device];
     if (!g_stage.buf[0]) {
         for (int b = 0; b < 2; ++b) {
             CU(cudaHostAlloc((void **)&g_stage.buf[b], CH, cudaHostAllocDefault));
@@ -661,6 +777,41 @@ int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
     return BMM_OK;
 }
 
+// Record the initial chain state (called once, at the end of bmm_plan_create).
+int snapshot_state(bmm_plan *pl) {
+    std::vector<DevBuf *> live;
+    if (pl->grid_path) live = {&pl->theta_cur, &pl->pi_cur, &pl->alpha_cur};
+    else if (pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING)
+        live = {&pl->theta_cur, &pl->pi_cur, &pl->alpha_cur};
+    else live = {&pl->z_cur, &pl->cnt, &pl->alpha_cur, &pl->dp_used, &pl->dp_free};
+    for (DevBuf *b : live) {
+        if (!b->p || !b->bytes) continue;
+        std::unique_ptr<bmm_plan::Snap> sn(new bmm_plan::Snap());
+        sn->live = b;
+        CU(sn->copy.alloc(b->bytes, false));
+        CU(cudaMemcpy(sn->copy.p, b->p, b->bytes, cudaMemcpyDeviceToDevice));
+        pl->snaps.push_back(std::move(sn));
+    }
+    // zero-initialised in the reference and not fully overwritten by a run: the relabelling stores (slices before
+    // sweep 1 when burnrelabel > burnin; the DP sampler writes only the columns of live labels and never clears
+    // probs_sample, collapsed_gibbs_dp.cpp:91-92,195-199), the DP theta histories (:77-78), the status words
+    pl->zero_at_run = {&pl->status, &pl->cube, &pl->cube_f, &pl->probs_sample, &pl->Q, &pl->logQ};
+    if (pl->sampler == BMM_SAMPLER_DP) {
+        pl->zero_at_run.push_back(&pl->theta_out);
+        pl->zero_at_run.push_back(&pl->theta_rel_out);
+        pl->zero_at_run.push_back(&pl->kactive);
+    }
+    return BMM_OK;
+}
+
+int restore_state(bmm_plan *pl) {
+    for (auto &sn : pl->snaps)
+        CU(cudaMemcpyAsync(sn->live->p, sn->copy.p, sn->copy.bytes, cudaMemcpyDeviceToDevice, pl->stream));
+    for (DevBuf *b : pl->zero_at_run)
+        if (b->p && b->bytes) CU(cudaMemsetAsync(b->p, 0, b->bytes, pl->stream));
+    return BMM_OK;
+}
+
 int first_status(bmm_plan *pl, std::vector<int> &st) {
     st.assign(pl->C, 0);
     CU(cudaMemcpy(st.data(), pl->status.p, (size_t)pl->C * 4, cudaMemcpyDeviceToHost));
@@ -668,6 +819,10 @@ int first_status(bmm_plan *pl, std::vector<int> &st) {
 }
 
 }  // namespace
+
+namespace bmm {
+void set_last_error(const char *msg) { g_err = msg ? msg : ""; }
+}
 
 #pragma GCC visibility push(default)
 extern "C" {
@@ -717,25 +872,13 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
         const size_t eb = (size_t)pl->deb;
         const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
         cudaError_t e2 = cudaSuccess;
-        pl->pipelined = (args->flags & BMM_FLAG_PIPELINE) && widen && !pl->grid_path;
-        if (pl->pipelined) {
-            pl->CH = 64;
-            const size_t cb = (size_t)pl->C * pl->N * pl->CH;
-            for (int b = 0; b < 2 && e2 == cudaSuccess; ++b) {
-                e2 = pl->zc_orig[b].alloc(cb, false);
-                if (e2 == cudaSuccess && pl->relabel) e2 = pl->zc_rel[b].alloc(cb, false);
-                if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ck_done[b], cudaEventDisableTiming);
-                if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&pl->ck_copied[b], cudaEventDisableTiming);
-            }
-            if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking);
-        } else {
-            e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
-            if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
-        }
+        e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
+        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
         if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
     }
+    if (!rc) rc = snapshot_state(pl);
     if (!rc) { cudaError_t e3 = cudaDeviceSynchronize(); if (e3 != cudaSuccess) rc = fail(BMM_ERR_CUDA, cudaGetErrorString(e3)); }
-    if (rc) { delete pl; return rc; }
+    if (rc) { cudaDeviceSynchronize(); delete pl; return rc; }
     *plan = pl;
     return BMM_OK;
 }
@@ -744,6 +887,7 @@ int bmm_plan_run(bmm_plan *pl) {
     if (!pl) return fail(BMM_ERR_INVALID, "plan is NULL");
     CU(cudaSetDevice(pl->a.device));
     const int ns = pl->ns, burnin = pl->a.burnin;
+    if (pl->runs++ > 0) TRY(restore_state(pl));   // the first run starts from the freshly created state
     CU(cudaEventRecord(pl->ev0, pl->stream));
     CU(cudaEventRecord(pl->evk0, pl->stream));
     CU(cudaEventRecord(pl->evs[0], pl->stream));
@@ -800,12 +944,17 @@ int bmm_plan_kernel_ms(bmm_plan *pl, float ms_out[4]) {
     if (pl->grid_path) {
         // [0] sum of the sweep kernels, [1] everything else in the sweep loop (parameter kernels,
         // all-reduce), [2] 0, [3] history layout conversion
+        // (the sweep kernels bracketed by events -- every ev_stride-th -- scaled to all ns - 1 of them)
         float sweeps = 0.f, total = ms_out[0];
+        int timed = 0;
         for (int j = 1; j < pl->ns; ++j) {
+            if (pl->ev_stride <= 0 || (j % pl->ev_stride) != 0) continue;
             float t = 0.f;
             CU(cudaEventElapsedTime(&t, pl->sweep_ev[2 * j], pl->sweep_ev[2 * j + 1]));
             sweeps += t;
+            ++timed;
         }
+        sweeps = timed ? sweeps * (float)(pl->ns - 1) / (float)timed : 0.f;
         ms_out[0] = sweeps; ms_out[1] = total - sweeps; ms_out[2] = 0.f;
     }
     return BMM_OK;
@@ -906,80 +1055,13 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
 }
 
 int bmm_plan_destroy(bmm_plan *pl) {
-    if (pl) { cudaSetDevice(pl->a.device); delete pl; }
+    if (pl) {
+        // the blocks go back to the free list on delete: nothing of this plan may still be running on them
+        cudaSetDevice(pl->a.device);
+        if (pl->stream) cudaStreamSynchronize(pl->stream);
+        delete pl;
+    }
     return BMM_OK;
-}
-
-// One-shot call with the allocation matrices delivered while the chain still runs: the post-burn-in
-// sweeps go in chunks of CH; chunk k is transposed to [chain][observation][CH] bytes on the device,
-// DMA'd into pinned staging on a second stream and widened by the host workers into its slice of the
-// S x N column-major int32 matrices while chunk k+1 is being sampled.  The S x N matrices are >90 % of
-// the returned bytes, and widening them (host memory bandwidth) takes longer than the sampling.
-static int run_fetch_pipelined(bmm_plan *pl, bmm_out *out) {
-    CU(cudaSetDevice(pl->a.device));
-    const int ns = pl->ns, burnin = pl->a.burnin, S = pl->S, CH = pl->CH, K = pl->K;
-    const size_t C = pl->C, N = pl->N;
-    const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
-    static uint8_t *stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    static size_t stage_bytes = 0;
-    const size_t cb = C * N * CH;
-    if (cb > stage_bytes) {
-        for (auto &row : stage) for (auto &b : row) { if (b) cudaFreeHost(b); b = nullptr; }
-        for (auto &row : stage) for (auto &b : row) CU(cudaHostAlloc((void **)&b, cb, cudaHostAllocDefault));
-        stage_bytes = cb;
-    }
-    static const int threads = [] {
-        const char *e = getenv("BMM_FETCH_THREADS");
-        int ranks = 1;
-        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(lw) > 0 ? atoi(lw) : 1;
-        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / (2 * ranks);
-        return t < 1 ? 1 : (t > 8 && !e ? 8 : (t > 32 ? 32 : t));
-    }();
-    CU(cudaEventRecord(pl->ev0, pl->stream));
-    TRY(run_segment(pl, 1, burnin));
-    if (pl->relabel)
-        CU(bmm::launch_stephens_batch(pl->C, pl->U, K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
-                                      pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(), pl->logQ.as<double>(),
-                                      pl->sb_perm.as<int>(), pl->sb_cost.as<double>(), pl->sb_ws.as<char>(), pl->stream,
-                                      (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
-    const int nck = (S + CH - 1) / CH;
-    auto enqueue = [&](int k) -> int {
-        const int j0 = burnin + k * CH, cs = std::min(CH, ns - j0), b = k & 1;
-        if (k >= 2) CU(cudaStreamWaitEvent(pl->stream, pl->ck_copied[b], 0));
-        TRY(run_segment(pl, j0, j0 + cs));
-        CU(bmm::launch_finalize_chunk(pl->C, pl->N, ns, j0, cs, K, S, k * CH, pl->zhist.as<uint8_t>(),
-                                      pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->zc_orig[b].as<uint8_t>(),
-                                      pl->relabel ? pl->zc_rel[b].as<uint8_t>() : nullptr, pl->stream));
-        CU(cudaEventRecord(pl->ck_done[b], pl->stream));
-        return BMM_OK;
-    };
-    TRY(enqueue(0));
-    if (nck > 1) TRY(enqueue(1));
-    int32_t *dst_main = out->z, *dst_orig = pl->relabel ? out->z_original : nullptr;
-    for (int k = 0; k < nck; ++k) {
-        const int j0 = burnin + k * CH, cs = std::min(CH, ns - j0), b = k & 1;
-        const size_t bytes = C * N * cs;
-        CU(cudaStreamWaitEvent(pl->copy_stream, pl->ck_done[b], 0));
-        CU(cudaMemcpyAsync(stage[b][0], pl->zc_orig[b].p, bytes, cudaMemcpyDeviceToHost, pl->copy_stream));
-        if (pl->relabel) CU(cudaMemcpyAsync(stage[b][1], pl->zc_rel[b].p, bytes, cudaMemcpyDeviceToHost, pl->copy_stream));
-        CU(cudaEventRecord(pl->ck_copied[b], pl->copy_stream));
-        if (k + 2 < nck) TRY(enqueue(k + 2));
-        CU(cudaEventSynchronize(pl->ck_copied[b]));
-        if (pl->relabel) {
-            if (dst_main) bmm_widen_rows_u8_i32(stage[b][1], dst_main, C * N, cs, S, (size_t)k * CH, threads);
-            if (dst_orig) bmm_widen_rows_u8_i32(stage[b][0], dst_orig, C * N, cs, S, (size_t)k * CH, threads);
-        } else if (dst_main) {
-            bmm_widen_rows_u8_i32(stage[b][0], dst_main, C * N, cs, S, (size_t)k * CH, threads);
-        }
-    }
-    CU(cudaEventRecord(pl->ev1, pl->stream));
-    for (int e = 0; e < 5; ++e) CU(cudaEventRecord(pl->evs[e], pl->stream));
-    CU(cudaEventRecord(pl->evk0, pl->stream));
-    CU(cudaEventRecord(pl->evk1, pl->stream));
-    pl->ran = true;
-    bmm_out rest = *out;       // everything but the allocation matrices comes the ordinary way
-    rest.z = nullptr; rest.z_original = nullptr;
-    return bmm_plan_fetch(pl, &rest);
 }
 
 static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm_out *out) {
@@ -990,15 +1072,6 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     if (out->loglik) a.flags |= BMM_FLAG_PROBE_LOGLIK;
     if (out->counts) a.flags |= BMM_FLAG_PROBE_COUNTS;
     if (out->z_freq) a.flags |= BMM_FLAG_PROBE_ZFREQ;
-    {   // Overlapping sampling and download (run_fetch_pipelined) is OFF unless BMM_PIPELINE=1: chunking by
-        // sweeps makes the host write 256-byte pieces of every S x N column per chunk, and those scattered
-        // non-temporal stores ran at ~8 GB/s instead of ~120 GB/s (C2: 899 ms against 131 ms unpipelined).
-        const char *pe = getenv("BMM_PIPELINE");
-        const long long C = a.n_chains < 1 ? 1 : a.n_chains, S = (long long)a.nsamples - a.burnin;
-        if ((pe && pe[0] == '1') && out->z && !(a.flags & BMM_FLAG_COMPACT_Z) && !a.replay && S >= 256 &&
-            C * S * a.N >= ((long long)64 << 20) && !(a.relabel && !out->z_original))
-            a.flags |= BMM_FLAG_PIPELINE;
-    }
     bmm_plan *pl = nullptr;
     static const bool trace = getenv("BMM_TRACE") != nullptr;   // wall-clock phases of the one-shot call on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1006,16 +1079,10 @@ static int run_once(int sampler, const bmm_args *args, const bmm_init *init, bmm
     int rc = bmm_plan_create(sampler, &a, init, &pl);
     if (rc) return rc;
     const double t1 = now();
-    double t2;
-    if (pl->pipelined) {
-        rc = run_fetch_pipelined(pl, out);
-        t2 = t1;
-    } else {
-        rc = bmm_plan_run(pl);
-        if (!rc && trace) rc = bmm_plan_sync(pl);
-        t2 = now();
-        if (!rc) rc = bmm_plan_fetch(pl, out);
-    }
+    rc = bmm_plan_run(pl);
+    if (!rc && trace) rc = bmm_plan_sync(pl);
+    const double t2 = now();
+    if (!rc) rc = bmm_plan_fetch(pl, out);
     const double t3 = now();
     bmm_plan_destroy(pl);
     if (trace) fprintf(stderr, "bmm trace: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);

@@ -28,6 +28,7 @@ fn_errstr p_errstr = nullptr;
 ncclComm_t_ g_comm = nullptr;
 int g_rank = 0, g_world = 1;
 std::string g_derr;
+void derr(const std::string &m) { g_derr = m; set_last_error(m.c_str()); }
 
 bool load_nccl() {
     if (g_h) return true;
@@ -36,13 +37,13 @@ bool load_nccl() {
         g_h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (g_h) break;
     }
-    if (!g_h) { g_derr = "cannot dlopen libnccl.so.2"; return false; }
+    if (!g_h) { derr("cannot dlopen libnccl.so.2"); return false; }
     p_getid = (fn_getid)dlsym(g_h, "ncclGetUniqueId");
     p_init = (fn_init)dlsym(g_h, "ncclCommInitRank");
     p_destroy = (fn_destroy)dlsym(g_h, "ncclCommDestroy");
     p_allreduce = (fn_allreduce)dlsym(g_h, "ncclAllReduce");
     p_errstr = (fn_errstr)dlsym(g_h, "ncclGetErrorString");
-    if (!p_getid || !p_init || !p_destroy || !p_allreduce) { g_derr = "libnccl lacks expected symbols"; return false; }
+    if (!p_getid || !p_init || !p_destroy || !p_allreduce) { derr("libnccl lacks expected symbols"); return false; }
     return true;
 }
 }  // namespace
@@ -54,89 +55,85 @@ const char *dist_error() { return g_derr.c_str(); }
 // sum-all-reduce of int32 (dtype 2 = ncclInt32, op 0 = ncclSum) in place on `st`
 int dist_allreduce_i32(int *buf, size_t n, cudaStream_t st) {
     if (g_world == 1) return 0;
-    if (!g_comm) { g_derr = "bmm_dist_init has not been called"; return -1; }
+    if (!g_comm) { derr("bmm_dist_init has not been called"); return -1; }
     int rc = p_allreduce(buf, buf, n, 2, 0, g_comm, st);
-    if (rc) { g_derr = std::string("ncclAllReduce: ") + (p_errstr ? p_errstr(rc) : "error"); return -1; }
+    if (rc) { derr(std::string("ncclAllReduce: ") + (p_errstr ? p_errstr(rc) : "error")); return -1; }
     return 0;
 }
 // double (dtype 8 = ncclFloat64)
 int dist_allreduce_f64(double *buf, size_t n, cudaStream_t st) {
     if (g_world == 1) return 0;
-    if (!g_comm) { g_derr = "bmm_dist_init has not been called"; return -1; }
+    if (!g_comm) { derr("bmm_dist_init has not been called"); return -1; }
     int rc = p_allreduce(buf, buf, n, 8, 0, g_comm, st);
-    if (rc) { g_derr = std::string("ncclAllReduce: ") + (p_errstr ? p_errstr(rc) : "error"); return -1; }
+    if (rc) { derr(std::string("ncclAllReduce: ") + (p_errstr ? p_errstr(rc) : "error")); return -1; }
     return 0;
 }
 
 
-// ---- one-shot all-reduce over NVLink peer memory ------------------------------------------------------
-// The per-sweep exchange is a few KB of int32 counts: latency-bound, and an NCCL call costs ~25 us of
-// the ~70 us sweep at 8 GPUs.  Every rank owns an inbox [2 parities][world][cap] ints plus flags
-// [2][world] in one cudaMalloc'ed block that the peers map through CUDA IPC.  After its sweep a rank
-// PUSHES its counts into slot `rank` of every peer's inbox (remote stores), fences, and writes the sweep
-// number into the peer's flag; the gather kernel of each rank spins on its LOCAL flags and sums its
-// local inbox.  Parity double-buffering is enough: a rank cannot publish sweep j+2 before it has
-// received every peer's sweep j+1, which those peers only send after they consumed sweep j.
+// ---- count exchange over NVLink peer memory ----------------------------------------------------------
+// The per-sweep exchange is a few KB of int32 counts: latency-bound.  Every rank owns an inbox
+// [2 parities][world][cap] ints plus flags [2][world] in one cudaMalloc'ed block that the peers map through
+// CUDA IPC.  After its sweep a rank PUSHES its counts into slot `rank` of every rank's inbox (remote stores
+// over NVLink, its own slot included), fences at system scope and writes the exchange number into the
+// flag; the consumer (big_update_kernel) spins on its LOCAL flags with acquire loads and sums the slots it
+// needs.  There is no separate gather launch and, on the warp-specialised tensor path, no publish launch
+// either: the last CTA of the sweep kernel to flush its counts does the push (kern_big_ws.cu).
+// Parity double-buffering is enough: a rank cannot publish exchange s+2 before it has received every
+// peer's s+1, which those peers only send after they consumed s.
+// Exchange numbers come from a device-side counter so that a captured CUDA graph replays with fresh
+// numbers: seq[0] = number of sweep 0 of the current run, seq[1] = next free number.
 namespace {
 struct P2P {
     int *local = nullptr;            // this rank's block
     int *peer[64] = {nullptr};       // peer[r] = rank r's block mapped here (peer[rank] = local)
     int **peer_dev = nullptr;        // device copy of peer[]
+    int *seq = nullptr;              // device: [0] base of the current run, [1] next free exchange number
     size_t cap = 0;                  // ints per (parity, source) slot
     bool attached = false;
 } g_p2p;
 
 __host__ __device__ inline size_t p2p_block_ints(size_t cap, int world) { return 2 * (size_t)world * cap + 2 * (size_t)world; }
 
-__global__ void p2p_publish_kernel(int **peer, const int *counts, size_t n, size_t cap, int world, int rank, int parity,
-                                   int sweep) {
+__global__ void p2p_begin_run_kernel(int *seq, int n) {
+    seq[0] = seq[1];
+    seq[1] += n;
+}
+
+// generic publish (sweep kernels without a fused push): block r pushes to rank r
+__global__ void p2p_publish_kernel(int *const *peer, const int *counts, size_t n, size_t cap, int world, int rank,
+                                   const int *seq, int j) {
+    const int s = seq[0] + j, parity = s & 1;
     int *dst_block = peer[blockIdx.x];
     int *dst = dst_block + ((size_t)parity * world + rank) * cap;
     for (size_t e = threadIdx.x; e < n; e += blockDim.x) dst[e] = counts[e];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile int *flag = dst_block + 2 * (size_t)world * cap + (size_t)parity * world + rank;
-        *flag = sweep;
-        __threadfence_system();
-    }
-}
-
-__global__ void p2p_gather_kernel(const int *local, int *counts, size_t n, size_t cap, int world, int parity, int sweep,
-                                  int *status) {
-    __shared__ int ok_sh;
-    if (threadIdx.x == 0) ok_sh = 1;
-    __syncthreads();
-    if (threadIdx.x < world) {
-        const volatile int *flag = local + 2 * (size_t)world * cap + (size_t)parity * world + threadIdx.x;
-        long long spins = 0;
-        while (*flag != sweep) {
-            if (++spins > (1ll << 26)) { ok_sh = 0; break; }   // a peer never published: do not hang the GPU
-        }
-    }
-    __syncthreads();
-    if (!ok_sh) { if (threadIdx.x == 0) *status = -7; return; }   // BMM_ERR_NCCL: exchange failed
-    __threadfence_system();
-    const int *in = local + (size_t)parity * world * cap;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        int acc = 0;
-        for (int r = 0; r < world; ++r) acc += ((const volatile int *)in)[(size_t)r * cap + e];
-        counts[e] = acc;
+        int *flag = dst_block + 2 * (size_t)world * cap + (size_t)parity * world + rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(flag), "r"(s) : "memory");
     }
 }
 }  // namespace
 
 bool dist_p2p_ready(size_t n) { return g_p2p.attached && n <= g_p2p.cap && g_world > 1 && g_world <= 64; }
 
-// sum-all-reduce of int32 counts in place.  Every rank makes the same sequence of calls, so a per-process
-// call counter is a consistent exchange number; consecutive exchanges alternate the inbox parity.
-int dist_p2p_allreduce_i32(int *buf, size_t n, int *status, cudaStream_t st) {
-    static int seq = 0;
-    const int sweep = ++seq, parity = sweep & 1;
-    p2p_publish_kernel<<<g_world, 256, 0, st>>>(g_p2p.peer_dev, buf, n, g_p2p.cap, g_world, g_rank, parity, sweep);
-    const int blocks = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
-    p2p_gather_kernel<<<blocks, 256, 0, st>>>(g_p2p.local, buf, n, g_p2p.cap, g_world, parity, sweep, status);
-    if (cudaGetLastError() != cudaSuccess) { g_derr = "p2p all-reduce launch failed"; return -1; }
+P2PView dist_p2p_view() {
+    P2PView v;
+    v.peer = g_p2p.peer_dev; v.local = g_p2p.local; v.seq = g_p2p.seq; v.cap = g_p2p.cap;
+    v.world = g_world; v.rank = g_rank;
+    return v;
+}
+
+// reserve the exchange numbers of a run of n sweeps (stream-ordered; every rank makes the same calls)
+int dist_p2p_begin_run(int n, cudaStream_t st) {
+    p2p_begin_run_kernel<<<1, 1, 0, st>>>(g_p2p.seq, n);
+    if (cudaGetLastError() != cudaSuccess) { derr("p2p begin_run launch failed"); return -1; }
+    return 0;
+}
+
+int dist_p2p_publish(const int *counts, size_t n, int j, cudaStream_t st) {
+    p2p_publish_kernel<<<g_world, 256, 0, st>>>(g_p2p.peer_dev, counts, n, g_p2p.cap, g_world, g_rank, g_p2p.seq, j);
+    if (cudaGetLastError() != cudaSuccess) { derr("p2p publish launch failed"); return -1; }
     return 0;
 }
 
@@ -149,7 +146,7 @@ int bmm_dist_unique_id(uint8_t id_out[128]) {
     if (!id_out) return BMM_ERR_INVALID;
     if (!bmm::load_nccl()) return BMM_ERR_NCCL;
     bmm::ncclUniqueId_t id;
-    if (bmm::p_getid(&id)) { bmm::g_derr = "ncclGetUniqueId failed"; return BMM_ERR_NCCL; }
+    if (bmm::p_getid(&id)) { bmm::derr("ncclGetUniqueId failed"); return BMM_ERR_NCCL; }
     memcpy(id_out, id.internal, 128);
     return BMM_OK;
 }
@@ -164,7 +161,7 @@ int bmm_dist_init(int32_t rank, int32_t world, const uint8_t id[128], int32_t de
     bmm::ncclUniqueId_t uid;
     memcpy(uid.internal, id, 128);
     int rc = bmm::p_init(&bmm::g_comm, world, uid, rank);
-    if (rc) { bmm::g_derr = std::string("ncclCommInitRank: ") + (bmm::p_errstr ? bmm::p_errstr(rc) : "error"); return BMM_ERR_NCCL; }
+    if (rc) { bmm::derr(std::string("ncclCommInitRank: ") + (bmm::p_errstr ? bmm::p_errstr(rc) : "error")); return BMM_ERR_NCCL; }
     return BMM_OK;
 }
 
@@ -173,11 +170,14 @@ int bmm_dist_p2p_local(uint64_t cap_ints, uint8_t handle_out[64]) {
     if (!handle_out || cap_ints == 0 || g_world < 2 || g_world > 64) return BMM_ERR_INVALID;
     if (g_p2p.local) return BMM_ERR_INVALID;
     const size_t ints = p2p_block_ints(cap_ints, g_world);
-    if (cudaMalloc((void **)&g_p2p.local, ints * sizeof(int)) != cudaSuccess) { g_derr = "p2p: cudaMalloc failed"; return BMM_ERR_CUDA; }
+    if (cudaMalloc((void **)&g_p2p.local, ints * sizeof(int)) != cudaSuccess) { derr("p2p: cudaMalloc failed"); return BMM_ERR_CUDA; }
     cudaMemset(g_p2p.local, 0xFF, ints * sizeof(int));     // flags = -1: no sweep published yet
+    if (cudaMalloc((void **)&g_p2p.seq, 2 * sizeof(int)) != cudaSuccess) { derr("p2p: cudaMalloc failed"); return BMM_ERR_CUDA; }
+    const int seq0[2] = {1, 1};
+    cudaMemcpy(g_p2p.seq, seq0, sizeof seq0, cudaMemcpyHostToDevice);
     cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
-    if (cudaIpcGetMemHandle(&h, g_p2p.local) != cudaSuccess) { g_derr = "p2p: cudaIpcGetMemHandle failed"; cudaGetLastError(); return BMM_ERR_CUDA; }
+    if (cudaIpcGetMemHandle(&h, g_p2p.local) != cudaSuccess) { derr("p2p: cudaIpcGetMemHandle failed"); cudaGetLastError(); return BMM_ERR_CUDA; }
     static_assert(sizeof(h) == 64, "CUDA IPC handle size");
     memcpy(handle_out, &h, 64);
     g_p2p.cap = cap_ints;
@@ -193,7 +193,7 @@ int bmm_dist_p2p_attach(const uint8_t *handles) {
         memcpy(&h, handles + (size_t)r * 64, 64);
         void *ptr = nullptr;
         if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            g_derr = "p2p: cudaIpcOpenMemHandle failed (no peer access between the devices?)";
+            derr("p2p: cudaIpcOpenMemHandle failed (no peer access between the devices?)");
             cudaGetLastError();
             return BMM_ERR_CUDA;
         }
@@ -216,6 +216,7 @@ int bmm_dist_finalize(void) {
         for (int r = 0; r < bmm::g_world; ++r)
             if (r != bmm::g_rank && bmm::g_p2p.peer[r]) cudaIpcCloseMemHandle(bmm::g_p2p.peer[r]);
         if (bmm::g_p2p.peer_dev) cudaFree(bmm::g_p2p.peer_dev);
+        if (bmm::g_p2p.seq) cudaFree(bmm::g_p2p.seq);
         cudaFree(bmm::g_p2p.local);
         bmm::g_p2p = bmm::P2P{};
     }

@@ -28,11 +28,6 @@ void widen_range(const uint8_t *src, int32_t *dst, size_t n) {
     for (; i < n; ++i) dst[i] = src[i];
 }
 
-// rows of `cs` bytes -> dst[row * stride + off .. + cs) as int32 (a chunk of sweeps of every S x N column)
-void widen_rows(const uint8_t *src, int32_t *dst, size_t row_lo, size_t row_hi, size_t cs, size_t stride, size_t off) {
-    for (size_t r = row_lo; r < row_hi; ++r) widen_range(src + r * cs, dst + r * stride + off, cs);
-}
-
 // Persistent workers: creating threads per 32 MB chunk cost more than the widening itself.
 class Pool {
 public:
@@ -44,9 +39,9 @@ public:
         cv_.notify_all();
         for (auto &w : workers_) w.join();
     }
-    void run(const uint8_t *src, int32_t *dst, size_t n, size_t cs = 0, size_t stride = 0, size_t off = 0) {
+    void run(const uint8_t *src, int32_t *dst, size_t n) {
         std::unique_lock<std::mutex> g(m_);
-        src_ = src; dst_ = dst; count_ = n; cs_ = cs; stride_ = stride; off_ = off; pending_ = n_; ++gen_;
+        src_ = src; dst_ = dst; count_ = n; pending_ = n_; ++gen_;
         cv_.notify_all();
         done_.wait(g, [this] { return pending_ == 0; });
     }
@@ -56,21 +51,16 @@ private:
     void loop(int t) {
         unsigned long seen = 0;
         for (;;) {
-            const uint8_t *src; int32_t *dst; size_t n, cs, stride, off;
+            const uint8_t *src; int32_t *dst; size_t n;
             {
                 std::unique_lock<std::mutex> g(m_);
                 cv_.wait(g, [&] { return gen_ != seen; });
                 seen = gen_;
                 if (stop_) return;
-                src = src_; dst = dst_; n = count_; cs = cs_; stride = stride_; off = off_;
+                src = src_; dst = dst_; n = count_;
             }
-            if (cs == 0) {       // flat: n bytes
-                const size_t per = ((n + n_ - 1) / n_ + 63) & ~(size_t)63, lo = (size_t)t * per;
-                if (lo < n) widen_range(src + lo, dst + lo, lo + per <= n ? per : n - lo);
-            } else {             // n rows of cs bytes into strided rows
-                const size_t per = (n + n_ - 1) / n_, lo = (size_t)t * per;
-                if (lo < n) widen_rows(src, dst, lo, lo + per <= n ? lo + per : n, cs, stride, off);
-            }
+            const size_t per = ((n + n_ - 1) / n_ + 63) & ~(size_t)63, lo = (size_t)t * per;
+            if (lo < n) widen_range(src + lo, dst + lo, lo + per <= n ? per : n - lo);
             {
                 std::lock_guard<std::mutex> g(m_);
                 if (--pending_ == 0) done_.notify_one();
@@ -81,7 +71,7 @@ private:
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_;
-    const uint8_t *src_ = nullptr; int32_t *dst_ = nullptr; size_t count_ = 0, cs_ = 0, stride_ = 0, off_ = 0;
+    const uint8_t *src_ = nullptr; int32_t *dst_ = nullptr; size_t count_ = 0;
     int pending_ = 0; unsigned long gen_ = 0; bool stop_ = false;
 };
 
@@ -96,14 +86,4 @@ extern "C" __attribute__((visibility("default"))) void bmm_widen_u8_i32(const ui
     std::lock_guard<std::mutex> g(pool_m);
     if (!pool || pool->size() != threads) { delete pool; pool = new Pool(threads); }
     pool->run(src, dst, n);
-}
-
-// rows x cs bytes (contiguous) -> dst[r * stride + off + s] = src[r * cs + s]
-extern "C" __attribute__((visibility("default"))) void bmm_widen_rows_u8_i32(const uint8_t *src, int32_t *dst, size_t rows, size_t cs,
-                                                                             size_t stride, size_t off, int threads) {
-    if (threads < 1) threads = 1;
-    if (threads == 1 || rows * cs < (1u << 20)) { widen_rows(src, dst, 0, rows, cs, stride, off); return; }
-    std::lock_guard<std::mutex> g(pool_m);
-    if (!pool || pool->size() != threads) { delete pool; pool = new Pool(threads); }
-    pool->run(src, dst, rows, cs, stride, off);
 }

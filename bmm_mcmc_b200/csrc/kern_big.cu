@@ -26,6 +26,7 @@
 
 #include "kernels.h"
 #include "common.cuh"
+#include "ws_table.cuh"
 
 namespace bmm {
 namespace {
@@ -157,94 +158,166 @@ __global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams 
     }
 }
 
-// One thread per parameter: gamma / stick draws for t < K, theta draws for t >= K.
-__global__ void big_param_kernel(const BigParams p, const int j) {
-    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples;
-    const int *cnt = p.counts + (size_t)(j & 1) * (K + KP);
-    const uint32_t chain = (uint32_t)p.chain_offset;
-    const double alpha_prev = *p.alpha_cur;
-    const bool replay = p.rtheta != nullptr;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + KP; t += gridDim.x * blockDim.x) {
-        if (t < K) {
-            if (replay) continue;
-            if (!p.stickbreaking) {  // Dirichlet via K Gamma(alpha/K + c_k, 1) (full_gibbs.cpp:202-210)
-                Stream st(p.seed, chain, (uint32_t)j, ST_PI, (uint32_t)t);
-                p.gsc[t] = st.gamma(alpha_prev / K + cnt[t]);
-            } else {                 // v_k ~ Beta(1 + c_k, alpha + sum_{l>k} c_l) (stickbreaking.cpp:187-193)
-                long long later = 0;
-                for (int l = t + 1; l < K; ++l) later += cnt[l];
-                Stream st(p.seed, chain, (uint32_t)j, ST_STICK, (uint32_t)t);
-                p.gsc[t] = st.beta(1.0 + cnt[t], alpha_prev + (double)later);
-            }
-        } else {                     // theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) (full_gibbs.cpp:213-225)
-            const int e = t - K, k = e % K, d = e / K;
-            double th;
-            if (replay) th = p.rtheta[(size_t)KP * j + e];
-            else {
-                Stream st(p.seed, chain, (uint32_t)j, ST_THETA, (uint32_t)(k * P + d));
-                th = st.beta(p.beta + cnt[K + e], p.gamma + cnt[k] - cnt[K + e]);
-            }
-            p.theta_cur[e] = th;
-            p.w1[e] = log(th);
-            p.w0[e] = log(1 - th);
-            if (p.theta_out && j >= p.burnin) p.theta_out[(size_t)KP * (j - p.burnin) + e] = th;
-            if (p.theta_rel_out && j >= p.burnin)   // theta_rel[perm[k], :] = theta[k, :] (full_gibbs.cpp:221-223)
-                p.theta_rel_out[(size_t)KP * (j - p.burnin) + p.perm_cur[k] + (size_t)K * d] = th;
-        }
-    }
-    (void)ns;
+constexpr int UPD_THREADS = 256;
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-// One block: pi, alpha, log pi, history rows; zero the next sweep's count buffer.
-__global__ void big_finish_kernel(const BigParams p, const int j) {
+// One launch per sweep, after the z-sweep: blocks 0..K-1 own one cluster each (theta_k., its log tables and, for
+// the tensor path, row k of the operand image), block K draws pi / sticks / alpha, writes the history rows and
+// zeroes the next sweep's count buffer.  On an N-sharded run over peer memory every block first waits for the
+// counts of all ranks (acquire-polling the flags in this rank's own inbox) and sums the slots it needs; the
+// reduced values are integers, and every draw is keyed by its parameter index, so all ranks compute identical
+// tables without a broadcast (full_gibbs.cpp:182-230, stickbreaking.cpp:164-235, utils.cpp:6-14).
+__global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams p, const int j) {
     __shared__ double red[32];
     __shared__ double ag[4];
+    __shared__ double sh_w0[128];
+    __shared__ int sh_c[256];
+    __shared__ int sh_ok;
     const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = ns - p.burnin, tid = threadIdx.x;
+    const int blk = blockIdx.x;
     const bool replay = p.rtheta != nullptr;
+    int *cur = p.counts + (size_t)(j & 1) * (K + KP);
+    const uint32_t chain = (uint32_t)p.chain_offset;
     const double alpha_prev = *p.alpha_cur;
+    const int world = p.x_world > 1 ? p.x_world : 1;
+    const int *slots = nullptr;          // [world][cap] of this exchange when the counts come from the inbox
+    if (world > 1) {
+        const int s = p.x_seq[0] + j;
+        if (tid == 0) sh_ok = 1;
+        __syncthreads();
+        if (tid < world) {
+            const int *flag = p.x_local + x_flag_off(s, world, tid, (size_t)p.x_cap);
+            // a peer that never publishes must not hang the GPU: give up after 20 s of wall time
+            unsigned long long t0 = 0, t1;
+            unsigned spins = 0;
+            while (ld_acquire_sys(flag) != s) {
+                if ((++spins & 1023u) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (!t0) t0 = t1;
+                    else if (t1 - t0 > 20000000000ull) { sh_ok = 0; break; }
+                }
+            }
+        }
+        __syncthreads();
+        if (!sh_ok && tid == 0) *p.status = -7;   // BMM_ERR_NCCL: exchange failed
+        slots = p.x_local + x_slot_off(s, world, 0, (size_t)p.x_cap);
+    }
+    auto count_of = [&](int e) -> int {       // reduced count e (c_k for e < K, V_kd at K + k + K d)
+        if (!slots) return cur[e];
+        int acc = 0;
+        for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * p.x_cap + e);
+        return acc;
+    };
+
+    if (blk < K) {
+        // ---------------- cluster block: theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) ----------------
+        const int k = blk;
+        const int ck = count_of(k);
+        for (int d0 = 0; d0 < P; d0 += UPD_THREADS) {
+            const int d = d0 + tid;
+            if (d < P) {
+                const int e = k + K * d;
+                const int v = count_of(K + e);
+                double th;
+                if (replay) th = p.rtheta[(size_t)KP * j + e];
+                else {
+                    Stream st(p.seed, chain, (uint32_t)j, ST_THETA, (uint32_t)(k * P + d));
+                    th = st.beta(p.beta + v, p.gamma + ck - v);
+                }
+                const double l1 = log(th), l0 = log(1 - th);
+                p.theta_cur[e] = th;
+                p.w1[e] = l1;
+                p.w0[e] = l0;
+                if (p.theta_out && j >= p.burnin) p.theta_out[(size_t)KP * (j - p.burnin) + e] = th;
+                if (p.theta_rel_out && j >= p.burnin)   // theta_rel[perm[k], :] = theta[k, :] (full_gibbs.cpp:221-223)
+                    p.theta_rel_out[(size_t)KP * (j - p.burnin) + p.perm_cur[k] + (size_t)K * d] = th;
+                if (p.ws_b1) {
+                    ws_store_cell(p.ws_b1, k, d, l1, l0);
+                    sh_w0[d] = l0;
+                }
+            }
+        }
+        if (p.ws_b1) {      // s0_k in a fixed order (every rank must get the same bits)
+            __syncthreads();
+            if (tid < 32) {
+                double a = 0.0;
+                for (int d = tid; d < P; d += 32) a += sh_w0[d];
+                a = warp_sum_xor(a, 32);
+                if (tid == 0) p.ws_s0[k] = a;
+            }
+        }
+        return;
+    }
+
+    // ---------------- last block: pi, alpha, log pi, history rows; zero the next sweep's count buffer ----------------
     int *next = p.counts + (size_t)((j + 1) & 1) * (K + KP);
     for (int t = tid; t < K + KP; t += blockDim.x) next[t] = 0;
-    if (p.counts_out) {
-        const int *cur = p.counts + (size_t)(j & 1) * (K + KP);
-        for (int t = tid; t < K + KP; t += blockDim.x) p.counts_out[(size_t)j * (K + KP) + t] = cur[t];
-    }
+    if (p.counts_out)
+        for (int t = tid; t < K + KP; t += blockDim.x) p.counts_out[(size_t)j * (K + KP) + t] = count_of(t);
     if (replay) {
         for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.rpi[j + (size_t)ns * k];
         __syncthreads();
         if (tid == 0) *p.alpha_cur = p.ralpha[j];
-    } else if (!p.stickbreaking) {
-        double part = 0.0;
-        for (int k = tid; k < K; k += blockDim.x) part += p.gsc[k];
-        part = warp_sum_xor(part, 32);
-        if ((tid & 31) == 0) red[tid >> 5] = part;
+    } else {
+        for (int t = tid; t < K; t += blockDim.x) sh_c[t] = count_of(t);
         __syncthreads();
-        double sum = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
-        for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.gsc[k] / sum;
-        if (p.alpha0 == 0.0) {          // the four Gamma substreams of the alpha update, one thread each
-            if (tid < 4) {
-                Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, (uint32_t)tid);
-                ag[tid] = st.gamma(alpha_gamma_shape(tid, alpha_prev, p.a, (int)p.N_global, K));
+        for (int t = tid; t < K; t += blockDim.x) {
+            if (!p.stickbreaking) {  // Dirichlet via K Gamma(alpha/K + c_k, 1) (full_gibbs.cpp:202-210)
+                Stream st(p.seed, chain, (uint32_t)j, ST_PI, (uint32_t)t);
+                p.gsc[t] = st.gamma(alpha_prev / K + sh_c[t]);
+            } else {                 // v_k ~ Beta(1 + c_k, alpha + sum_{l>k} c_l) (stickbreaking.cpp:187-193)
+                long long later = 0;
+                for (int l = t + 1; l < K; ++l) later += sh_c[l];
+                Stream st(p.seed, chain, (uint32_t)j, ST_STICK, (uint32_t)t);
+                p.gsc[t] = st.beta(1.0 + sh_c[t], alpha_prev + (double)later);
+            }
+        }
+        __syncthreads();
+        if (!p.stickbreaking) {
+            double part = 0.0;
+            for (int k = tid; k < K; k += blockDim.x) part += p.gsc[k];
+            part = warp_sum_xor(part, 32);
+            if ((tid & 31) == 0) red[tid >> 5] = part;
+            __syncthreads();
+            double sum = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+            for (int k = tid; k < K; k += blockDim.x) p.pi_cur[k] = p.gsc[k] / sum;
+            if (p.alpha0 == 0.0) {          // the four Gamma substreams of the alpha update, one thread each
+                if (tid < 4) {
+                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)tid);
+                    ag[tid] = st.gamma(alpha_gamma_shape(tid, alpha_prev, p.a, (int)p.N_global, K));
+                }
+                __syncthreads();
+                if (tid == 0) *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, K);
+            }
+        } else {                         // stick-breaking weights (stickbreaking.cpp:195-214)
+            __shared__ int kv_sh;
+            if (tid == 0) {
+                p.gsc[K - 1] = 1.0;
+                int K_viable = 0;
+                double cumprod = 1.0;
+                for (int k = 0; k < K; ++k) {
+                    const double pk = (k == 0) ? p.gsc[0] : cumprod * p.gsc[k];
+                    p.pi_cur[k] = pk;
+                    if (pk > 0.01) K_viable++;
+                    cumprod *= (1 - p.gsc[k]);
+                }
+                kv_sh = K_viable;
             }
             __syncthreads();
-            if (tid == 0) *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, K);
-        }
-    } else if (tid == 0) {           // stick-breaking weights (stickbreaking.cpp:195-214)
-        p.gsc[K - 1] = 1.0;
-        int K_viable = 0;
-        double cumprod = 1.0;
-        for (int k = 0; k < K; ++k) {
-            const double pk = (k == 0) ? p.gsc[0] : cumprod * p.gsc[k];
-            p.pi_cur[k] = pk;
-            if (pk > 0.01) K_viable++;
-            cumprod *= (1 - p.gsc[k]);
-        }
-        if (p.alpha0 == 0.0) {
-            for (int q = 0; q < 4; ++q) {
-                Stream st(p.seed, (uint32_t)p.chain_offset, (uint32_t)j, ST_ALPHA, (uint32_t)q);
-                ag[q] = st.gamma(alpha_gamma_shape(q, alpha_prev, p.a, (int)p.N_global, K_viable));
+            if (p.alpha0 == 0.0) {
+                if (tid < 4) {
+                    Stream st(p.seed, chain, (uint32_t)j, ST_ALPHA, (uint32_t)tid);
+                    ag[tid] = st.gamma(alpha_gamma_shape(tid, alpha_prev, p.a, (int)p.N_global, kv_sh));
+                }
+                __syncthreads();
+                if (tid == 0) *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, kv_sh);
             }
-            *p.alpha_cur = alpha_combine(ag, p.a, p.b, (int)p.N_global, K_viable);
         }
     }
     __syncthreads();
@@ -254,7 +327,19 @@ __global__ void big_finish_kernel(const BigParams p, const int j) {
         if (p.pi_out && j >= p.burnin) p.pi_out[(j - p.burnin) + (size_t)S * k] = pk;
     }
     if (tid == 0 && p.alpha_out && j >= p.burnin) p.alpha_out[j - p.burnin] = *p.alpha_cur;
-    (void)P;
+}
+
+// operand image of the initial tables (sweep 1 reads theta_0); later sweeps get it from big_update_kernel
+__global__ void ws_table_kernel(const BigParams p) {
+    const int K = p.K, P = p.P;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < K * P; e += gridDim.x * blockDim.x)
+        ws_store_cell(p.ws_b1, e % K, e / K, p.w1[e], p.w0[e]);
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {   // any fixed order: this launch happens once per run
+            double a = 0.0;
+            for (int d = 0; d < P; ++d) a += p.w0[k + K * d];
+            p.ws_s0[k] = a;
+        }
 }
 
 // Log tables of the initial state (sweep 1 reads theta_0, pi_0); iteration 0 of the histories.
@@ -341,8 +426,7 @@ cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st) {
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     static const bool no_tc = getenv("BMM_NO_TC") != nullptr;  // A/B switch: CUDA-core float path
     if (!no_tc && !(p.flags & 32u /* BMM_FLAG_NO_TENSOR */)) {
-        static const bool no_ws = getenv("BMM_TC_WS") && getenv("BMM_TC_WS")[0] == '0';   // A/B: single-role kernel
-        if (big_tc_supported(p)) return no_ws ? launch_big_sweep_tc(p, j, sm_count, st) : launch_big_sweep_ws(p, j, sm_count, st);
+        if (big_tc_supported(p)) return launch_big_sweep_ws(p, j, sm_count, st);
         if (big_lp_supported(p)) return launch_big_sweep_lp(p, j, sm_count, st);
     }
     long long blocks = ((long long)p.N_local + BIG_THREADS - 1) / BIG_THREADS;
@@ -357,12 +441,14 @@ cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream
 }
 
 cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st) {
-    const int n = p.K + p.K * p.P;
-    big_param_kernel<<<min(1184, (n + 127) / 128), 128, 0, st>>>(p, j);
+    big_update_kernel<<<p.K + 1, UPD_THREADS, 0, st>>>(p, j);
     g_launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    big_finish_kernel<<<1, 256, 0, st>>>(p, j);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st) {
+    if (!p.ws_b1) return cudaSuccess;
+    ws_table_kernel<<<16, 256, 0, st>>>(p);
     g_launches++;
     return cudaGetLastError();
 }

@@ -252,12 +252,8 @@ bool grid_cost_tc_supported(long long N, int K) { return K >= 8 && K <= 128 && (
 // acc must be zero on entry
 cudaError_t launch_grid_cost_tc(long long N, int K, const float *P, const float *Q, int use_logp, double *acc, int *status,
                                 int sm_count, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(grid_cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static FuncAttrCache attr;
+    if (cudaError_t e = attr.ensure_smem(grid_cost_tc_kernel, CT_SMEM)) return e;
     const int fold = (128 % K) == 0 ? 128 / K : 1;
     const long long nst = ((N + fold - 1) / fold + CT_ROWS - 1) / CT_ROWS;
     const int grid = (int)(nst < sm_count ? nst : sm_count);

@@ -1,5 +1,5 @@
 // Large-P / large-K tensor-core path of the grid sampler (BASELINE config C5: N = 1e6, P = 4096,
-// K = 128).  Same algebra as kern_big_tc.cu -- loglh = X D^T + b on tcgen05 with D split into two
+// K = 128).  Same algebra as kern_big_ws.cu -- loglh = X D^T + b on tcgen05 with D split into two
 // fp16 terms, sufficient statistics as [X]^T onehot(z) -- but P no longer fits one shared-memory tile,
 // so the contraction runs as a pipelined k-loop and the statistics as a second kernel:
 //
@@ -324,12 +324,8 @@ bool big_lp_supported(const BigParams &p) {
 size_t big_lp_table_bytes(int P) { return (size_t)((P + LP_DK - 1) / LP_DK * LP_DK) / 8 * LP_NCOL * 16; }
 
 cudaError_t launch_big_sweep_lp(const BigParams &p, int j, int sm_count, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(lp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LpSmem::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static FuncAttrCache attr;
+    if (cudaError_t e = attr.ensure_smem(lp_sweep_kernel, (int)LpSmem::TOTAL)) return e;
     lp_table_kernel<<<(p.P + 63) / 64, 64, 0, st>>>(p);   // one thread per (padded) feature
     lp_bias_kernel<<<LP_KC, 128, 0, st>>>(p);
     const long long ntiles = ((long long)p.N_local + LP_ROWT - 1) / LP_ROWT;

@@ -357,12 +357,8 @@ cudaError_t launch_grid_assign(int K, double *acc, char *ws, int *perm_cur, int 
     const size_t wsb = ((size_t)(K + 1) * sizeof(double) + 15) & ~(size_t)15, costb = (size_t)K * K * sizeof(double);
     const int in_smem = wsb + costb <= 200 * 1024;
     const size_t smem = wsb + (in_smem ? costb : 0);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(grid_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = smem;
-    }
+    static FuncAttrCache attr;
+    if (cudaError_t e = attr.ensure_smem(grid_assign_kernel, (int)smem)) return e;
     grid_assign_kernel<<<1, 32, smem, st>>>(K, acc, in_smem, perm_cur, perm_dst, perm_stride, changed);
     g_launches++;
     return cudaGetLastError();

@@ -1,9 +1,8 @@
-// Warp-specialised tensor-core z-sweep for K <= 32, P <= 112 (BASELINE config C4): the same two
-// contractions as kern_big_tc.cu (loglh = X D^T on tcgen05; counts = [X|1]^T onehot(z)), but the work
-// of one 128-observation tile is split over dedicated warps connected by mbarrier rings, so the bit
-// expansion, the tensor pipe and the per-observation epilogue run concurrently instead of in lockstep
-// (the ncu profile of the single-role kernel showed its four warpgroups convoying: ALU phase and
-// tensor phase of a round did not overlap).
+// Warp-specialised tensor-core z-sweep for K <= 32, P <= 112 (BASELINE config C4): two contractions on
+// tcgen05 (loglh = X D^T; counts = [X|1]^T onehot(z)), with the work of one 128-observation tile split
+// over dedicated warps connected by mbarrier rings, so the bit expansion, the tensor pipe and the
+// per-observation epilogue run concurrently instead of in lockstep (the ncu profile of the earlier
+// single-role kernel showed its four warpgroups convoying: ALU phase and tensor phase did not overlap).
 //
 //   warps 0-3    producers: packed row -> fp16 A stage (ring of NS stages) -> arrive full_A
 //   warp  4      one thread issues GEMM1(k) into accumulator k % NA, tcgen05.commit publishes it
@@ -17,20 +16,18 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
+#include "ws_table.cuh"
 
 namespace bmm {
 namespace {
 
-constexpr int WS_KC = 32;
 constexpr int WS_NS = 5;      // A stages
-constexpr int WS_PARTS = 2;   // D = hi + lo in fp16 (22 significant bits; the 0/1 rows are exact)
 constexpr int WS_NA = 4;      // GEMM1 accumulators (64 TMEM columns each)
 constexpr int WS_NB = 4;      // one-hot stages
 constexpr int WS_NEPI = 3;    // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
 constexpr int WS_CHUNK = 2048;
 constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
-constexpr int WS_B1_ROW = WS_PARTS * WS_KC * 16;
 
 // shared memory: [A ring][B2 ring][B1 table][bias][barriers][tmem slot].  GEMM2 reads 16 chunks (M = 128)
 // from an A stage that only holds NCH + 1: the rows beyond are whatever follows (other stages, one-hot
@@ -76,24 +73,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         mbar_init(all_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = tid; e < WS_KC * NCH * 8; e += WS_THREADS) {
-        const int k = e % WS_KC, d = e / WS_KC;
-        double D = 0.0;
-        if (k < K && d < P) D = (p.w1[k + K * d] - p.w0[k + K * d]) * 1.4426950408889634;
-        D = fmin(fmax(D, -1.0e4), 1.0e4);     // theta exactly 0 / 1: log 0 = -inf would make 0 * inf = NaN in the contraction
-        if (D != D) D = 0.0;
-        const __half hi = __double2half(D);
-        const __half lo = __double2half(D - (double)__half2float(hi));
-        unsigned char *cell = B1 + (d >> 3) * WS_B1_ROW + k * 16 + (d & 7) * 2;
-        *(__half *)(cell + 0 * WS_KC * 16) = hi;
-        *(__half *)(cell + 1 * WS_KC * 16) = lo;
-    }
+    // weight table: the operand image the update kernel wrote (ws_table.cuh), 16 bytes per thread and step
+    for (int e = tid; e < NCH * WS_B1_ROW / 16; e += WS_THREADS) *(uint4 *)(B1 + e * 16) = __ldcg((const uint4 *)p.ws_b1 + e);
     for (int k = tid; k < WS_KC; k += WS_THREADS) {
         float b = -INFINITY;
         if (k < K) {
-            double s0 = 0.0;
-            for (int d = 0; d < P; ++d) s0 += p.w0[k + K * d];
-            const double bb = (p.lpi[k] + s0) * 1.4426950408889634;
+            const double bb = (p.lpi[k] + p.ws_s0[k]) * 1.4426950408889634;
             b = bb == bb ? (float)fmax(bb, -3.0e38) : -INFINITY;
         }
         bias[k] = b;
@@ -308,17 +293,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
     }
+    // ---- N-sharded run: the last CTA to get here pushes this rank's counts into every rank's inbox ----
+    if (p.x_fused) {
+        __shared__ int last_sh;
+        __threadfence();                 // this CTA's count atomics are performed before its ticket
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned ticket = atomicAdd(p.x_done, 1u);
+            last_sh = ticket == gridDim.x - 1;
+            if (last_sh) *p.x_done = 0u;         // ready for the next launch (stream order)
+        }
+        __syncthreads();
+        if (last_sh) {
+            __threadfence();
+            const int n = K + K * P, world = p.x_world, s = p.x_seq[0] + j;
+            const int *gcnt = p.counts + (size_t)(j & 1) * n;
+            for (int e = tid; e < n; e += WS_THREADS) {
+                const int v = __ldcg(gcnt + e);
+                for (int r = 0; r < world; ++r) p.x_peer[r][x_slot_off(s, world, p.x_rank, (size_t)p.x_cap) + e] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < world) {
+                int *flag = p.x_peer[tid] + x_flag_off(s, world, p.x_rank, (size_t)p.x_cap);
+                asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(flag), "r"(s) : "memory");
+            }
+        }
+    }
 }
 
 template <int NCH>
 cudaError_t launch_ws_nch(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     using L = WsLayout<NCH>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(big_sweep_ws_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static FuncAttrCache attr;
+    if (cudaError_t e = attr.ensure_smem(big_sweep_ws_kernel<NCH>, (int)L::TOTAL)) return e;
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     long long ctas = ntiles < sm_count ? ntiles : sm_count;
     if (ctas < 1) ctas = 1;
@@ -329,14 +337,21 @@ cudaError_t launch_ws_nch(const BigParams &p, int j, int sm_count, cudaStream_t 
 
 }  // namespace
 
+bool big_tc_supported(const BigParams &p) {
+    return p.precision == 1 && p.K <= 32 && p.P <= 112 && p.W <= 4 && p.ru == nullptr && p.loglik_out == nullptr;
+}
+
+size_t ws_b1_bytes(int P) { return (size_t)ws_nch(P) * WS_B1_ROW; }
+
 cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st) {
-    switch ((p.P + 15) / 16) {
-        case 1: return launch_ws_nch<2>(p, j, sm_count, st);
-        case 2: return launch_ws_nch<4>(p, j, sm_count, st);
-        case 3: return launch_ws_nch<6>(p, j, sm_count, st);
-        case 4: return launch_ws_nch<8>(p, j, sm_count, st);
-        case 5: return launch_ws_nch<10>(p, j, sm_count, st);
-        case 6: return launch_ws_nch<12>(p, j, sm_count, st);
+    if (!p.ws_b1 || !p.ws_s0) return cudaErrorInvalidValue;
+    switch (ws_nch(p.P)) {
+        case 2: return launch_ws_nch<2>(p, j, sm_count, st);
+        case 4: return launch_ws_nch<4>(p, j, sm_count, st);
+        case 6: return launch_ws_nch<6>(p, j, sm_count, st);
+        case 8: return launch_ws_nch<8>(p, j, sm_count, st);
+        case 10: return launch_ws_nch<10>(p, j, sm_count, st);
+        case 12: return launch_ws_nch<12>(p, j, sm_count, st);
         default: return launch_ws_nch<14>(p, j, sm_count, st);
     }
 }

@@ -70,32 +70,6 @@ __global__ void __launch_bounds__(256) finalize_z_u8x4_kernel(int N, int nsample
     }
 }
 
-// Chunk variant for the pipelined download: sweeps [j0, j0 + cs) of every chain, as bytes, laid out
-// [chain][observation][cs] so that the host can widen each row straight into its place in the S x N
-// column-major matrix.  perm_out is indexed with the absolute sweep offset sidx0 = j0 - burnin.
-__global__ void finalize_chunk_kernel(int N, int nsamples, int j0, int cs, int K, int S, int sidx0,
-                                      const uint8_t *__restrict__ zhist, const int *__restrict__ perm_out,
-                                      uint8_t *__restrict__ z_orig, uint8_t *__restrict__ z_rel) {
-    __shared__ uint8_t tile[32][33];
-    const int c = blockIdx.z;
-    const int i0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
-    const uint8_t *src = zhist + ((size_t)c * nsamples + j0) * N;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int s = s0 + r, i = i0 + threadIdx.x;
-        tile[r][threadIdx.x] = (s < cs && i < N) ? src[(size_t)s * N + i] : 0;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int i = i0 + r, s = s0 + threadIdx.x;
-        if (i < N && s < cs) {
-            const int z = tile[threadIdx.x][r];
-            const size_t o = ((size_t)c * N + i) * cs + s;
-            if (z_orig) z_orig[o] = (uint8_t)z;
-            if (z_rel) z_rel[o] = (uint8_t)((z >= 1 && z <= K) ? perm_out[(size_t)c * S * K + (sidx0 + s) + (size_t)S * (z - 1)] + 1 : 0);
-        }
-    }
-}
-
 __global__ void expand_rows_kernel(int N, int U, int K, const int *__restrict__ rowid, const double *__restrict__ src,
                                    double *__restrict__ dst) {
     const int c = blockIdx.y;
@@ -125,22 +99,6 @@ cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int
         else
             finalize_z_kernel<uint8_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
                 z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
-        g_launches++;
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_finalize_chunk(int n_chains, int N, int nsamples, int j0, int cs, int K, int S, int sidx0,
-                                  const uint8_t *zhist, const int *perm_out, uint8_t *z_orig, uint8_t *z_rel, cudaStream_t st) {
-    if (cs <= 0 || N <= 0) return cudaSuccess;
-    dim3 block(32, 8);
-    for (int c0 = 0; c0 < n_chains; c0 += 65535) {
-        const int nc = n_chains - c0 < 65535 ? n_chains - c0 : 65535;
-        dim3 grid((N + 31) / 32, (cs + 31) / 32, nc);
-        const size_t off = (size_t)c0 * N * cs;
-        finalize_chunk_kernel<<<grid, block, 0, st>>>(N, nsamples, j0, cs, K, S, sidx0, zhist + (size_t)c0 * nsamples * N,
-                                                       perm_out ? perm_out + (size_t)c0 * S * K : nullptr,
-                                                       z_orig ? z_orig + off : nullptr, z_rel ? z_rel + off : nullptr);
         g_launches++;
     }
     return cudaGetLastError();

@@ -8,6 +8,21 @@ namespace bmm {
 // Counter of kernel launches made by this library (bmm_launch_count()).
 extern unsigned long long g_launches;
 
+// cudaFuncSetAttribute is per device: remember, per kernel, the value already set on each device.
+struct FuncAttrCache {
+    int set[64] = {};
+    template <typename F>
+    cudaError_t ensure_smem(F *kernel, int bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64 && set[dev] >= bytes) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) set[dev] = bytes;
+        return e;
+    }
+};
+
 // ---- uncollapsed samplers, one chain per thread block (kern_full.cu) --------------------------
 // Data rows are de-duplicated on the host: U unique bit-packed rows, multiplicities wt[U],
 // rowid[N] maps each observation to its row.  Every per-row quantity (probabilities, Stephens Q)
@@ -121,17 +136,34 @@ struct BigParams {
     int *cnt_ws;                      // scratch of launch_big_counts: 2*(K+1) + N_local ints
     const double *ru; int ru_slots;   // replay
     const double *rpi, *rtheta, *ralpha;
+    // tensor path for K <= 32, P <= 112 (kern_big_ws.cu): operand image of the split weight table and
+    // s0_k = sum_d log(1 - theta_kd), written by the update kernel so that the sweep's prologue is a copy
+    unsigned char *ws_b1;             // [ws_b1_bytes(P)] or nullptr
+    double *ws_s0;                    // [32]
+    // count exchange of an N-sharded run over peer memory (dist.cu).  x_world <= 1: the counts in `counts` are
+    // complete (single GPU, or already all-reduced by NCCL)
+    int x_world, x_rank;
+    int x_fused;                      // the sweep kernel's last CTA pushes the counts itself
+    unsigned long long x_cap;         // ints per inbox slot
+    int *const *x_peer;               // [x_world] every rank's inbox block as mapped here
+    const int *x_local;               // this rank's inbox block
+    const int *x_seq;                 // x_seq[0] + j = exchange number of sweep j
+    unsigned *x_done;                 // CTA ticket counter of the fused push (zero between launches)
 };
+// inbox addressing shared by producer and consumer: slot of `rank` for exchange number s, and its flag
+__host__ __device__ inline size_t x_slot_off(int s, int world, int rank, size_t cap) { return ((size_t)(s & 1) * world + rank) * cap; }
+__host__ __device__ inline size_t x_flag_off(int s, int world, int rank, size_t cap) { return 2 * (size_t)world * cap + (size_t)(s & 1) * world + rank; }
+size_t ws_b1_bytes(int P);
+cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st);   // operand image from w1 / w0 (initial state)
 bool big_tables_fit_smem(int K, int P, int precision);
 int big_replay_max_k();
 cudaError_t launch_big_init(const BigParams &p, cudaStream_t st);
 cudaError_t launch_big_replay_load(const BigParams &p, int j, cudaStream_t st);
 cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream_t st);
 cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st);
-// tcgen05 sweep (kern_big_tc.cu): log-likelihood and sufficient statistics as tensor-core contractions
+// tcgen05 sweep for K <= 32, P <= 112 (kern_big_ws.cu): log-likelihood and sufficient statistics as tensor-core
+// contractions, warp-specialised (producer / MMA / epilogue warps over mbarrier rings)
 bool big_tc_supported(const BigParams &p);
-cudaError_t launch_big_sweep_tc(const BigParams &p, int j, int sm_count, cudaStream_t st);
-// same shapes, warp-specialised (producer / MMA / epilogue warps over mbarrier rings): kern_big_ws.cu
 cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st);
 // sufficient statistics from the bit-packed rows (kern_big_counts.cu): counting sort by cluster + bit-sliced
 // per-variable counters; counts must be zero on entry, ws holds 2*(K+1) + N ints
@@ -177,9 +209,6 @@ cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long s
 // elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).
 cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
                               const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st);
-// sweeps [j0, j0 + cs) as bytes in [chain][observation][cs] order (pipelined download)
-cudaError_t launch_finalize_chunk(int n_chains, int N, int nsamples, int j0, int cs, int K, int S, int sidx0,
-                                  const uint8_t *zhist, const int *perm_out, uint8_t *z_orig, uint8_t *z_rel, cudaStream_t st);
 // expand a per-row matrix [c][U*K] to per-observation [c][N*K]
 cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
                                cudaStream_t st);

@@ -53,8 +53,9 @@ def exchange_unique_id(get_id, rank, world, group=None):
 
 
 def init(rank, world, device, group=None, p2p_cap_ints=1 << 20):
-    """Create the library's NCCL communicator for this process (no-op for world == 1) and, with
-    BMM_P2P=1, the peer-memory inboxes of the one-shot count exchange (`p2p_cap_ints` >= K + K*P)."""
+    """Create the library's NCCL communicator for this process (no-op for world == 1) and the peer-memory
+    inboxes of the per-sweep count exchange (`p2p_cap_ints` >= K + K*P; BMM_P2P=0: NCCL all-reduce instead).
+    Returns True when the peer-memory exchange is in use."""
     L = _lib.lib()
     if world == 1:
         _lib.check(L.bmm_dist_init(0, 1, None, int(device)))
@@ -68,10 +69,10 @@ def init(rank, world, device, group=None, p2p_cap_ints=1 << 20):
     uid = exchange_unique_id(get_id, rank, world, group)
     arr = (C.c_uint8 * 128)(*uid)
     _lib.check(L.bmm_dist_init(int(rank), int(world), arr, int(device)))
-    # Off by default: measured on 8 x B200 (C4, 8.3 KB of counts per sweep) the push + gather kernels cost
-    # 154 us per sweep against 45 us for the NCCL all-reduce (2 GPUs: 31 vs 27 us) -- the system-scope
-    # fences and two extra launches outweigh the saved NCCL latency.  BMM_P2P=1 enables it.
-    if p2p_cap_ints and os.environ.get("BMM_P2P", "0") == "1":
+    # The count exchange goes over peer memory when the inboxes can be mapped (BMM_P2P=0 forces the NCCL
+    # all-reduce): the producer side is the tail of the sweep kernel, the consumer side the head of the
+    # parameter-update kernel, so a sweep costs no extra launch and no collective call.
+    if p2p_cap_ints and os.environ.get("BMM_P2P", "1") != "0":
         return attach_p2p(rank, world, p2p_cap_ints, group)
     return False
 

@@ -97,6 +97,59 @@ def test_stickbreaking_replay(oracle, datasets):
     assert np.array_equal(g["permutations"][:, occ], t["permutations"][:, occ])
 
 
+def test_stickbreaking_burnrelabel_above_burnin_replay(oracle, datasets):
+    """The reference's gibbs_stickbreaking wrapper does not clamp burnrelabel (R/utils.R:95-107): the C++ runs with
+    probs_out slices that were never written (zero -> 1e-6 in my_stephens_batch).  Same here, chain and grid path."""
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    K, ns, burnin, br = 4, 60, 6, 50
+    ip, th = _init_full(K, X.shape[1], 5)
+    r = oracle.gibbs_stickbreaking(X, ip, th, ns, K, burnin=burnin, relabel=True, burnrelabel=br, seed=3)
+    t = r.tail()
+    occ = np.unique(t["z_original"]) - 1
+    for grid in (False, True):
+        g = B.gibbs_stickbreaking(X, ns, K, burnin=burnin, relabel=True, burnrelabel=br, initial_pi=ip, initial_theta=th,
+                                  replay=_replay_of(r), grid_path=grid)
+        assert np.array_equal(g["z_original"], t["z_original"]), grid
+        assert np.array_equal(g["permutations"][:, occ], t["permutations"][:, occ]), grid
+
+
+@pytest.mark.parametrize("sampler", ["full", "stickbreaking", "collapsed", "dp", "grid"])
+def test_plan_rerun_is_identical(datasets, sampler):
+    """bmm_plan_run restores the chain state bmm_plan_create built, so every run of a plan is the same chain
+    (the DP sampler used to seat all observations again on top of the previous run's clusters)."""
+    _need_gpu()
+    from bmm_mcmc_b200 import api
+    X = datasets["K2_N100_P5"]
+    N, P = X.shape
+    ns, burnin, br, C_ = 40, 12, 5, 3
+    kw = dict(alpha=0.0, beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=True, burnrelabel=br, seed=11)
+    if sampler in ("full", "stickbreaking", "grid"):
+        K = 4
+        C_ = 1 if sampler == "grid" else C_
+        rng = RRng(2)
+        ip = np.exp(rng.runif(C_ * K)).reshape(C_, K)
+        ip /= ip.sum(1, keepdims=True)
+        th = rng.runif(C_ * K * P).reshape(C_, P, K)
+        sid = _lib.SAMPLER_STICKBREAKING if sampler == "stickbreaking" else _lib.SAMPLER_FULL
+        plan = api.Plan(sid, X, ns, K, chains=C_, init_pi=np.ascontiguousarray(ip), init_theta=np.ascontiguousarray(th),
+                        grid_path=sampler == "grid", **kw)
+    elif sampler == "collapsed":
+        iz = np.stack([RRng(5 + c).sample_int(3, N) for c in range(C_)]).astype(np.int32)
+        plan = api.Plan(_lib.SAMPLER_COLLAPSED, X, ns, 3, chains=C_, init_z=np.ascontiguousarray(iz), **kw)
+    else:
+        plan = api.Plan(_lib.SAMPLER_DP, X, ns, 20, chains=C_, **kw)
+    plan.run()
+    first = {k: v.copy() for k, v in plan.fetch().items()}
+    for _ in range(2):
+        plan.run()
+    again = plan.fetch()
+    plan.close()
+    assert set(first) == set(again)
+    for k in first:
+        assert np.array_equal(first[k], again[k], equal_nan=True), (sampler, k)
+
+
 @pytest.mark.parametrize("kernel", ["fast", "generic"])
 @pytest.mark.parametrize("name,K,relabel,alpha", [("K2_N100_P5", 2, False, 0.0), ("K3_N1000_P5", 3, True, 0.0),
                                                   ("K2_N1000_P5", 4, True, 1.5)])
@@ -407,7 +460,7 @@ def test_grid_path_large_synthetic():
     assert (g["z"][0] != h["z"][0]).mean() < 1e-3
 
 
-# ---- tcgen05 sweep of the grid path (kern_big_tc.cu) ----------------------------------------------
+# ---- tcgen05 sweep of the grid path (kern_big_ws.cu) ----------------------------------------------
 def _host_counts(z, X, K):
     """[S][K + K*P]: c_k then V_kd (k + K*d) from an S x N allocation history."""
     S, P = z.shape[0], X.shape[1]
@@ -715,23 +768,6 @@ def test_posterior_means_collapsed_and_stickbreaking(oracle, datasets):
         gm, om = np.mean([s[idx] for s in gs], 0), np.mean([s[idx] for s in os_], 0)
         se = np.std([s[idx] for s in gs], 0) / np.sqrt(24) + np.std([s[idx] for s in os_], 0) / np.sqrt(4) + 0.015
         assert (np.abs(gm - om) < 4 * se).all(), ("stickbreaking", idx, gm, om)
-
-
-@pytest.mark.parametrize("sampler,relabel", [("full", True), ("full", False), ("collapsed", False)])
-def test_pipelined_download_equals_plain(datasets, monkeypatch, sampler, relabel):
-    """BMM_PIPELINE=1: above 64M allocations the one-shot call samples in chunks of sweeps and downloads /
-    widens each chunk while the next one runs: identical outputs to the plain call (ragged last chunk).
-    (Off by default: measured slower, see capi.cu.)"""
-    _need_gpu()
-    monkeypatch.setenv("BMM_PIPELINE", "1")
-    X = datasets["K3_N1000_P5"]
-    kw = dict(burnin=30, relabel=relabel, burnrelabel=10, chains=256, seed=8)
-    f = B.gibbs_full if sampler == "full" else B.gibbs_collapsed
-    a = f(X, 300, 3, **kw)                                # 256 * 270 * 1000 = 69M allocations, S = 270 = 4 * 64 + 14
-    monkeypatch.setenv("BMM_PIPELINE", "0")
-    b = f(X, 300, 3, **kw)
-    for k in a:
-        assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
 @pytest.mark.parametrize("relabel", [False, True])

@@ -1,4 +1,4 @@
-// Micro-benchmark (not product code): cycles per tcgen05.mma for the operand layouts kern_big_tc.cu uses.
+// Micro-benchmark (not product code): cycles per tcgen05.mma for the operand layouts kern_big_ws.cu uses.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe umma_probe.cu && ./umma_probe
 #include <cstdint>
 #include <cstdio>
