@@ -150,6 +150,7 @@ struct bmm_plan {
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     unsigned long long glaunches[2] = {0, 0};
     DevBuf ws_b1, ws_s0, x_done;
+    DevBuf x_inbox, x_peer_arr, x_seq;   // single-GPU inbox of the tensor path (x_world = 1)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias, cnt_ws;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
     DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
@@ -437,6 +438,18 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
             b.x_fused = tensor_ws ? 1 : 0;
         }
     }
+    if (tensor_ws && !pl->sharded) {     // one GPU: the same tagged hand-over through a local inbox
+        const size_t ncnt = (size_t)K + KP;
+        CU(pl->x_inbox.alloc(2 * ncnt * sizeof(int2), false));
+        CU(cudaMemset(pl->x_inbox.p, 0xFF, pl->x_inbox.bytes));
+        int2 *self = pl->x_inbox.as<int2>();
+        TRY(upload(pl->x_peer_arr, &self, 1));
+        const int seq0[2] = {1, 1};
+        TRY(upload(pl->x_seq, seq0, 2));
+        CU(pl->x_done.alloc(sizeof(unsigned)));
+        b.x_world = 1; b.x_rank = 0; b.x_cap = ncnt; b.x_peer = pl->x_peer_arr.as<int2 *>(); b.x_local = self;
+        b.x_seq = pl->x_seq.as<int>(); b.x_done = pl->x_done.as<unsigned>(); b.x_fused = 1;
+    }
     {   // sweep-kernel timing: every sweep for short runs, every 8th otherwise (BMM_SWEEP_EVENTS = stride, 0 = none)
         const char *e = getenv("BMM_SWEEP_EVENTS");
         pl->ev_stride = e ? atoi(e) : (ns <= 24 ? 1 : 8);
@@ -545,6 +558,7 @@ int enqueue_segment(bmm_plan *pl, int seg, int jsplit) {
         if (pl->zfreq.p) CU(cudaMemsetAsync(pl->zfreq.p, 0, pl->zfreq.bytes, pl->stream));
         if (pl->x_done.p) CU(cudaMemsetAsync(pl->x_done.p, 0, pl->x_done.bytes, pl->stream));
         if (pl->x_p2p && bmm::dist_p2p_begin_run(ns, pl->stream)) return fail(BMM_ERR_NCCL, bmm::dist_error());
+        if (pl->x_seq.p) CU(bmm::launch_x_begin_run(pl->x_seq.as<int>(), ns, pl->stream));
         CU(bmm::launch_big_init(b, pl->stream));
         CU(bmm::launch_ws_table(b, pl->stream));
         if (pl->relabel) CU(bmm::launch_grid_identity_perm(b.K, b.K, pl->perm_cur.as<int>(), pl->stream));

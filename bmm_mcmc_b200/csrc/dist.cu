@@ -7,6 +7,7 @@
 #include <string>
 #include "../../include/bmm_capi.h"
 #include "dist.h"
+#include "kernels.h"
 
 namespace bmm {
 
@@ -72,46 +73,36 @@ int dist_allreduce_f64(double *buf, size_t n, cudaStream_t st) {
 
 // ---- count exchange over NVLink peer memory ----------------------------------------------------------
 // The per-sweep exchange is a few KB of int32 counts: latency-bound.  Every rank owns an inbox
-// [2 parities][world][cap] ints plus flags [2][world] in one cudaMalloc'ed block that the peers map through
-// CUDA IPC.  After its sweep a rank PUSHES its counts into slot `rank` of every rank's inbox (remote stores
-// over NVLink, its own slot included), fences at system scope and writes the exchange number into the
-// flag; the consumer (big_update_kernel) spins on its LOCAL flags with acquire loads and sums the slots it
-// needs.  There is no separate gather launch and, on the warp-specialised tensor path, no publish launch
-// either: the last CTA of the sweep kernel to flush its counts does the push (kern_big_ws.cu).
+// [2 parities][world][cap] of 8-byte words (count, exchange number) in one cudaMalloc'ed block that the peers
+// map through CUDA IPC.  After its sweep a rank PUSHES its counts into slot `rank` of every rank's inbox
+// (remote 8-byte stores over NVLink, its own slot included); the consumer (big_update_kernel) re-reads each
+// word it needs until the word carries the number of the exchange it waits for, and sums over the ranks.
+// No fence, no flag, no gather launch (system-scope fences after remote stores cost ~10 us per sweep on this
+// box, which is what made the first, flag-based version of this exchange slower than NCCL), and on the
+// warp-specialised tensor path no publish launch either: the last CTA of the sweep kernel to flush its
+// counts does the push (kern_big_ws.cu).
 // Parity double-buffering is enough: a rank cannot publish exchange s+2 before it has received every
 // peer's s+1, which those peers only send after they consumed s.
 // Exchange numbers come from a device-side counter so that a captured CUDA graph replays with fresh
 // numbers: seq[0] = number of sweep 0 of the current run, seq[1] = next free number.
 namespace {
 struct P2P {
-    int *local = nullptr;            // this rank's block
-    int *peer[64] = {nullptr};       // peer[r] = rank r's block mapped here (peer[rank] = local)
-    int **peer_dev = nullptr;        // device copy of peer[]
+    int2 *local = nullptr;           // this rank's block
+    int2 *peer[64] = {nullptr};      // peer[r] = rank r's block mapped here (peer[rank] = local)
+    int2 **peer_dev = nullptr;       // device copy of peer[]
     int *seq = nullptr;              // device: [0] base of the current run, [1] next free exchange number
     size_t cap = 0;                  // ints per (parity, source) slot
     bool attached = false;
 } g_p2p;
 
-__host__ __device__ inline size_t p2p_block_ints(size_t cap, int world) { return 2 * (size_t)world * cap + 2 * (size_t)world; }
-
-__global__ void p2p_begin_run_kernel(int *seq, int n) {
-    seq[0] = seq[1];
-    seq[1] += n;
-}
+__host__ __device__ inline size_t p2p_block_words(size_t cap, int world) { return 2 * (size_t)world * cap; }
 
 // generic publish (sweep kernels without a fused push): block r pushes to rank r
-__global__ void p2p_publish_kernel(int *const *peer, const int *counts, size_t n, size_t cap, int world, int rank,
+__global__ void p2p_publish_kernel(int2 *const *peer, const int *counts, size_t n, size_t cap, int world, int rank,
                                    const int *seq, int j) {
-    const int s = seq[0] + j, parity = s & 1;
-    int *dst_block = peer[blockIdx.x];
-    int *dst = dst_block + ((size_t)parity * world + rank) * cap;
-    for (size_t e = threadIdx.x; e < n; e += blockDim.x) dst[e] = counts[e];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int *flag = dst_block + 2 * (size_t)world * cap + (size_t)parity * world + rank;
-        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(flag), "r"(s) : "memory");
-    }
+    const int s = seq[0] + j;
+    int2 *dst = peer[blockIdx.x] + x_slot_off(s, world, rank, cap);
+    for (size_t e = threadIdx.x; e < n; e += blockDim.x) x_store(dst + e, counts[e], s);
 }
 }  // namespace
 
@@ -126,8 +117,7 @@ P2PView dist_p2p_view() {
 
 // reserve the exchange numbers of a run of n sweeps (stream-ordered; every rank makes the same calls)
 int dist_p2p_begin_run(int n, cudaStream_t st) {
-    p2p_begin_run_kernel<<<1, 1, 0, st>>>(g_p2p.seq, n);
-    if (cudaGetLastError() != cudaSuccess) { derr("p2p begin_run launch failed"); return -1; }
+    if (launch_x_begin_run(g_p2p.seq, n, st) != cudaSuccess) { derr("p2p begin_run launch failed"); return -1; }
     return 0;
 }
 
@@ -169,9 +159,9 @@ int bmm_dist_p2p_local(uint64_t cap_ints, uint8_t handle_out[64]) {
     using namespace bmm;
     if (!handle_out || cap_ints == 0 || g_world < 2 || g_world > 64) return BMM_ERR_INVALID;
     if (g_p2p.local) return BMM_ERR_INVALID;
-    const size_t ints = p2p_block_ints(cap_ints, g_world);
-    if (cudaMalloc((void **)&g_p2p.local, ints * sizeof(int)) != cudaSuccess) { derr("p2p: cudaMalloc failed"); return BMM_ERR_CUDA; }
-    cudaMemset(g_p2p.local, 0xFF, ints * sizeof(int));     // flags = -1: no sweep published yet
+    const size_t words = p2p_block_words(cap_ints, g_world);
+    if (cudaMalloc((void **)&g_p2p.local, words * sizeof(int2)) != cudaSuccess) { derr("p2p: cudaMalloc failed"); return BMM_ERR_CUDA; }
+    cudaMemset(g_p2p.local, 0xFF, words * sizeof(int2));     // tags = -1: nothing published yet
     if (cudaMalloc((void **)&g_p2p.seq, 2 * sizeof(int)) != cudaSuccess) { derr("p2p: cudaMalloc failed"); return BMM_ERR_CUDA; }
     const int seq0[2] = {1, 1};
     cudaMemcpy(g_p2p.seq, seq0, sizeof seq0, cudaMemcpyHostToDevice);
@@ -197,10 +187,10 @@ int bmm_dist_p2p_attach(const uint8_t *handles) {
             cudaGetLastError();
             return BMM_ERR_CUDA;
         }
-        g_p2p.peer[r] = (int *)ptr;
+        g_p2p.peer[r] = (int2 *)ptr;
     }
-    if (cudaMalloc((void **)&g_p2p.peer_dev, 64 * sizeof(int *)) != cudaSuccess) return BMM_ERR_CUDA;
-    cudaMemcpy(g_p2p.peer_dev, g_p2p.peer, 64 * sizeof(int *), cudaMemcpyHostToDevice);
+    if (cudaMalloc((void **)&g_p2p.peer_dev, 64 * sizeof(int2 *)) != cudaSuccess) return BMM_ERR_CUDA;
+    cudaMemcpy(g_p2p.peer_dev, g_p2p.peer, 64 * sizeof(int2 *), cudaMemcpyHostToDevice);
     g_p2p.attached = true;
     return BMM_OK;
 }

@@ -11,8 +11,8 @@ int dist_allreduce_i32(int *buf, size_t n, cudaStream_t st);
 int dist_allreduce_f64(double *buf, size_t n, cudaStream_t st);
 // count exchange over IPC-mapped peer memory (bmm_dist_p2p_local / bmm_dist_p2p_attach); see dist.cu
 struct P2PView {
-    int *const *peer = nullptr;   // device array [world]: every rank's inbox block as mapped into this process
-    int *local = nullptr;         // this rank's inbox block: [2][world][cap] ints, then flags [2][world]
+    int2 *const *peer = nullptr;  // device array [world]: every rank's inbox block as mapped into this process
+    int2 *local = nullptr;        // this rank's inbox block: [2][world][cap] words of (count, exchange number)
     const int *seq = nullptr;     // device: seq[0] + j = exchange number of sweep j of the current run
     size_t cap = 0;
     int world = 1, rank = 0;

@@ -160,16 +160,10 @@ __global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams 
 
 constexpr int UPD_THREADS = 256;
 
-__device__ __forceinline__ int ld_acquire_sys(const int *p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // One launch per sweep, after the z-sweep: blocks 0..K-1 own one cluster each (theta_k., its log tables and, for
 // the tensor path, row k of the operand image), block K draws pi / sticks / alpha, writes the history rows and
-// zeroes the next sweep's count buffer.  On an N-sharded run over peer memory every block first waits for the
-// counts of all ranks (acquire-polling the flags in this rank's own inbox) and sums the slots it needs; the
+// zeroes the next sweep's count buffer.  On an N-sharded run over peer memory every thread sums, over the ranks, the
+// inbox words it needs, re-reading a word until it carries this exchange's number (kernels.h); the
 // reduced values are integers, and every draw is keyed by its parameter index, so all ranks compute identical
 // tables without a broadcast (full_gibbs.cpp:182-230, stickbreaking.cpp:164-235, utils.cpp:6-14).
 __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams p, const int j) {
@@ -177,40 +171,44 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
     __shared__ double ag[4];
     __shared__ double sh_w0[128];
     __shared__ int sh_c[256];
-    __shared__ int sh_ok;
     const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = ns - p.burnin, tid = threadIdx.x;
     const int blk = blockIdx.x;
     const bool replay = p.rtheta != nullptr;
     int *cur = p.counts + (size_t)(j & 1) * (K + KP);
     const uint32_t chain = (uint32_t)p.chain_offset;
     const double alpha_prev = *p.alpha_cur;
-    const int world = p.x_world > 1 ? p.x_world : 1;
-    const int *slots = nullptr;          // [world][cap] of this exchange when the counts come from the inbox
-    if (world > 1) {
-        const int s = p.x_seq[0] + j;
-        if (tid == 0) sh_ok = 1;
-        __syncthreads();
-        if (tid < world) {
-            const int *flag = p.x_local + x_flag_off(s, world, tid, (size_t)p.x_cap);
-            // a peer that never publishes must not hang the GPU: give up after 20 s of wall time
-            unsigned long long t0 = 0, t1;
-            unsigned spins = 0;
-            while (ld_acquire_sys(flag) != s) {
-                if ((++spins & 1023u) == 0) {
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (!t0) t0 = t1;
-                    else if (t1 - t0 > 20000000000ull) { sh_ok = 0; break; }
-                }
-            }
-        }
-        __syncthreads();
-        if (!sh_ok && tid == 0) *p.status = -7;   // BMM_ERR_NCCL: exchange failed
-        slots = p.x_local + x_slot_off(s, world, 0, (size_t)p.x_cap);
+    // the next sweep kernel may start its prologue now; it waits for this grid before it reads the tables
+    griddep_launch();
+    // Inbox mode without relabelling needs nothing from the predecessor but the tagged words themselves; otherwise wait
+    // until the kernel in front (sweep, all-reduce or Q update) has completed.
+    if (p.x_world < 1 || p.theta_rel_out) griddep_wait();
+    const int world = p.x_world;
+    const int2 *slots = nullptr;         // [world][cap] words of this exchange when the counts come from the inbox
+    int xs = 0;
+    if (world >= 1) {
+        xs = p.x_seq[0] + j;
+        slots = p.x_local + x_slot_off(xs, world, 0, (size_t)p.x_cap);
     }
     auto count_of = [&](int e) -> int {       // reduced count e (c_k for e < K, V_kd at K + k + K d)
         if (!slots) return cur[e];
         int acc = 0;
-        for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * p.x_cap + e);
+        for (int r = 0; r < world; ++r) {
+            const int2 *w = slots + (size_t)r * p.x_cap + e;
+            int2 v = x_load(w);
+            if (v.y != xs) {
+                // not there yet; a peer that never publishes must not hang the GPU: give up after 20 s of wall time
+                unsigned long long t0 = 0, t1;
+                unsigned spins = 0;
+                while ((v = x_load(w)).y != xs) {
+                    if ((++spins & 1023u) == 0) {
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (!t0) t0 = t1;
+                        else if (t1 - t0 > 20000000000ull) { *p.status = -7; break; }   // BMM_ERR_NCCL: exchange failed
+                    }
+                }
+            }
+            acc += v.x;
+        }
         return acc;
     };
 
@@ -251,6 +249,7 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
                 if (tid == 0) p.ws_s0[k] = a;
             }
         }
+        griddep_wait();     // this grid must not complete before the sweep kernel in front has (see the end of the kernel)
         return;
     }
 
@@ -327,6 +326,10 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
         if (p.pi_out && j >= p.burnin) p.pi_out[(j - p.burnin) + (size_t)S * k] = pk;
     }
     if (tid == 0 && p.alpha_out && j >= p.burnin) p.alpha_out[j - p.burnin] = *p.alpha_cur;
+    // In inbox mode nothing above waited for the sweep kernel itself, only for its tagged words.  Whatever follows in the
+    // stream is ordered after THIS grid, so this grid completes only once the sweep kernel has (its allocation history
+    // is read by the layout kernels, its count buffer is zeroed two sweeps later).
+    griddep_wait();
 }
 
 // operand image of the initial tables (sweep 1 reads theta_0); later sweeps get it from big_update_kernel
@@ -440,8 +443,22 @@ cudaError_t launch_big_sweep(const BigParams &p, int j, int sm_count, cudaStream
     return launch_sweep_t<double>(p, j, grid, st);
 }
 
+bool pdl_enabled() {
+    static const bool on = !(getenv("BMM_PDL") && getenv("BMM_PDL")[0] == '0');
+    return on;
+}
+
 cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st) {
-    big_update_kernel<<<p.K + 1, UPD_THREADS, 0, st>>>(p, j);
+    g_launches++;
+    return launch_pdl(big_update_kernel, dim3(p.K + 1), dim3(UPD_THREADS), 0, st, p, j);
+}
+
+__global__ void x_begin_run_kernel(int *seq, int n) {
+    seq[0] = seq[1];
+    seq[1] += n;
+}
+cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st) {
+    x_begin_run_kernel<<<1, 1, 0, st>>>(seq, n_sweeps);
     g_launches++;
     return cudaGetLastError();
 }

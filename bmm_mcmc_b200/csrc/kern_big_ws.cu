@@ -21,7 +21,6 @@
 namespace bmm {
 namespace {
 
-constexpr int WS_NS = 5;      // A stages
 constexpr int WS_NA = 4;      // GEMM1 accumulators (64 TMEM columns each)
 constexpr int WS_NB = 4;      // one-hot stages
 constexpr int WS_NEPI = 3;    // epilogue warpgroups (4 at 80 registers/thread measured no faster)
@@ -32,21 +31,30 @@ constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
 // shared memory: [A ring][B2 ring][B1 table][bias][barriers][tmem slot].  GEMM2 reads 16 chunks (M = 128)
 // from an A stage that only holds NCH + 1: the rows beyond are whatever follows (other stages, one-hot
 // rows, the weight table -- all finite fp16) and land in accumulator lanes that are never read.
+// A stages: as many as fit (at most 9).  A stage is held from the bit expansion until GEMM2 of its tile has run, i.e.
+// across the whole epilogue of that tile, so the ring has to cover ~5 tile times of latency; with the 5 stages of the
+// first version the epilogue warps spent 30 % of their samples waiting for an accumulator (profiles/r01_ncu_big_sweep_ws.txt).
 template <int NCH>
 struct WsLayout {
     static constexpr int A_STAGE = (NCH + 1) * WS_CHUNK;
+    static constexpr int FIXED = WS_NB * WS_B2_BYTES + NCH * WS_B1_ROW + WS_KC * 4 + 64 * 8 + 16;
+    static constexpr int NS_FIT = (226 * 1024 - FIXED) / A_STAGE;
+    static constexpr int WS_NS = NS_FIT > 9 ? 9 : NS_FIT;
     static constexpr int B2_OFF = WS_NS * A_STAGE;
     static constexpr int B1_OFF = B2_OFF + WS_NB * WS_B2_BYTES;
     static constexpr int BIAS_OFF = B1_OFF + NCH * WS_B1_ROW;
     static constexpr int BAR_OFF = BIAS_OFF + WS_KC * 4;
     static constexpr int NBAR = 2 * WS_NS + 2 * WS_NA + 2 * WS_NB + 1;
     static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16;
+    static_assert(WS_NS >= 4, "too few A stages");
+    static_assert(NBAR <= 64, "barrier block");
     static_assert(B1_OFF + NCH * WS_B1_ROW - (WS_NS - 1) * A_STAGE >= 16 * WS_CHUNK, "GEMM2 over-read must stay inside the operand data");
 };
 
 template <int NCH>
 __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigParams p, const int j) {
     using L = WsLayout<NCH>;
+    constexpr int WS_NS = L::WS_NS;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int K = p.K, P = p.P, W = p.W;
@@ -73,6 +81,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         mbar_init(all_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // everything above overlaps the tail of the update kernel in front (programmatic dependent launch); its
+    // tables, log pi and the zeroed count buffer are needed from here on
+    griddep_wait();
     // weight table: the operand image the update kernel wrote (ws_table.cuh), 16 bytes per thread and step
     for (int e = tid; e < NCH * WS_B1_ROW / 16; e += WS_THREADS) *(uint4 *)(B1 + e * 16) = __ldcg((const uint4 *)p.ws_b1 + e);
     for (int k = tid; k < WS_KC; k += WS_THREADS) {
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc2 = tmem_base + WS_NA * WS_PARTS * WS_KC;
     const long long ntiles = ((long long)p.N_local + 127) / 128;
-    const long long T = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+    const int T = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;   // tiles of this CTA
     bool ok = true;
 
     if (warp < 4) {
@@ -118,27 +129,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         uint32_t ring[PF][NW];
 #pragma unroll
         for (int d = 0; d < PF; ++d) load_row(d, ring[d]);
-        for (long long k0 = 0; k0 < T && ok; k0 += PF) {
+        int s = 0;
+        uint32_t ph = 0;            // pass number & 1; the n-th reuse of a stage waits for completion n - 1 of its "free" barrier
+        bool first_pass = true;
+        for (int k0 = 0; k0 < T && ok; k0 += PF) {
 #pragma unroll
             for (int d = 0; d < PF; ++d) {
-                const long long k = k0 + d;
+                const int k = k0 + d;
                 if (k >= T || !ok) break;
+                // 8 bits -> 8 fp16 (0.0 / 1.0): y = byte * 0x8001 puts bit i at i and at i + 15, so (y >> 2p) & 0x10001 holds
+                // bits 2p, 2p + 1 in the two halves; times 0x3C00 = fp16 1.0 (14 instructions per byte)
                 uint4 ex[NCH];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    const uint32_t byte = ring[d][c >> 2] >> ((c & 3) * 8);
-                    ex[c] = make_uint4(bits2_f16x2(byte), bits2_f16x2(byte >> 2), bits2_f16x2(byte >> 4), bits2_f16x2(byte >> 6));
+                    const uint32_t y = __byte_perm(ring[d][c >> 2], 0u, 0x4440u + (c & 3)) * 0x8001u;
+                    ex[c] = make_uint4((y & 0x10001u) * 0x3C00u, ((y >> 2) & 0x10001u) * 0x3C00u,
+                                       ((y >> 4) & 0x10001u) * 0x3C00u, ((y >> 6) & 0x10001u) * 0x3C00u);
                 }
                 load_row(k + PF, ring[d]);
-                const int s = (int)(k % WS_NS);
-                const long long n = k / WS_NS;
-                if (n > 0) ok = mbar_wait(free_a + 8 * s, (uint32_t)((n - 1) & 1));
+                if (!first_pass) ok = mbar_wait(free_a + 8 * s, ph ^ 1u);
                 if (!ok) break;
                 unsigned char *A = smem + s * L::A_STAGE;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) *(uint4 *)(A + c * WS_CHUNK + t * 16) = ex[c];
                 fence_async_smem();
                 mbar_arrive(full_a + 8 * s);
+                if (++s == WS_NS) { s = 0; ph ^= 1u; first_pass = false; }
             }
         }
     } else if (warp == 4) {
@@ -148,11 +164,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (tid == 128) {
             constexpr uint32_t IDESC1 = umma_idesc_f16(128, WS_PARTS * WS_KC, 0, 0);
             const uint64_t da0 = umma_desc(smem_u32(smem), WS_CHUNK, 128), db0 = umma_desc(smem_u32(B1), WS_B1_ROW, 128);
-            for (long long k = 0; k < T && ok; ++k) {
-                const int s = (int)(k % WS_NS), a = (int)(k % WS_NA);
-                const long long na = k / WS_NA;
-                ok = mbar_wait(full_a + 8 * s, (uint32_t)((k / WS_NS) & 1));
-                if (ok && na > 0) ok = mbar_wait(acc_free + 8 * a, (uint32_t)((na - 1) & 1));
+            int s = 0, a = 0;
+            uint32_t ph_s = 0, ph_a = 0;
+            for (int k = 0; k < T && ok; ++k) {
+                ok = mbar_wait(full_a + 8 * s, ph_s);
+                if (ok && k >= WS_NA) ok = mbar_wait(acc_free + 8 * a, ph_a ^ 1u);
                 if (!ok) break;
                 tc_fence_after();
                 const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
@@ -161,6 +177,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                     umma_f16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
                               db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
                 umma_commit(acc_full + 8 * a);
+                if (++s == WS_NS) { s = 0; ph_s ^= 1u; }
+                if (++a == WS_NA) { a = 0; ph_a ^= 1u; }
             }
         }
         __syncwarp();
@@ -169,9 +187,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (tid == 160) {
             constexpr uint32_t IDESC2 = umma_idesc_f16(128, WS_KC, 1, 1);
             const uint64_t da0 = umma_desc(smem_u32(smem), 128, WS_CHUNK), db0 = umma_desc(smem_u32(smem + L::B2_OFF), 128, WS_CHUNK);
-            for (long long q = 0; q < T && ok; ++q) {
-                const int s = (int)(q % WS_NS), b = (int)(q % WS_NB);
-                ok = mbar_wait(b2_full + 8 * b, (uint32_t)((q / WS_NB) & 1));
+            int s = 0, b = 0;
+            uint32_t ph_b = 0;
+            for (int q = 0; q < T && ok; ++q) {
+                ok = mbar_wait(b2_full + 8 * b, ph_b);
                 if (!ok) break;
                 tc_fence_after();
                 const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4), db = db0 + (uint64_t)((b * WS_B2_BYTES) >> 4);
@@ -180,49 +199,97 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                     umma_f16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(free_a + 8 * s);
                 umma_commit(b2_free + 8 * b);
+                if (++s == WS_NS) s = 0;
+                if (++b == WS_NB) { b = 0; ph_b ^= 1u; }
             }
             umma_commit(all_done);
         }
         __syncwarp();
     } else if (warp >= 8) {
         // ================= epilogue warpgroups =================
-        const int e = (warp - 8) >> 2, t = (tid - 256) & 127, wq = warp & 3;
+        const int e = (warp - 8) >> 2, t = (tid - 256) & 127, wq = warp & 3, lane = tid & 31;
         const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)p.chain_offset);
         const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
         uint8_t *zrow = p.zhist ? p.zhist + (size_t)(p.keep_history ? j : 0) * p.N_local : nullptr;
-        for (long long k = e; k < T && ok; k += WS_NEPI) {
-            const long long i = (blockIdx.x + k * gridDim.x) * 128 + t;
+        const float2 *bias2 = (const float2 *)bias;
+        // One Philox block carries the uniforms of four consecutive observations, and a warp's 32 rows of a tile use 8
+        // blocks: each lane evaluates ONE block per four tiles of its warpgroup (lane = 8 * tile slot + block) and the
+        // words are handed out by shuffles, instead of every lane evaluating its own block for every tile.
+        const bool shared_rng = (p.row_offset & 3) == 0;
+        uint4 rnd4 = make_uint4(0u, 0u, 0u, 0u);
+        int a = e % WS_NA, b = e % WS_NB;                       // tile k uses accumulator k % NA, one-hot stage k % NB
+        uint32_t ph_a = (uint32_t)((e / WS_NA) & 1), ph_b = (uint32_t)((e / WS_NB) & 1);
+        int it = 0;
+        for (int k = e; k < T && ok; k += WS_NEPI, ++it) {
+            const long long i = ((long long)blockIdx.x + (long long)k * gridDim.x) * 128 + t;
             const bool valid = i < p.N_local;
             const unsigned long long gi = (unsigned long long)p.row_offset + (unsigned long long)i;
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
-            const float u = u32_unit_f(philox_word(rnd, (int)(gi & 3)));
-            const int a = (int)(k % WS_NA), b = (int)(k % WS_NB);
-            ok = mbar_wait(acc_full + 8 * a, (uint32_t)((k / WS_NA) & 1));
+            uint32_t uw;
+            if (shared_rng) {
+                if ((it & 3) == 0) {
+                    const int kk = k + WS_NEPI * (lane >> 3);          // the tile this lane's block belongs to
+                    const unsigned long long g0 = (unsigned long long)p.row_offset +
+                        (unsigned long long)(((long long)blockIdx.x + (long long)kk * gridDim.x) * 128 + wq * 32 + 4 * (lane & 7));
+                    rnd4 = philox4x32_10(make_uint4((uint32_t)(g0 >> 2), (uint32_t)(g0 >> 34), sid, (uint32_t)j), key);
+                }
+                const int src = 8 * (it & 3) + (lane >> 2);
+                const uint32_t w0 = __shfl_sync(0xffffffffu, rnd4.x, src), w1 = __shfl_sync(0xffffffffu, rnd4.y, src);
+                const uint32_t w2 = __shfl_sync(0xffffffffu, rnd4.z, src), w3 = __shfl_sync(0xffffffffu, rnd4.w, src);
+                uw = (lane & 2) ? ((lane & 1) ? w3 : w2) : ((lane & 1) ? w1 : w0);
+            } else {
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), sid, (uint32_t)j), key);
+                uw = philox_word(rnd, (int)(gi & 3));
+            }
+            const float u = u32_unit_f(uw);
+            ok = mbar_wait(acc_full + 8 * a, ph_a);
             if (!ok) break;
             tc_fence_after();
-            float l[WS_KC];
-#pragma unroll
-            for (int part = 0; part < WS_PARTS; ++part) {
+            // logits: hi part + bias, then + lo part, two lanes of fp32 per instruction (FADD2)
+            unsigned long long lp[WS_KC / 2];
+            {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * WS_PARTS * WS_KC + part * WS_KC), v);
+                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * WS_PARTS * WS_KC), v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) l[q] = part == 0 ? __uint_as_float(v[q]) + bias[q] : l[q] + __uint_as_float(v[q]);
+                for (int q = 0; q < WS_KC / 2; ++q) {
+                    const float2 bq = bias2[q];
+                    lp[q] = f2_add(f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), f2_pack(bq.x, bq.y));
+                }
+                tmem_ld32(tmem_base + lane_sel + (uint32_t)(a * WS_PARTS * WS_KC + WS_KC), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < WS_KC / 2; ++q)
+                    lp[q] = f2_add(lp[q], f2_pack(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
             }
             tc_fence_before();
             mbar_arrive(acc_free + 8 * a);      // accumulator a may be overwritten by GEMM1(k + NA)
-            float mx = l[0];
+            float l[WS_KC];
 #pragma unroll
-            for (int q = 1; q < WS_KC; ++q) mx = fmaxf(mx, l[q]);
+            for (int q = 0; q < WS_KC / 2; ++q) f2_unpack(lp[q], l[2 * q], l[2 * q + 1]);
+            // maximum with the three-input instruction (FMNMX3): 10 + 4 + 2 instead of 31
+            float mx;
+            {
+                float m[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) m[q] = fmax3(l[3 * q], l[3 * q + 1], l[3 * q + 2]);
+                const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
+                const float m3 = fmax3(m[9], l[30], l[31]);
+                mx = fmaxf(fmax3(m0, m1, m2), m3);
+            }
+            {
+                const unsigned long long nmx = f2_pack(-mx, -mx);
+#pragma unroll
+                for (int q = 0; q < WS_KC / 2; ++q) { lp[q] = f2_add(lp[q], nmx); f2_unpack(lp[q], l[2 * q], l[2 * q + 1]); }
+            }
             float run = 0.f;
             if (p.probs_out == nullptr && p.probs_f32 == nullptr) {
 #pragma unroll
-                for (int q = 0; q < WS_KC; ++q) { run += ex2_ftz(l[q] - mx); l[q] = run; }
+                for (int q = 0; q < WS_KC; ++q) { run += ex2_ftz(l[q]); l[q] = run; }
             } else {
                 float sum = 0.f;
 #pragma unroll
-                for (int q = 0; q < WS_KC; ++q) { l[q] = ex2_ftz(l[q] - mx); sum += l[q]; }
+                for (int q = 0; q < WS_KC; ++q) { l[q] = ex2_ftz(l[q]); sum += l[q]; }
                 const float inv = 1.f / sum;
                 if (valid && p.probs_out) {
 #pragma unroll
@@ -245,14 +312,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                 for (int q = 0; q < WS_KC; ++q) { run += l[q]; l[q] = run; }
             }
             if (!(run > 0.f) || !isfinite(run)) *p.status = -9;  // BMM_ERR_PROB
+            // z = #{q : cum_q <= u * total}: compare-to-mask (-1 / 0) and three-input integer adds
             const float target = u * run;
-            int z = 0;
+            int zneg = 0;
 #pragma unroll
-            for (int q = 0; q < WS_KC; ++q) z += (l[q] <= target) ? 1 : 0;
-            z = min(z, K - 1);
+            for (int q = 0; q < WS_KC; q += 2) zneg += set_le(l[q], target) + set_le(l[q + 1], target);
+            const int z = min(-zneg, K - 1);
             if (valid && zrow) zrow[i] = (uint8_t)(z + 1);
-            const long long nb = k / WS_NB;
-            if (nb > 0) ok = mbar_wait(b2_free + 8 * b, (uint32_t)((nb - 1) & 1));
+            if (k >= WS_NB) ok = mbar_wait(b2_free + 8 * b, ph_b ^ 1u);
             if (!ok) break;
             {
                 unsigned char *B2 = smem + L::B2_OFF + b * WS_B2_BYTES;
@@ -265,8 +332,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             }
             fence_async_smem();
             mbar_arrive(b2_full + 8 * b);
+            a += WS_NEPI; if (a >= WS_NA) { a -= WS_NA; ph_a ^= 1u; }
+            b += WS_NEPI; if (b >= WS_NB) { b -= WS_NB; ph_b ^= 1u; }
         }
     }
+    griddep_launch();   // the update kernel may be scheduled as CTAs drain; it waits on the tagged inbox words
     // ---- flush the counts: TMEM lane d of acc2 holds V_kd (d < P) or c_k (d == ONES) ----
     if (warp >= 8 && warp < 12) {
         const int t = tid - 256;
@@ -308,15 +378,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             __threadfence();
             const int n = K + K * P, world = p.x_world, s = p.x_seq[0] + j;
             const int *gcnt = p.counts + (size_t)(j & 1) * n;
+            const size_t off = x_slot_off(s, world, p.x_rank, (size_t)p.x_cap);
             for (int e = tid; e < n; e += WS_THREADS) {
                 const int v = __ldcg(gcnt + e);
-                for (int r = 0; r < world; ++r) p.x_peer[r][x_slot_off(s, world, p.x_rank, (size_t)p.x_cap) + e] = v;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < world) {
-                int *flag = p.x_peer[tid] + x_flag_off(s, world, p.x_rank, (size_t)p.x_cap);
-                asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(flag), "r"(s) : "memory");
+                for (int r = 0; r < world; ++r) x_store(p.x_peer[r] + off + e, v, s);   // (count, tag) in one 8-byte store
             }
         }
     }
@@ -330,9 +395,8 @@ cudaError_t launch_ws_nch(const BigParams &p, int j, int sm_count, cudaStream_t 
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     long long ctas = ntiles < sm_count ? ntiles : sm_count;
     if (ctas < 1) ctas = 1;
-    big_sweep_ws_kernel<NCH><<<(int)ctas, WS_THREADS, L::TOTAL, st>>>(p, j);
     g_launches++;
-    return cudaGetLastError();
+    return launch_pdl(big_sweep_ws_kernel<NCH>, dim3((unsigned)ctas), dim3(WS_THREADS), (size_t)L::TOTAL, st, p, j);
 }
 
 }  // namespace

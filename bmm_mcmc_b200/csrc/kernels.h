@@ -140,19 +140,50 @@ struct BigParams {
     // s0_k = sum_d log(1 - theta_kd), written by the update kernel so that the sweep's prologue is a copy
     unsigned char *ws_b1;             // [ws_b1_bytes(P)] or nullptr
     double *ws_s0;                    // [32]
-    // count exchange of an N-sharded run over peer memory (dist.cu).  x_world <= 1: the counts in `counts` are
-    // complete (single GPU, or already all-reduced by NCCL)
+    // Counts handed from the sweep kernel to the update kernel through an inbox of tagged words: over peer memory on
+    // an N-sharded run (dist.cu), through a local inbox (x_world = 1) on one GPU -- the tags make the hand-over
+    // self-synchronising, so the update kernel can be launched before the sweep kernel has drained.
+    // x_world = 0: the counts in `counts` are complete when the update kernel starts (other sweep kernels, NCCL)
     int x_world, x_rank;
     int x_fused;                      // the sweep kernel's last CTA pushes the counts itself
     unsigned long long x_cap;         // ints per inbox slot
-    int *const *x_peer;               // [x_world] every rank's inbox block as mapped here
-    const int *x_local;               // this rank's inbox block
+    int2 *const *x_peer;              // [x_world] every rank's inbox block as mapped here
+    const int2 *x_local;              // this rank's inbox block
     const int *x_seq;                 // x_seq[0] + j = exchange number of sweep j
     unsigned *x_done;                 // CTA ticket counter of the fused push (zero between launches)
 };
-// inbox addressing shared by producer and consumer: slot of `rank` for exchange number s, and its flag
+// Inbox of the count exchange: [2 parities][world][cap] words of (count, exchange number).  Every word carries
+// its own validity tag and is written with one 8-byte store, so neither side needs a fence or a separate flag
+// (the "LL" idea of NCCL's low-latency protocol): the consumer re-reads a word until its tag is the number it
+// waits for.
 __host__ __device__ inline size_t x_slot_off(int s, int world, int rank, size_t cap) { return ((size_t)(s & 1) * world + rank) * cap; }
-__host__ __device__ inline size_t x_flag_off(int s, int world, int rank, size_t cap) { return 2 * (size_t)world * cap + (size_t)(s & 1) * world + rank; }
+__device__ __forceinline__ void x_store(int2 *dst, int value, int s) {     // one 64-bit scalar store: single-copy atomic
+    const unsigned long long w = (unsigned long long)(unsigned)value | ((unsigned long long)(unsigned)s << 32);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst), "l"(w) : "memory");
+}
+__device__ __forceinline__ int2 x_load(const int2 *src) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+    return make_int2((int)(unsigned)w, (int)(unsigned)(w >> 32));
+}
+// Programmatic dependent launch: a kernel launched with launch_pdl may start while its predecessor in the stream is
+// still running; it must call griddep_wait() before touching anything the predecessor writes (the call returns once
+// the predecessor has completed and its writes are visible).  griddep_launch() lets the successor start early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st);   // seq[0] = seq[1]; seq[1] += n_sweeps
 size_t ws_b1_bytes(int P);
 cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st);   // operand image from w1 / w0 (initial state)
 bool big_tables_fit_smem(int K, int P, int precision);

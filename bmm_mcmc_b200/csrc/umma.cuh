@@ -93,6 +93,32 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// two fp32 lanes per instruction (FADD2 on sm_100a) and the three-input maximum (FMNMX3)
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// -1 when a <= b, else 0
+__device__ __forceinline__ int set_le(float a, float b) {
+    int r;
+    asm("set.le.s32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+
 // exp2 of a non-positive argument: one MUFU, denormal results flushed to zero
 __device__ __forceinline__ float ex2_ftz(float x) {
     float y;

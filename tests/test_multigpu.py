@@ -46,6 +46,16 @@ for prec in ("fp64", "fp32"):
 g = B.gibbs_full(X[lo:hi], 14, K, alpha=1.0, burnin=6, relabel=True, burnrelabel=3, seed=9, device=rank, precision="fp32",
                  grid_path=True, n_global=N, row_offset=lo)
 out["rel"] = {k: g[k] for k in ("z", "z_original", "permutations", "theta")}
+# a device-resident plan run three times: the captured sweep graph is replayed with fresh exchange numbers
+from bmm_mcmc_b200 import api, _lib
+ip = np.full((1, K), 1.0 / K); ith = np.ascontiguousarray(rng.uniform(0.2, 0.8, (1, P, K)))
+plan = api.Plan(_lib.SAMPLER_STICKBREAKING, X[lo:hi], 8, K, 1.0, 0.5, 0.5, 1.0, 1.0, 1, False, 0, seed=5, device=rank,
+                precision="fp32", grid_path=True, n_global=N, row_offset=lo, init_pi=ip, init_theta=ith)
+for _ in range(3):
+    plan.run()
+g = plan.fetch()
+plan.close()
+out["plan"] = {k: g[k][0] for k in ("z", "theta", "pi")}
 np.savez(os.path.join(os.environ["BMM_OUT"], "rank%d.npz" % rank), lo=lo, hi=hi,
          **{p + "_" + k: v for p, g in out.items() for k, v in g.items()})
 bdist.finalize()
@@ -76,6 +86,16 @@ def test_n_sharded_equals_unsharded(tmp_path, p2p):
         assert np.array_equal(z, g["z"]), prec
         for k in ("theta", "pi", "alpha", "counts"):
             assert np.array_equal(r[0][prec + "_" + k], g[k]) and np.array_equal(r[1][prec + "_" + k], g[k]), (prec, k)
+    from bmm_mcmc_b200 import api, _lib
+    ip = np.full((1, K), 1.0 / K); ith = np.ascontiguousarray(rng.uniform(0.2, 0.8, (1, P, K)))
+    plan = api.Plan(_lib.SAMPLER_STICKBREAKING, X, 8, K, 1.0, 0.5, 0.5, 1.0, 1.0, 1, False, 0, seed=5, precision="fp32",
+                    grid_path=True, init_pi=ip, init_theta=ith)
+    plan.run()
+    g = plan.fetch()
+    plan.close()
+    assert np.array_equal(np.concatenate([r[0]["plan_z"], r[1]["plan_z"]], axis=1), g["z"][0])
+    for k in ("theta", "pi"):
+        assert np.array_equal(r[0]["plan_" + k], g[k][0]) and np.array_equal(r[1]["plan_" + k], g[k][0]), k
     # relabelling on the sharded chain: the sweeps are bit-identical; the permutations come from all-reduced
     # costs whose float partial sums are grouped differently, so they agree wherever the optimum is not a
     # near-tie -- on this well-separated data everywhere -- and both ranks must hold the same ones
