@@ -32,7 +32,7 @@ METRIC = "allocation updates/sec (N*chains*sweeps/s)"
 # Chain-parallel workloads (independent chains, split across GPUs with no collective).
 # "c2" is BASELINE.json configs[1] and the default; the others are the remaining chain configs.
 WORKLOADS = {
-    "c2": dict(sampler="full", dataset="K3_N1000_P5", K=3, chains=1024, nsamples=1000, burnin=100, burnrelabel=50,
+    "c2": dict(sampler="full", dataset="K3_N1000_P5", K=3, chains=1024, nsamples=2000, burnin=200, burnrelabel=50,
                relabel=True, label="C2: gibbs_full K3_N1000_P5 (N=1000,P=5) K=3"),
     "collapsed": dict(sampler="collapsed", dataset="K3_N1000_P5", K=3, chains=1024, nsamples=300, burnin=30,
                       burnrelabel=10, relabel=False, label="gibbs_collapsed K3_N1000_P5 (N=1000,P=5) K=3 (north_star 100x target)"),
@@ -133,27 +133,60 @@ def init_states(chains, P, seed):
     return np.ascontiguousarray(ip), np.ascontiguousarray(th)
 
 
+def cpu_kind():
+    """'reference' when oracle/_ref/libbmm_ref.so (the reference's own src/*.cpp, compiled unmodified against the
+    header shim, oracle/build_ref.sh) is present, else 'port' (the oracle restatement)."""
+    try:
+        from oracle import pyref
+        return "reference" if pyref.available() else "port"
+    except Exception:
+        return "port"
+
+
 def cpu_chain(args):
-    """One oracle chain of the bench workload; returns (updates, seconds)."""
+    """One CPU chain of the bench workload through the reference's own compiled sampler (its registered .Call
+    symbol) -- or the oracle port when that library is absent; returns (updates, seconds)."""
     seed, nsamples, burnin, br = args
-    from oracle import pyoracle as O
     import bmm_mcmc_b200 as B
     from bmm_mcmc_b200.rcompat import RRng
     X = B.load_dataset(DATASET)
     N, P = X.shape
-    kw = dict(burnin=burnin, relabel=WL["relabel"], burnrelabel=br, seed=seed, use_ref=O.has_ref(), probes=False)
+    ref = cpu_kind() == "reference"
+    if ref:
+        from oracle import pyref as R
+        R.lib()
+    else:
+        from oracle import pyoracle as O
+        kw = dict(burnin=burnin, relabel=WL["relabel"], burnrelabel=br, seed=seed, use_ref=O.has_ref(), probes=False)
+    rel = WL["relabel"]
     if WL["sampler"] == "full":
         ip, th = init_states(1, P, 1000 + seed)
         t0 = time.perf_counter()
-        O.gibbs_full(X, ip[0], th[0].T, nsamples, K, **kw)
+        if ref:
+            R.gibbs_cpp(X, ip[0], th[0].T, nsamples, K, 0.0, 0.5, 0.5, 1.0, 1.0, burnin, rel, br, seed=seed)
+        else:
+            O.gibbs_full(X, ip[0], th[0].T, nsamples, K, **kw)
     elif WL["sampler"] == "collapsed":
         iz = RRng(1000 + seed).sample_int(K, N)
         t0 = time.perf_counter()
-        O.gibbs_collapsed(X, iz, nsamples, K, **kw)
+        if ref:
+            R.collapsed_gibbs_cpp(X, iz, nsamples, K, 0.0, 0.5, 0.5, 1.0, 1.0, burnin, rel, br, seed=seed)
+        else:
+            O.gibbs_collapsed(X, iz, nsamples, K, **kw)
     else:
         t0 = time.perf_counter()
-        O.gibbs_dp(X, nsamples, maxK=K, **kw)
+        if ref:
+            R.collapsed_gibbs_dp_cpp(X, nsamples, 0.0, 0.5, 0.5, 1.0, 1.0, burnin, rel, br, K, seed=seed)
+        else:
+            O.gibbs_dp(X, nsamples, maxK=K, **kw)
     return N * (nsamples - 1), time.perf_counter() - t0
+
+
+CPU_NOTE = {
+    "reference": "the reference's own src/*.cpp compiled unmodified (g++ -O2, R's default level) against a header-only "
+                 "Rcpp/Armadillo stand-in, called through its registered .Call symbol, console output sunk",
+    "port": "oracle/oracle.cpp, the line-faithful restatement (compiled reference library absent)",
+}
 
 
 def cpu_sample_shape():
@@ -171,11 +204,10 @@ def cpu_baseline_single(budget_s=12.0):
     while sec < budget_s and chains < 16:
         u, s = cpu_chain((chains, ns, burnin, br))
         upd += u; sec += s; chains += 1
-    from oracle import pyoracle as O
     return {"value": upd / sec, "unit": "allocation updates/s", "cores": 1,
-            "kind": "port", "assignment": "reference lp_solve" if O.has_ref() else "Hungarian port",
-            "sample": "%d chain(s) x %d sweeps of %s, relabel=%s burnrelabel=%d, %.1f s"
-                      % (chains, ns - 1, WL["label"], WL["relabel"], br, sec)}
+            "kind": cpu_kind(), "assignment": "reference lp_solve",
+            "sample": "%d chain(s) x %d sweeps of %s, relabel=%s burnrelabel=%d, %.1f s; %s"
+                      % (chains, ns - 1, WL["label"], WL["relabel"], br, sec, CPU_NOTE[cpu_kind()])}
 
 
 def run_reference(a):
@@ -187,8 +219,13 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     select_workload(a.workload)
     ns, burnin, br = cpu_sample_shape()
-    from oracle import pyoracle as O
-    O.lib()
+    kind = cpu_kind()
+    if kind == "reference":
+        from oracle import pyref
+        pyref.lib()
+    else:
+        from oracle import pyoracle as O
+        O.lib()
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores) as pool:
@@ -207,9 +244,9 @@ def run_reference(a):
         "config": {"workload": "%s, relabel=%s burnrelabel=%d; CPU sample: %d chains x %d sweeps per step"
                                % (WL["label"], WL["relabel"], br, cores, ns - 1)},
         "cpu_baseline": {"value": val, "unit": "allocation updates/s", "cores": cores,
-                         "kind": "port", "assignment": "reference lp_solve" if O.has_ref() else "Hungarian port",
-                         "sample": "one chain per core, %d cores x %d sweeps per step (reference is single-threaded; "
-                                   "R is not installed, so the line-faithful C++ oracle stands in)" % (cores, ns - 1)},
+                         "kind": kind, "assignment": "reference lp_solve",
+                         "sample": "one chain per core, %d cores x %d sweeps per step (the reference is single-threaded); %s"
+                                   % (cores, ns - 1, CPU_NOTE[kind])},
         "e2e": {"value": val, "unit": "allocation updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -276,19 +313,29 @@ def grid_init(K, P):
 
 
 def grid_cpu_baseline(w):
-    from oracle import pyoracle as O
+    """One reduced CPU chain of a grid workload: the compiled reference where it can run the shape (C4), the
+    oracle port with a stabilised softmax where the reference underflows to NaN (C5)."""
     N, ns, K, P = w["cpu_N"], w["cpu_ns"], w["K"], w["P"]
     X = synth_rows(0, N, P, K)
     Xi = ((X.bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(N, -1)[:, :P].astype(np.int32)
     ip, th = grid_init(K, P)
-    f = O.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else O.gibbs_full
-    t0 = time.perf_counter()
-    f(Xi, ip[0], th[0].T, ns, K, alpha=w["alpha"], burnin=1, seed=3, probes=False, **({"stabilise": True} if w.get("stabilise") else {}))
+    kind = "port" if w.get("stabilise") else cpu_kind()
+    if kind == "reference":
+        from oracle import pyref as R
+        f = R.gibbs_stickbreaking_cpp if w["sampler"] == "stickbreaking" else R.gibbs_cpp
+        R.lib()
+        t0 = time.perf_counter()
+        f(Xi, ip[0], th[0].T, ns, K, w["alpha"], 0.5, 0.5, 1.0, 1.0, 1, False, 1, seed=3)
+    else:
+        from oracle import pyoracle as O
+        f = O.gibbs_stickbreaking if w["sampler"] == "stickbreaking" else O.gibbs_full
+        t0 = time.perf_counter()
+        f(Xi, ip[0], th[0].T, ns, K, alpha=w["alpha"], burnin=1, seed=3, probes=False, **({"stabilise": True} if w.get("stabilise") else {}))
     sec = time.perf_counter() - t0
-    return {"value": N * (ns - 1) / sec, "unit": "allocation updates/s", "cores": 1, "kind": "port",
+    return {"value": N * (ns - 1) / sec, "unit": "allocation updates/s", "cores": 1, "kind": kind,
             "sample": "%s reduced to N=%d, %d sweeps (the reference's N x K x nsamples double cube cannot hold N=%g; "
-                      "per-update cost of the uncollapsed sampler does not depend on N), %.1f s"
-                      % (w["label"], N, ns - 1, w["N"], sec)}, sec
+                      "per-update cost of the uncollapsed sampler does not depend on N), %.1f s; %s"
+                      % (w["label"], N, ns - 1, w["N"], sec, CPU_NOTE[kind])}, sec
 
 
 def run_grid_reference(a):
@@ -297,8 +344,7 @@ def run_grid_reference(a):
     import multiprocessing as mp
     w = GRID_WORKLOADS[a.workload]
     cores = os.cpu_count() or 1
-    from oracle import pyoracle as O
-    O.lib()
+    kind = "port" if w.get("stabilise") else cpu_kind()
     ctx = mp.get_context("fork")
     tot_u, tot_s = 0, 0.0
     with ctx.Pool(cores) as pool:
@@ -315,7 +361,8 @@ def run_grid_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / max(a.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seed 17)",
         "config": {"workload": w["label"] + "; CPU sample: " + sample},
-        "cpu_baseline": {"value": val, "unit": "allocation updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "allocation updates/s", "cores": cores, "kind": kind,
+                         "sample": sample + "; " + CPU_NOTE[kind]},
         "e2e": {"value": val, "unit": "allocation updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
     return 0

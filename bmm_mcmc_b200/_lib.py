@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbmm_b200.so")
+LIB_PATH = os.environ.get("BMM_LIB") or os.path.join(_HERE, "libbmm_b200.so")   # BMM_LIB: A/B builds of the same ABI
 
 BMM_FP64, BMM_FP32 = 0, 1
 FLAG_STABLE_SOFTMAX, FLAG_COMPACT_Z, FLAG_NO_Z_HISTORY, FLAG_GRID_PATH, FLAG_X_PACKED, FLAG_NO_TENSOR = 1, 2, 4, 8, 16, 32

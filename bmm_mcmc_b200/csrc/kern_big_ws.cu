@@ -21,9 +21,18 @@
 namespace bmm {
 namespace {
 
-constexpr int WS_NA = 4;      // GEMM1 accumulators (64 TMEM columns each)
-constexpr int WS_NB = 4;      // one-hot stages
-constexpr int WS_NEPI = 3;    // epilogue warpgroups (4 at 80 registers/thread measured no faster)
+#ifndef WS_NA_CFG
+#define WS_NA_CFG 4
+#endif
+#ifndef WS_NB_CFG
+#define WS_NB_CFG 4
+#endif
+#ifndef WS_NEPI_CFG
+#define WS_NEPI_CFG 3
+#endif
+constexpr int WS_NA = WS_NA_CFG;      // GEMM1 accumulators (64 TMEM columns each)
+constexpr int WS_NB = WS_NB_CFG;      // one-hot stages
+constexpr int WS_NEPI = WS_NEPI_CFG;  // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
 constexpr int WS_CHUNK = 2048;
 constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
@@ -218,6 +227,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         // words are handed out by shuffles, instead of every lane evaluating its own block for every tile.
         const bool shared_rng = (p.row_offset & 3) == 0;
         uint4 rnd4 = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t prevz = 0xFFFFFFFFu;       // the label this thread last stored in each of the (at most 4) one-hot stages
+        static_assert(WS_NB <= 4, "prevz holds one byte per one-hot stage");
         int a = e % WS_NA, b = e % WS_NB;                       // tile k uses accumulator k % NA, one-hot stage k % NB
         uint32_t ph_a = (uint32_t)((e / WS_NA) & 1), ph_b = (uint32_t)((e / WS_NB) & 1);
         int it = 0;
@@ -282,10 +293,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
 #pragma unroll
                 for (int q = 0; q < WS_KC / 2; ++q) { lp[q] = f2_add(lp[q], nmx); f2_unpack(lp[q], l[2 * q], l[2 * q + 1]); }
             }
+            // Unnormalised probabilities e_q = 2^(l_q - max) and their prefix sums.  The draw needs
+            // z = #{q : e_0 + ... + e_q <= u * total}; the prefix sums are kept per group of 8 (four independent
+            // dependency chains instead of one of 32) and each group is compared with the target minus the mass
+            // of the groups before it.
             float run = 0.f;
+            float off[WS_KC / 8];        // mass of the groups before group g
             if (p.probs_out == nullptr && p.probs_f32 == nullptr) {
 #pragma unroll
-                for (int q = 0; q < WS_KC; ++q) { run += ex2_ftz(l[q]); l[q] = run; }
+                for (int g = 0; g < WS_KC / 8; ++g) {
+                    float c = 0.f;
+#pragma unroll
+                    for (int q = 8 * g; q < 8 * g + 8; ++q) { c += ex2_ftz(l[q]); l[q] = c; }
+                }
+#pragma unroll
+                for (int g = 0; g < WS_KC / 8; ++g) { off[g] = run; run += l[8 * g + 7]; }
             } else {
                 float sum = 0.f;
 #pragma unroll
@@ -309,26 +331,46 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < WS_KC; ++q) { run += l[q]; l[q] = run; }
+                for (int g = 0; g < WS_KC / 8; ++g) {
+                    float c = 0.f;
+#pragma unroll
+                    for (int q = 8 * g; q < 8 * g + 8; ++q) { c += l[q]; l[q] = c; }
+                }
+#pragma unroll
+                for (int g = 0; g < WS_KC / 8; ++g) { off[g] = run; run += l[8 * g + 7]; }
             }
             if (!(run > 0.f) || !isfinite(run)) *p.status = -9;  // BMM_ERR_PROB
-            // z = #{q : cum_q <= u * total}: compare-to-mask (-1 / 0) and three-input integer adds
+            // d_q = (target - off_g) - c_q, two per FFMA2; its sign bit says "not counted" and is shifted into a per-group
+            // mask with one funnel shift per element (a compare + select + add costs three)
             const float target = u * run;
-            int zneg = 0;
+            const unsigned long long neg1 = f2_pack(-1.f, -1.f);
+            int over = 0;
 #pragma unroll
-            for (int q = 0; q < WS_KC; q += 2) zneg += set_le(l[q], target) + set_le(l[q + 1], target);
-            const int z = min(-zneg, K - 1);
+            for (int g = 0; g < WS_KC / 8; ++g) {
+                const float tg = target - off[g];
+                const unsigned long long tg2 = f2_pack(tg, tg);
+                uint32_t mask = 0u;
+#pragma unroll
+                for (int q = 8 * g; q < 8 * g + 8; q += 2) {
+                    float d0, d1;
+                    f2_unpack(f2_fma(f2_pack(l[q], l[q + 1]), neg1, tg2), d0, d1);
+                    mask = __funnelshift_l(__float_as_uint(d0), mask, 1);
+                    mask = __funnelshift_l(__float_as_uint(d1), mask, 1);
+                }
+                over += __popc(mask);
+            }
+            const int z = min(WS_KC - over, K - 1);
             if (valid && zrow) zrow[i] = (uint8_t)(z + 1);
             if (k >= WS_NB) ok = mbar_wait(b2_free + 8 * b, ph_b ^ 1u);
             if (!ok) break;
-            {
-                unsigned char *B2 = smem + L::B2_OFF + b * WS_B2_BYTES;
-                const uint32_t h = valid ? ((z & 1) ? 0x3C000000u : 0x3C00u) : 0u;
-                const int wsel = (z & 7) >> 1, csel = z >> 3;
-                const uint4 hot = make_uint4(wsel == 0 ? h : 0u, wsel == 1 ? h : 0u, wsel == 2 ? h : 0u, wsel == 3 ? h : 0u);
-#pragma unroll
-                for (int cc = 0; cc < WS_KC / 8; ++cc)
-                    *(uint4 *)(B2 + cc * WS_CHUNK + t * 16) = (csel == cc) ? hot : make_uint4(0u, 0u, 0u, 0u);
+            {   // one-hot row of this observation in stage b: clear the entry this thread set there last time (the
+                // stages start zeroed and row t of a stage is only ever written by this thread), set the new one
+                unsigned char *row = smem + L::B2_OFF + b * WS_B2_BYTES + t * 16;
+                const uint32_t pz = (prevz >> (8 * b)) & 0xFFu;
+                if (pz != 0xFFu) *(unsigned short *)(row + (pz >> 3) * WS_CHUNK + (pz & 7u) * 2) = 0;
+                const uint32_t nz = valid ? (uint32_t)z : 0xFFu;
+                if (valid) *(unsigned short *)(row + (z >> 3) * WS_CHUNK + (z & 7) * 2) = 0x3C00;
+                prevz = (prevz & ~(0xFFu << (8 * b))) | (nz << (8 * b));
             }
             fence_async_smem();
             mbar_arrive(b2_full + 8 * b);

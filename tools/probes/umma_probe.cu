@@ -17,6 +17,14 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
+// 8-bit operands (e4m3 x e4m3 -> f32), K = 32 per instruction
+__device__ __forceinline__ void umma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
@@ -32,7 +40,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 
 // mode 0: K-major A (LBO 2048, SBO 128) x K-major B;  mode 1: MN-major A and B (LBO 128, SBO 2048)
 // nacc: number of distinct accumulators the MMAs rotate over (1 = fully dependent chain)
-template <int N, int MODE, int NMMA, int NACC>
+template <int N, int MODE, int NMMA, int NACC, int M = 128, int F8 = 0>
 __global__ void probe(int reps, long long *out) {
     constexpr int mode = MODE;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -54,7 +62,7 @@ __global__ void probe(int reps, long long *out) {
     const uint32_t tm = slot;
     if (threadIdx.x == 0) {
         const uint32_t a0 = smem_u32(smem), b0 = a0 + 48 * 1024;
-        const uint32_t idesc = umma_idesc(128, N, mode, mode);
+        const uint32_t idesc = F8 ? umma_idesc_f8(M, N, mode, mode) : umma_idesc(M, N, mode, mode);
         long long best = 1ll << 60;
         for (int r = 0; r < reps; ++r) {
             long long t0 = clock64();
@@ -63,7 +71,8 @@ __global__ void probe(int reps, long long *out) {
                 const uint32_t off = (m & 3) * (mode ? 256 : 4096);
                 const uint64_t da = mode ? umma_desc(a0 + off, 128, 2048) : umma_desc(a0 + off, 2048, 128);
                 const uint64_t db = mode ? umma_desc(b0 + off, 128, 2048) : umma_desc(b0 + (m & 3) * 2 * (N * 16), N * 16, 128);
-                umma(tm + (uint32_t)((m % NACC) * N), da, db, idesc, m >= NACC);
+                if (F8) umma_f8(tm + (uint32_t)((m % NACC) * N), da, db, idesc, m >= NACC);
+                else umma(tm + (uint32_t)((m % NACC) * N), da, db, idesc, m >= NACC);
             }
             commit(smem_u32(&bar));
             mbar_wait(smem_u32(&bar), r & 1);
@@ -81,15 +90,15 @@ __global__ void probe(int reps, long long *out) {
 }
 
 
-template <int N, int MODE, int NMMA, int NACC>
+template <int N, int MODE, int NMMA, int NACC, int M = 128, int F8 = 0>
 void run(long long *d) {
     long long h;
-    cudaFuncSetAttribute(probe<N, MODE, NMMA, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    probe<N, MODE, NMMA, NACC><<<1, 128, 96 * 1024>>>(20, d);
+    cudaFuncSetAttribute(probe<N, MODE, NMMA, NACC, M, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    probe<N, MODE, NMMA, NACC, M, F8><<<1, 128, 96 * 1024>>>(20, d);
     cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+    if (e != cudaSuccess) { printf("M %d f8 %d mode %d N %d: error %s\n", M, F8, MODE, N, cudaGetErrorString(e)); cudaGetLastError(); return; }
     cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%d %3d %d %2d %6lld %7.1f\n", MODE, N, NACC, NMMA, h, (double)h / NMMA);
+    printf("%d %3d %d %2d %6lld %7.1f   M=%d %s\n", MODE, N, NACC, NMMA, h, (double)h / NMMA, M, F8 ? "e4m3 K=32" : "bf16 K=16");
 }
 template <int N, int MODE>
 void runN(long long *d) {
@@ -101,5 +110,9 @@ int main() {
     printf("mode N nacc nmma cycles cycles/mma\n");
     runN<16, 0>(d); runN<32, 0>(d); runN<64, 0>(d); runN<96, 0>(d); runN<128, 0>(d);
     runN<32, 1>(d); runN<64, 1>(d); runN<128, 1>(d);
+    // M = 64 and 8-bit operands (round 2: candidates for the count contraction)
+    run<32, 1, 32, 1, 64, 0>(d); run<32, 0, 32, 1, 64, 0>(d); run<64, 0, 32, 1, 64, 0>(d);
+    run<32, 0, 32, 1, 128, 1>(d); run<32, 0, 32, 1, 64, 1>(d); run<64, 0, 32, 1, 128, 1>(d);
+    run<32, 1, 32, 1, 128, 1>(d); run<32, 1, 32, 1, 64, 1>(d);
     return 0;
 }
