@@ -286,7 +286,7 @@ def synth_rows(lo, hi, P, K_true, seed=17, chunk=None):
     from bmm_mcmc_b200 import PackedX
     chunk = chunk or (500_000 if P <= 64 else 16_384)
     th = np.random.default_rng([seed, 0]).uniform(0.1, 0.9, (K_true, P)).astype(np.float32)
-    thq = np.clip(np.round(th * 256.0), 1, 255).astype(np.uint8)      # large P: 8-bit thresholds, 1 B of randomness per bit
+    thq = np.clip(np.round(th * 256.0), 1, 255).astype(np.uint8)      # 8-bit thresholds, 1 B of randomness per bit
     W = (P + 31) // 32
     out = np.zeros((hi - lo, W), dtype=np.uint32)
     c0 = lo // chunk
@@ -294,10 +294,7 @@ def synth_rows(lo, hi, P, K_true, seed=17, chunk=None):
         a0, a1 = c0 * chunk, (c0 + 1) * chunk
         rng = np.random.default_rng([seed, 1 + c0])
         z = rng.integers(0, K_true, chunk)
-        if P <= 64:
-            x = rng.random((chunk, P), dtype=np.float32) < th[z]
-        else:
-            x = rng.integers(0, 256, (chunk, P), dtype=np.uint8) < thq[z]
+        x = rng.integers(0, 256, (chunk, P), dtype=np.uint8) < thq[z]
         s0, s1 = max(a0, lo), min(a1, hi)
         out[s0 - lo:s1 - lo] = PackedX.pack(x[s0 - a0:s1 - a0]).bits
         c0 += 1
@@ -513,6 +510,115 @@ def run_grid(a):
     return 0
 
 
+def _max_over_ranks(x, dist):
+    if not dist:
+        return x
+    import torch
+    t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sharded_leg(rank, world, local, dist, steps=3, warmup=2):
+    """The path that communicates (BASELINE configs[3], north_star's multi-GPU deliverable): ONE stick-breaking chain
+    over N = 1e7 observations, rows block-partitioned over the ranks, per-sweep count exchange (stickbreaking.cpp:164-194
+    counts summed over ranks).  Short runs, relabelling off and on; device-timed, max over ranks."""
+    from bmm_mcmc_b200 import _lib, api, dist as bdist
+    L = _lib.lib()
+    w = GRID_WORKLOADS["c4"]
+    N, P, K = w["N"], w["P"], w["K"]
+    p2p = bdist.init(rank, world, local)
+    lo, hi = bdist.shard_rows(N, world, rank)
+    X = synth_rows(lo, hi, P, K)
+    ip, th = grid_init(K, P)
+    shard = dict(n_global=N, row_offset=lo) if world > 1 else {}
+    pk, _ = peaks()
+    out = {"workload": "C4: gibbs_stickbreaking synthetic N=1e7 P=64 maxK=32, alpha=1, rows sharded over %d GPU(s)" % world,
+           "rows_per_gpu": hi - lo, "scaling": "strong",
+           "exchange": ("tagged 8-byte words pushed over IPC-mapped NVLink peer memory by the sweep kernel's last CTA, "
+                        "summed by the parameter-update kernel" if p2p else ("NCCL all-reduce" if world > 1 else "none (one GPU)")),
+           "comm_nranks": world}
+    for name, ns, burnin, relabel, br in (("relabel_off", 31, 1, False, 0), ("relabel_on", 26, 6, True, 1)):
+        plan = api.Plan(_lib.SAMPLER_STICKBREAKING, X, ns, K, chains=1, seed=2026, device=local, init_pi=ip, init_theta=th,
+                        precision="fp32", compact_z=True, grid_path=True, alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0,
+                        burnin=burnin, relabel=relabel, burnrelabel=br, **shard)
+        clocks = ClockSampler(local)
+        clocks.launch()
+        for _ in range(warmup):
+            plan.run(); plan.sync()
+        if dist:
+            dist.barrier()
+        clocks.start()
+        l0 = L.bmm_launch_count()
+        dev_ms, kern = 0.0, np.zeros(4)
+        for _ in range(steps):
+            plan.run(); plan.sync()
+            dev_ms += plan.elapsed_ms()[0]
+            kern += np.array(plan.kernel_ms())
+        if dist:
+            dist.barrier()
+        clk = clocks.stop()
+        launches = int(L.bmm_launch_count() - l0)
+        plan.check()
+        plan.close()
+        dev_ms = _max_over_ranks(dev_ms, dist)
+        sweeps = (ns - 1) * steps
+        sweep_us = 1e3 * kern[0] / sweeps
+        other_us = 1e3 * (kern[1]) / sweeps
+        n_local = hi - lo
+        bytes_upd = (P + 7) // 8 + 1 + (2 * K * 4 if relabel else 0)       # SURVEY 8d: X row + z (+ Q read and write)
+        out[name] = {
+            "value": N * sweeps / (dev_ms / 1e3), "unit": "allocation updates/s", "nsamples": ns, "burnin": burnin,
+            "steps": steps, "ms_per_sweep": dev_ms / sweeps, "sweep_kernel_us": sweep_us,
+            "exchange_us": other_us, "exchange_note": "everything of a sweep that is not the z-sweep kernel: count exchange + "
+            "parameter update" + (" + cost contraction, assignment, Q update" if relabel else "") + ", per sweep, this rank",
+            "hbm_frac": n_local * bytes_upd / (dev_ms / 1e3 / sweeps) / 1e9 / pk["hbm_gbs"],
+            "hbm_bytes_per_update": bytes_upd,
+            "tensor_frac": 2.0 * K * P * n_local / (sweep_us * 1e-6) / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+            "gpu_launches": launches, "clocks": clk}
+    bdist.finalize()
+    return out
+
+
+def collapsed_leg(rank, world, local, dist, steps=3, warmup=2):
+    """north_star's >= 100x target workload: gibbs_collapsed on K3_N1000_P5, 1024 chains per GPU, device-timed."""
+    import bmm_mcmc_b200 as B
+    from bmm_mcmc_b200 import _lib, api
+    from bmm_mcmc_b200.rcompat import RRng
+    w = WORKLOADS["collapsed"]
+    X = B.load_dataset(w["dataset"])
+    N, P = X.shape
+    Kc, C_, ns, burnin = w["K"], w["chains"], w["nsamples"], w["burnin"]
+    iz = np.ascontiguousarray(np.random.default_rng(1 + rank).integers(1, Kc + 1, (C_, N)), dtype=np.int32)
+    iz[0] = RRng(1 + rank).sample_int(Kc, N)
+    plan = api.Plan(_lib.SAMPLER_COLLAPSED, X, ns, Kc, chains=C_, seed=2026, device=local, chain_offset=rank * C_, init_z=iz,
+                    alpha=0.0, beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=burnin, relabel=False, burnrelabel=w["burnrelabel"])
+    for _ in range(warmup):
+        plan.run(); plan.sync()
+    if dist:
+        dist.barrier()
+    dev_ms = 0.0
+    for _ in range(steps):
+        plan.run(); plan.sync()
+        dev_ms += plan.elapsed_ms()[0]
+    plan.check()
+    plan.close()
+    dev_ms = _max_over_ranks(dev_ms, dist)
+    val = N * C_ * (ns - 1) * steps * world / (dev_ms / 1e3)
+    out = {"workload": "%s, %d chains/GPU, nsamples=%d" % (w["label"], C_, ns), "value": val, "unit": "allocation updates/s",
+           "ms_per_step": dev_ms / steps, "scaling": "weak"}
+    if rank == 0 and world == 1:
+        global WL, DATASET, K, NSAMPLES, BURNIN, BURNRELABEL
+        keep = (WL, DATASET, K, NSAMPLES, BURNIN, BURNRELABEL)
+        select_workload("collapsed")
+        cpu = cpu_baseline_single(budget_s=6.0)
+        WL, DATASET, K, NSAMPLES, BURNIN, BURNRELABEL = keep
+        out["cpu_baseline"] = cpu
+        out["ratio_vs_one_cpu_core"] = val / cpu["value"]
+        out["ratio_vs_all_host_cores_ideal"] = val / (cpu["value"] * (os.cpu_count() or 1))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,6 +631,7 @@ def main():
     ap.add_argument("--chains", type=int, default=None)
     ap.add_argument("--nsamples", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.sharded / extra.collapsed_1024 on the default line")
     a = ap.parse_args()
     if a.workload in GRID_WORKLOADS:
         if a.impl == "reference":
@@ -684,6 +791,14 @@ def main():
                   "kernels_ms": {"sweeps_pre_burnin": kern[0] / a.steps, "stephens_batch": kern[1] / a.steps,
                                  "sweeps_post_burnin": kern[2] / a.steps, "finalize_layout": kern[3] / a.steps}},
     }
+    if a.workload == "c2" and not a.no_extra:
+        # the other two north_star workloads ride on every default line, so the driver's 1 -> 8 runs carry them
+        import gc
+        del bufs, r
+        gc.collect()
+        L.bmm_release_cache()
+        line["extra"]["sharded"] = sharded_leg(rank, world, local, dist)
+        line["extra"]["collapsed_1024"] = collapsed_leg(rank, world, local, dist)
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     elif rank == 0:

@@ -5,3 +5,4 @@ sampling itself runs in hand-written sm_100a CUDA behind the C ABI of include/bm
 """
 from .api import gibbs_full, gibbs_collapsed, gibbs_dp, gibbs_stickbreaking, Plan, PackedX  # noqa: F401
 from .rcompat import RRng, load_dataset, DATASET_NAMES  # noqa: F401
+from .plot import plot_gibbs, plot_alpha  # noqa: F401

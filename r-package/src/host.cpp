@@ -134,3 +134,15 @@ IntegerMatrix my_lpsolve(NumericMatrix cost) {
     if (bmm_assign(K, 1, cost.begin(), sol.begin()) != BMM_OK) stop(bmm_last_error());
     return sol;
 }
+
+// rdirichlet_cpp (reference: src/full_gibbs.cpp:10-27, registered as _bmmmcmc_rdirichlet_cpp,
+// src/RcppExports.cpp:56-64): one Dirichlet(alpha_m) draw as a column vector.  The Philox key comes from
+// options(bmm.seed) or, when that is NULL, from R's RNG, so set.seed() keeps it reproducible.
+// [[Rcpp::export]]
+NumericMatrix rdirichlet_cpp(NumericVector alpha_m) {
+    const int K = alpha_m.size();
+    if (K < 1) stop("alpha_m must not be empty");
+    NumericMatrix out(K, 1);                       // arma::vec wraps as a K x 1 matrix in the reference
+    if (bmm_rdirichlet(K, alpha_m.begin(), philox_seed(), out.begin()) != BMM_OK) stop(bmm_last_error());
+    return out;
+}
