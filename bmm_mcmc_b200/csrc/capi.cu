@@ -695,6 +695,7 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     bmm::CollapsedParams &q = pl->cp;
     q.N = N; q.P = P; q.K = K; q.W = W;
     q.nsamples = ns; q.burnin = a.burnin; q.relabel = pl->relabel; q.burnrelabel = a.burnrelabel; q.dp = dp;
+    q.fp32 = a.precision == BMM_FP32;
     q.alpha0 = a.alpha; q.beta = a.beta; q.gamma = a.gamma; q.a = a.a; q.b = a.b;
     q.seed = a.seed; q.chain_offset = a.chain_offset; q.flags = a.flags;
     q.xbits = pl->xbits.as<uint32_t>();

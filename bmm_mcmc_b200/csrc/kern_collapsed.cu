@@ -372,6 +372,183 @@ __global__ void __launch_bounds__(32) collapsed_fast_kernel(const CollapsedParam
     if (lane == 0) p.alpha_cur[c] = alpha_sh;
 }
 
+// ------------------------------------------------------------------------------------------------
+// finite-K collapsed Gibbs in PRODUCT form (Philox mode, K <= 32, P <= 8).  The conditional of
+// collapsed_gibbs.cpp:105-130 is exp(log(N_k + a/K) - log(N - 1 + a) + sum_d [log(beta + S_kd) or
+// log(gamma + N_k - S_kd)] - P log(beta + gamma + N_k)); up to the factor 1 / (N - 1 + a), which is the same
+// for every cluster and cancels in the normalisation, that is
+//     (N_k + a/K) * prod_d (beta + S_kd  |  gamma + N_k - S_kd) / (beta + gamma + N_k)^P
+// -- a handful of multiplications instead of P + 2 table look-ups, P dependent additions and an fp64 exp.
+// Lane k keeps beta + S_kd and gamma + N_k - S_kd as reals in registers (they change by exactly +-1) and the
+// reciprocal (beta + gamma + n)^-P comes from a table in shared memory.  The draw gathers the K weights into
+// every lane when K <= 4 (no dependent shuffle chain), else uses the butterfly sum and scan.
+// R = double agrees with the log form to ~1e-15 relative; R = float (precision fp32) to ~5e-7.
+// The replay mode keeps the log-form kernels: bit-exact parity is defined on the reference's operation order.
+// ------------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ R shfl_r(R v, int src);
+template <> __device__ __forceinline__ double shfl_r<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ float shfl_r<float>(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <typename R, int PM, int WIDTH>
+__global__ void __launch_bounds__(32) collapsed_prod_kernel(const CollapsedParams p) {
+    extern __shared__ __align__(16) char smem_raw[];
+    __shared__ double alpha_sh;
+    CSmem s;
+    const size_t base_bytes = collapsed_layout(p, smem_raw, &s);
+    FastTabs tb;
+    collapsed_fast_extra(p, smem_raw + base_bytes, &tb);
+    R *rbgp = (R *)tb.logA;                         // (beta + gamma + n)^-P, n = 0..N (the table area of the log-form kernel)
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const int K = p.K, P = p.P, N = p.N, W = p.W, ns = p.nsamples, P1 = P + 1;
+    const uint32_t chain = (uint32_t)(p.chain_offset + c);
+    const size_t NK = (size_t)N * K;
+
+    for (int e = lane; e < N; e += 32) { tb.xs[e] = (uint8_t)(p.xbits[(size_t)e * W] & 0xFFu); s.z[e] = p.z_cur[(size_t)c * N + e]; }
+    for (int n = lane; n <= N; n += 32) {
+        const double x = p.beta + p.gamma + n;
+        double r = 1.0;
+        for (int d = 0; d < P; ++d) r *= x;
+        rbgp[n] = (R)(1.0 / r);
+    }
+    for (int k = lane; k < K; k += 32) s.perm[k] = k;
+    int S[PM], Nk = 0;
+#pragma unroll
+    for (int d = 0; d < PM; ++d) S[d] = (lane < K && d < P) ? p.cnt[((size_t)c * K + lane) * P1 + d] : 0;
+    if (lane < K) Nk = p.cnt[((size_t)c * K + lane) * P1 + P];
+    R SB[PM], G[PM];                                 // beta + S_kd, gamma + N_k - S_kd; 1 for the padding d >= P
+#pragma unroll
+    for (int d = 0; d < PM; ++d) {
+        SB[d] = d < P ? (R)(p.beta + S[d]) : (R)1;
+        G[d] = d < P ? (R)(p.gamma + (Nk - S[d])) : (R)1;
+    }
+    if (lane == 0) alpha_sh = p.alpha_cur[c];
+    __syncthreads();
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    const uint2 key = make_uint2((uint32_t)p.seed, chain);
+    const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
+
+    for (int j = p.j_begin; j < p.j_end; ++j) {
+        const R aK = (R)(alpha_sh / K);
+        uint8_t *zrow = p.zhist + ((size_t)c * ns + j) * N;
+        double *stash_dst = stash_target(p, c, j);
+        const bool need_probs = stash_dst || p.probs_out;
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        int a = s.z[0];
+        uint32_t xb = tb.xs[0];
+        for (int i = 0; i < N; ++i) {
+            if ((i & 63) == 0)
+                rnd = philox4x32_10(make_uint4((uint32_t)((i >> 1) + lane), 0u, sid, (uint32_t)j), key);
+            const int inext = i + 1 < N ? i + 1 : i;
+            const int a_next = s.z[inext];
+            const uint32_t xb_next = tb.xs[inext];
+            // this update's uniform does not depend on the weights: fetch it first
+            const int src = (i & 63) >> 1;
+            const uint32_t w0 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.z : rnd.x, src);
+            const uint32_t w1 = __shfl_sync(0xffffffffu, (i & 1) ? rnd.w : rnd.y, src);
+            const R u = (R)u53(w0, w1);
+            const int own = (lane == a);
+            const int Nk1 = Nk - own;
+            const R ownr = own ? (R)1 : (R)0;
+            R v = (R)0;
+            {
+                R f[PM];
+#pragma unroll
+                for (int d = 0; d < PM; ++d) f[d] = d < P ? (((xb >> d) & 1u) ? SB[d] : G[d]) - ownr : (R)1;
+#pragma unroll
+                for (int w = PM / 2; w >= 1; w >>= 1)
+#pragma unroll
+                    for (int d = 0; d < w; ++d) f[d] *= f[d + w];
+                const R head = ((R)Nk1 + aK) * rbgp[Nk1 > 0 ? Nk1 : 0];
+                // empty cluster: probability exactly 0 (collapsed_gibbs.cpp:104,131-133)
+                v = (lane < K && Nk1 > 0) ? head * f[0] : (R)0;
+            }
+            R tot;
+            int z;
+            if (WIDTH <= 4) {
+                R g[WIDTH];
+#pragma unroll
+                for (int k = 0; k < WIDTH; ++k) g[k] = shfl_r<R>(v, k);
+                R cum[WIDTH];
+                cum[0] = g[0];
+#pragma unroll
+                for (int k = 1; k < WIDTH; ++k) cum[k] = cum[k - 1] + g[k];
+                tot = cum[WIDTH - 1];
+                const R target = u * tot;
+                z = 0;
+#pragma unroll
+                for (int k = 0; k < WIDTH - 1; ++k) z += (k < K - 1 && !(target < cum[k])) ? 1 : 0;
+            } else {
+                tot = v;
+#pragma unroll
+                for (int off = 1; off < WIDTH; off <<= 1) tot += shfl_r<R>(tot, lane ^ off);
+                const R target = u * tot;
+                R cum = v;                                    // inclusive prefix sums over the lanes
+#pragma unroll
+                for (int off = 1; off < WIDTH; off <<= 1) {
+                    const R t = shfl_r<R>(cum, lane >= off ? lane - off : lane);
+                    if (lane >= off) cum += t;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, lane < K - 1 && target < cum);
+                z = hit ? __ffs(hit) - 1 : K - 1;
+            }
+            if (!(tot > (R)0) || !isfinite(tot)) { if (lane == 0) p.status[c] = -9; }
+            if (need_probs && lane < K) {
+                const double pr = (double)v / (double)tot;
+                if (stash_dst) stash_dst[i + (size_t)N * lane] = pr;
+                if (p.probs_out) p.probs_out[((size_t)c * ns + j) * NK + i + (size_t)N * lane] = pr;
+            }
+            if (z != a) {
+                const int da = (lane == z) - (lane == a);     // +1 for the new cluster, -1 for the old one
+                const R dr = (R)da;
+                Nk += da;
+#pragma unroll
+                for (int d = 0; d < PM; ++d) {
+                    if (d < P) {
+                        const int xd = (int)((xb >> d) & 1);
+                        S[d] += da * xd;
+                        if (xd) SB[d] += dr; else G[d] += dr;
+                    }
+                }
+                if (lane == 0) s.z[i] = (uint8_t)z;
+            }
+            if (lane == 0) zrow[i] = (uint8_t)(z + 1);
+            a = a_next;
+            xb = xb_next;
+        }
+        if (lane < K) {
+#pragma unroll
+            for (int d = 0; d < PM; ++d) if (d < P) s.cnt[lane * P1 + d] = S[d];
+            s.cnt[lane * P1 + P] = Nk;
+        }
+        __syncwarp();
+        collapsed_after_sweep(p, s, c, j, &alpha_sh, K, nullptr, 0);
+    }
+    if (lane < K) {
+#pragma unroll
+        for (int d = 0; d < PM; ++d) if (d < P) p.cnt[((size_t)c * K + lane) * P1 + d] = S[d];
+        p.cnt[((size_t)c * K + lane) * P1 + P] = Nk;
+    }
+    for (int e = lane; e < N; e += 32) p.z_cur[(size_t)c * N + e] = s.z[e];
+    if (lane == 0) p.alpha_cur[c] = alpha_sh;
+}
+
+template <typename R, int WIDTH>
+cudaError_t launch_prod_w(const CollapsedParams &p, int n_chains, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(collapsed_prod_kernel<R, 8, WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    collapsed_prod_kernel<R, 8, WIDTH><<<n_chains, 32, smem, st>>>(p);
+    g_launches++;
+    return cudaGetLastError();
+}
+template <typename R>
+cudaError_t launch_prod(const CollapsedParams &p, int n_chains, size_t smem, cudaStream_t st) {
+    if (p.K <= 2) return launch_prod_w<R, 2>(p, n_chains, smem, st);
+    if (p.K <= 4) return launch_prod_w<R, 4>(p, n_chains, smem, st);
+    if (p.K <= 8) return launch_prod_w<R, 8>(p, n_chains, smem, st);
+    if (p.K <= 16) return launch_prod_w<R, 16>(p, n_chains, smem, st);
+    return launch_prod_w<R, 32>(p, n_chains, smem, st);
+}
+
 template <int WIDTH>
 cudaError_t launch_fast_w(const CollapsedParams &p, int n_chains, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(collapsed_fast_kernel<8, WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -647,9 +824,15 @@ cudaError_t launch_collapsed(const CollapsedParams &p, int n_chains, cudaStream_
     // chain and 1.01e9 vs 0.86e9 for 1024 chains, so it is used whenever the shape fits (K <= 32, P <= 8).
     // BMM_COLLAPSED_KERNEL=fast|generic overrides (the parity tests run both).
     const char *force = getenv("BMM_COLLAPSED_KERNEL");
-    const bool want_fast = force ? force[0] == 'f' : true;
+    const bool want_fast = force ? force[0] != 'g' : true;
     if (want_fast && collapsed_fast_ok(p)) {
         smem += collapsed_fast_extra(p, (char *)0, nullptr);
+        // Philox mode: the product-form kernel (no exp, no log tables); replay keeps the reference's operation order.
+        // BMM_COLLAPSED_KERNEL=log keeps the log form in Philox mode too (A/B).
+        if (!p.ru && !(force && force[0] == 'l')) {
+            // the chain-parallel fp32 variant is opt-in through precision = fp32
+            return p.fp32 ? launch_prod<float>(p, n_chains, smem, st) : launch_prod<double>(p, n_chains, smem, st);
+        }
         if (p.K <= 2) return launch_fast_w<2>(p, n_chains, smem, st);
         if (p.K <= 4) return launch_fast_w<4>(p, n_chains, smem, st);
         if (p.K <= 8) return launch_fast_w<8>(p, n_chains, smem, st);

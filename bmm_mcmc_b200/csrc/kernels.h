@@ -75,6 +75,7 @@ struct CollapsedParams {
     int N, P, K, W;               // K = maxK for dp
     int nsamples, burnin, relabel, burnrelabel, dp;
     int j_begin, j_end;
+    int fp32;                     // BMM_FP32: single-precision weights in the product-form kernel
     double alpha0, beta, gamma, a, b;
     unsigned long long seed;
     int chain_offset;

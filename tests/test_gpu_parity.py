@@ -177,6 +177,27 @@ def test_collapsed_replay(oracle, datasets, monkeypatch, name, K, relabel, alpha
         _close(g["Q_final"], r["Q_final"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("name,K", [("K2_N100_P5", 2), ("K3_N1000_P5", 3), ("K2_N1000_P5", 7), ("K3_N1000_P5", 20)])
+def test_collapsed_product_form_equals_log_form(datasets, monkeypatch, name, K):
+    """Philox mode runs the conditional of collapsed_gibbs.cpp:105-130 in product form (no exp, no log tables).
+    Same seed, same uniforms: the probabilities equal the log-form kernel's to 1e-12 relative in double (the two
+    differ only by rounding), to 1e-6 in single precision, and the chains are the same chains."""
+    _need_gpu()
+    X = datasets[name]
+    kw = dict(burnin=4, relabel=True, burnrelabel=2, chains=3, seed=17, probes=("probs",))
+    monkeypatch.setenv("BMM_COLLAPSED_KERNEL", "log")
+    ref = B.gibbs_collapsed(X, 12, K, **kw)
+    monkeypatch.delenv("BMM_COLLAPSED_KERNEL")
+    g = B.gibbs_collapsed(X, 12, K, **kw)
+    assert np.array_equal(g["z_original"], ref["z_original"]) and np.array_equal(g["permutations"], ref["permutations"])
+    _close(g["probs"][:, 1:], ref["probs"][:, 1:], rtol=1e-12, atol=1e-300)
+    _close(g["theta"], ref["theta"], rtol=0)
+    f = B.gibbs_collapsed(X, 12, K, precision="fp32", **kw)
+    # single precision: the first sweep starts from the same state, so its probabilities are comparable entry by entry
+    _close(f["probs"][:, 1], ref["probs"][:, 1], rtol=2e-6, atol=1e-30)
+    assert (f["z_original"][:, 0] != ref["z_original"][:, 0]).mean() < 1e-3
+
+
 @pytest.mark.parametrize("name,maxK,relabel", [("K2_N1000_P5", 64, False), ("K2_N100_P5", 30, True), ("K2_N100_P5", 4, False)])
 def test_dp_replay(oracle, datasets, name, maxK, relabel):
     _need_gpu()
