@@ -155,7 +155,7 @@ struct bmm_plan {
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
     DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
     // data
-    DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN;
+    DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN, rBGP;
     // state
     DevBuf theta_cur, pi_cur, alpha_cur, Q, logQ, cube, logp, prob_g, hist_g, ll_g, assign_ws, status, cost_g;
     DevBuf z_cur, cnt, dp_used, dp_free, probs_sample, sb_perm, sb_cost, sb_ws, perm_inv;
@@ -639,6 +639,14 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     TRY(upload(pl->logB, lB.data(), lB.size()));
     TRY(upload(pl->logG, lG.data(), lG.size()));
     TRY(upload(pl->logBG, lBG.data(), lBG.size()));
+    // product form of the DP conditional (kern_collapsed.cu): the factors reach (beta or gamma + N)^P and (beta + gamma)^-P ... (.. + N)^-P
+    const bool prod_ok = dp && !a.replay && !getenv("BMM_DP_LOGFORM") &&
+                         P * std::fabs(std::log10(a.beta + a.gamma + N)) < 250.0 && P * std::fabs(std::log10(a.beta + a.gamma)) < 250.0;
+    if (prod_ok) {
+        std::vector<double> r(N + 1);
+        for (int n = 0; n <= N; ++n) r[n] = std::pow(a.beta + a.gamma + n, -(double)P);
+        TRY(upload(pl->rBGP, r.data(), r.size()));
+    }
     const size_t P1 = P + 1, NK = (size_t)N * K, KP = (size_t)K * P;
     std::vector<uint8_t> zc((size_t)C * N, 0xFF);
     std::vector<int> cnt((size_t)C * K * P1, 0);
@@ -700,7 +708,7 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     q.seed = a.seed; q.chain_offset = a.chain_offset; q.flags = a.flags;
     q.xbits = pl->xbits.as<uint32_t>();
     q.logB = pl->logB.as<double>(); q.logG = pl->logG.as<double>(); q.logBG = pl->logBG.as<double>();
-    q.logN = pl->logN.as<double>();
+    q.logN = pl->logN.as<double>(); q.rBGP = pl->rBGP.as<double>();
     q.z_cur = pl->z_cur.as<uint8_t>(); q.cnt = pl->cnt.as<int>(); q.alpha_cur = pl->alpha_cur.as<double>();
     q.dp_used = pl->dp_used.as<int>(); q.dp_free = pl->dp_free.as<uint8_t>();
     q.Q = pl->Q.as<double>(); q.logQ = pl->logQ.as<double>(); q.probs_sample = pl->probs_sample.as<double>();

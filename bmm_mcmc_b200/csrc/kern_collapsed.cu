@@ -593,6 +593,12 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
     const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
     if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
     const double RHS_newk = P * (log(p.beta) - log(p.beta + p.gamma));  // (:71)
+    // Philox mode, when the products stay inside the double range: the conditional in product form, as in
+    // collapsed_prod_kernel -- N_k prod_d (beta + S_kd | gamma + N_k - S_kd) (beta + gamma + N_k)^-P for an existing
+    // cluster and alpha (beta / (beta + gamma))^P for a new one (the common 1 / (N - 1 + alpha) cancels).  No table
+    // logs, no max pass, no exp; normalised only when the probabilities themselves are stored.
+    const bool prod = !replay && p.rBGP != nullptr;
+    const double newk_c0 = exp(RHS_newk);
     bool dead = p.status[c] != 0;
 
     for (int j = p.j_begin; j < p.j_end && !dead; ++j) {
@@ -651,6 +657,36 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
             double lp[SLOTS];
             int lab[SLOTS];
             double mx = -INFINITY;
+            double pn[SLOTS], tot = 0.0;
+            if (prod) {
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    const int pos = lane + 32 * sl;
+                    double v = 0.0;
+                    int label = -1;
+                    if (pos < Kvar) {
+                        label = s.used[pos];
+                        const int Nk = s.cnt[label * P1 + P];
+                        v = (double)Nk * __ldg(&p.rBGP[Nk]);
+                        for (int d = 0; d < P; ++d) {
+                            const int xd = (s.x[i * W + (d >> 5)] >> (d & 31)) & 1;
+                            const int Sd = s.cnt[label * P1 + d];
+                            v *= xd ? p.beta + Sd : p.gamma + (Nk - Sd);
+                        }
+                    } else if (pos == Kvar) {
+                        label = new_label;
+                        v = alpha * newk_c0;
+                    }
+                    pn[sl] = v; lab[sl] = label;
+                    tot += v;
+                }
+                tot = warp_sum_all(tot);
+                if (!(tot > 0.0) || !isfinite(tot)) { if (lane == 0) p.status[c] = -9; }
+                if (stash_rel || p.probs_out) {
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) pn[sl] /= tot;
+                }
+            } else {
 #pragma unroll
             for (int sl = 0; sl < SLOTS; ++sl) {
                 const int pos = lane + 32 * sl;
@@ -677,12 +713,12 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
                 mx = fmax(mx, v);
             }
             mx = warp_max_xor(mx);
-            double pn[SLOTS], tot = 0.0;
 #pragma unroll
             for (int sl = 0; sl < SLOTS; ++sl) { pn[sl] = (lab[sl] >= 0) ? exp(lp[sl] - mx) : 0.0; tot += pn[sl]; }
             tot = warp_sum_all(tot);
 #pragma unroll
             for (int sl = 0; sl < SLOTS; ++sl) pn[sl] /= tot;                // exp-normalise (:174-186)
+            }
             if (stash_rel || p.probs_out) {                                 // stored by LABEL (:190-200)
 #pragma unroll
                 for (int sl = 0; sl < SLOTS; ++sl)

@@ -84,6 +84,7 @@ struct CollapsedParams {
     // tables shared by all chains: log(beta+n), log(gamma+n), log(beta+gamma+n), n = 0..N
     const double *logB, *logG, *logBG;
     const double *logN;           // log(n), n = 0..N (dp: log N_k)
+    const double *rBGP;           // dp, Philox mode: (beta + gamma + n)^-P, n = 0..N; nullptr when the products could leave the double range
     // chain state (global, persists between launches)
     uint8_t *z_cur;               // [c][N] labels 0..K-1 (0xFF = unseated, dp sweep 1)
     int *cnt;                     // [c][K*(P+1)]: S_kd at k*(P+1)+d, N_k at k*(P+1)+P

@@ -198,6 +198,22 @@ def test_collapsed_product_form_equals_log_form(datasets, monkeypatch, name, K):
     assert (f["z_original"][:, 0] != ref["z_original"][:, 0]).mean() < 1e-3
 
 
+@pytest.mark.parametrize("name,maxK", [("K2_N100_P5", 30), ("K2_N1000_P5", 64)])
+def test_dp_product_form_equals_log_form(datasets, monkeypatch, name, maxK):
+    """The DP sampler's Philox mode evaluates the conditional of collapsed_gibbs_dp.cpp:140-186 in product form;
+    same seed => same chains as the log / exp-normalise form, probabilities equal to rounding."""
+    _need_gpu()
+    X = datasets[name]
+    kw = dict(burnin=4, relabel=False, maxK=maxK, chains=3, seed=23, probes=("probs",))
+    monkeypatch.setenv("BMM_DP_LOGFORM", "1")
+    ref = B.gibbs_dp(X, 10, **kw)
+    monkeypatch.delenv("BMM_DP_LOGFORM")
+    g = B.gibbs_dp(X, 10, **kw)
+    assert np.array_equal(g["z"], ref["z"])
+    _close(g["probs"][:, 1:], ref["probs"][:, 1:], rtol=1e-11, atol=1e-300)
+    _close(g["alpha"], ref["alpha"], rtol=0)
+
+
 @pytest.mark.parametrize("name,maxK,relabel", [("K2_N1000_P5", 64, False), ("K2_N100_P5", 30, True), ("K2_N100_P5", 4, False)])
 def test_dp_replay(oracle, datasets, name, maxK, relabel):
     _need_gpu()
