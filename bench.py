@@ -709,6 +709,17 @@ def main():
     plan.close()
 
     # ---- end-to-end arm (e2e): the public call with host buffers, every step ------------------
+    # (the reference's list layout: S x N int32 allocation matrices, 15 GB per rank at the C2 size -- never drive the box
+    #  out of memory for it)
+    need = (2 if relabel else 1) * C_ * S * N * 4 * int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    if avail is not None and need > 0.8 * avail:
+        raise SystemExit("bench: the e2e leg needs %.0f GB of host memory for the returned histories, %.0f GB available"
+                         % (need / 1e9, avail / 1e9))
     bufs = api._alloc_out(sid, C_, N, P, K, ns, burnin, relabel, False, (), True)  # pinned
     host_out = api.out_nbytes(bufs[0])
     # bytes that actually cross PCIe: int32 z matrices above 8M allocations travel as 1 B per allocation and

@@ -149,7 +149,7 @@ struct bmm_plan {
     bool use_graph = true, capturing = false;
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     unsigned long long glaunches[2] = {0, 0};
-    DevBuf ws_b1, ws_s0, x_done;
+    DevBuf ws_b1, ws_s0, ws_rep, x_done;
     DevBuf x_inbox, x_peer_arr, x_seq;   // single-GPU inbox of the tensor path (x_world = 1)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias, cnt_ws;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
@@ -423,7 +423,10 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     if (tensor_ws) {
         CU(pl->ws_b1.alloc(bmm::ws_b1_bytes(P)));     // zero: rows k >= K and columns d >= P stay zero
         CU(pl->ws_s0.alloc(32 * 8));
-        b.ws_b1 = pl->ws_b1.as<unsigned char>(); b.ws_s0 = pl->ws_s0.as<double>();
+        CU(pl->ws_rep.alloc(bmm::ws_rep_bytes(K, P)));
+        CU(pl->x_done.alloc(sizeof(unsigned)));
+        b.ws_b1 = pl->ws_b1.as<unsigned char>(); b.ws_s0 = pl->ws_s0.as<double>(); b.ws_rep = pl->ws_rep.as<int>();
+        b.x_done = pl->x_done.as<unsigned>();
     }
     pl->sharded = n_global > N;
     if (pl->sharded) {
@@ -432,7 +435,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
         pl->x_p2p = bmm::dist_p2p_ready(ncnt);
         if (pl->x_p2p) {
             const bmm::P2PView v = bmm::dist_p2p_view();
-            CU(pl->x_done.alloc(sizeof(unsigned)));
+            if (!pl->x_done.p) CU(pl->x_done.alloc(sizeof(unsigned)));
             b.x_world = v.world; b.x_rank = v.rank; b.x_cap = v.cap; b.x_peer = v.peer; b.x_local = v.local; b.x_seq = v.seq;
             b.x_done = pl->x_done.as<unsigned>();
             b.x_fused = tensor_ws ? 1 : 0;
@@ -446,7 +449,6 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
         TRY(upload(pl->x_peer_arr, &self, 1));
         const int seq0[2] = {1, 1};
         TRY(upload(pl->x_seq, seq0, 2));
-        CU(pl->x_done.alloc(sizeof(unsigned)));
         b.x_world = 1; b.x_rank = 0; b.x_cap = ncnt; b.x_peer = pl->x_peer_arr.as<int2 *>(); b.x_local = self;
         b.x_seq = pl->x_seq.as<int>(); b.x_done = pl->x_done.as<unsigned>(); b.x_fused = 1;
     }
@@ -557,6 +559,7 @@ int enqueue_segment(bmm_plan *pl, int seg, int jsplit) {
         CU(cudaMemsetAsync(pl->counts.p, 0, pl->counts.bytes, pl->stream));
         if (pl->zfreq.p) CU(cudaMemsetAsync(pl->zfreq.p, 0, pl->zfreq.bytes, pl->stream));
         if (pl->x_done.p) CU(cudaMemsetAsync(pl->x_done.p, 0, pl->x_done.bytes, pl->stream));
+        if (pl->ws_rep.p) CU(cudaMemsetAsync(pl->ws_rep.p, 0, pl->ws_rep.bytes, pl->stream));
         if (pl->x_p2p && bmm::dist_p2p_begin_run(ns, pl->stream)) return fail(BMM_ERR_NCCL, bmm::dist_error());
         if (pl->x_seq.p) CU(bmm::launch_x_begin_run(pl->x_seq.as<int>(), ns, pl->stream));
         CU(bmm::launch_big_init(b, pl->stream));
@@ -889,8 +892,15 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
         // R-layout allocation histories are produced on the device by the finalize kernel
         // int32 output larger than a few MB: keep bytes on the device and widen on the host (fetch_z)
         const size_t zelems = (size_t)pl->C * pl->S * pl->N;
+        // Widening on the host moves a quarter of the bytes over PCIe but every rank's workers write the int32 matrices
+        // through the same host memory system: measured on the 8-GPU box (C2, 15 GB of int32 per rank and step) the call
+        // took 1035 ms with 8 ranks against 190 ms with one.  Each GPU has its own PCIe link, so with more than two
+        // ranks per host the device widens and the int32 matrices are DMA'd as they are.  BMM_FETCH_WIDEN=0/1 overrides.
         const char *wenv = getenv("BMM_FETCH_WIDEN");
-        const bool widen = !(args->flags & BMM_FLAG_COMPACT_Z) && zelems >= ((size_t)8 << 20) && !(wenv && wenv[0] == '0');
+        int local_ranks = 1;
+        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) local_ranks = atoi(lw) > 0 ? atoi(lw) : 1;
+        const bool widen_dflt = wenv ? wenv[0] != '0' : local_ranks <= 2;
+        const bool widen = !(args->flags & BMM_FLAG_COMPACT_Z) && zelems >= ((size_t)8 << 20) && widen_dflt;
         pl->deb = ((args->flags & BMM_FLAG_COMPACT_Z) || widen) ? 1 : 4;
         const size_t eb = (size_t)pl->deb;
         const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
@@ -1203,6 +1213,16 @@ int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t 
     CU(cudaMemcpy(st, sd.p, 8, cudaMemcpyDeviceToHost));
     if (st[0]) return fail(st[0], "grid cost kernel failed");
     CU(cudaMemcpy(out, od.p, ((size_t)K * K + K) * 8, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+/* diagnostic: %globaltimer stamps (ns) of CTA 0 of the last tensor-sweep launch, see kern_big_ws.cu */
+int bmm_debug_ws_trace(uint64_t out[8]) {
+    if (!out) return fail(BMM_ERR_INVALID, "out is NULL");
+    CU(cudaDeviceSynchronize());
+    unsigned long long t[8];
+    CU(bmm::ws_trace_read(t));
+    for (int i = 0; i < 8; ++i) out[i] = t[i];
     return BMM_OK;
 }
 

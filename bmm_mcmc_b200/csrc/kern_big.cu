@@ -449,6 +449,17 @@ bool pdl_enabled() {
 }
 
 cudaError_t launch_big_params(const BigParams &p, int j, cudaStream_t st) {
+    // keep the L1 / shared-memory split at the sweep kernel's (which needs > 200 KB): a different split between two
+    // kernels of the loop makes the SMs drain and reconfigure at every kernel boundary
+    static FuncAttrCache carve;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !carve.set[dev]) {
+            cudaFuncSetAttribute(big_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve.set[dev] = 1;
+        }
+    }
     g_launches++;
     return launch_pdl(big_update_kernel, dim3(p.K + 1), dim3(UPD_THREADS), 0, st, p, j);
 }

@@ -34,6 +34,17 @@ constexpr int WS_NA = WS_NA_CFG;      // GEMM1 accumulators (64 TMEM columns eac
 constexpr int WS_NB = WS_NB_CFG;      // one-hot stages
 constexpr int WS_NEPI = WS_NEPI_CFG;  // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
+constexpr int WS_REP = 32;    // replicas of the count vector the CTAs flush into
+
+// Phase stamps of the last launch (CTA 0; %globaltimer, ns): [0] entry, [1] tables loaded / pipeline start, [2] first
+// tile's allocation drawn, [3] last tile drawn (epilogue warpgroup 0), [4] counts flushed, [5] exit.  Diagnostic only
+// (bmm_debug_ws_trace): six timer reads per launch.
+__device__ unsigned long long g_ws_trace[8];
+__device__ __forceinline__ void ws_stamp(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_ws_trace[slot] = t;
+}
 constexpr int WS_CHUNK = 2048;
 constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
 
@@ -79,6 +90,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     const uint32_t all_done = b2_free + 8 * WS_NB;
 
     // ---- prologue ----
+    if (blockIdx.x == 0 && tid == 0) ws_stamp(0);
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc2 = tmem_base + WS_NA * WS_PARTS * WS_KC;
+    if (blockIdx.x == 0 && tid == 0) ws_stamp(1);
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     const int T = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;   // tiles of this CTA
     bool ok = true;
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             }
             const int z = min(WS_KC - over, K - 1);
             if (valid && zrow) zrow[i] = (uint8_t)(z + 1);
+            if (blockIdx.x == 0 && tid == 256) { if (k == 0) ws_stamp(2); if (k + WS_NEPI >= T) ws_stamp(3); }
             if (k >= WS_NB) ok = mbar_wait(b2_free + 8 * b, ph_b ^ 1u);
             if (!ok) break;
             {   // one-hot row of this observation in stage b: clear the entry this thread set there last time (the
@@ -385,7 +399,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (ok && T > 0) ok = mbar_wait(all_done, 0u);
         if (ok && T > 0) {
             tc_fence_after();
-            int *gcnt = p.counts + (size_t)(j & 1) * (K + K * P);
+            // Every CTA adds its counts to one of WS_REP replicas of the count vector: with a single copy all 148 CTAs
+            // hit the same 65 cache lines at the same moment and the L2 atomic units serialise them (13 us per launch,
+            // measured with the phase stamps); the last CTA sums the replicas.
+            int *rep = p.ws_rep + (size_t)(blockIdx.x % WS_REP) * (K + K * P);
             uint32_t v[32];
             tmem_ld32(acc2 + ((uint32_t)((warp & 3) * 32) << 16), v);
             tmem_ld_wait();
@@ -393,7 +410,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const int n = (int)(__uint_as_float(v[q]) + 0.5f);
-                    if (q < K && n) atomicAdd(t == ONES ? &gcnt[q] : &gcnt[K + q + K * t], n);
+                    if (q < K && n) atomicAdd(t == ONES ? &rep[q] : &rep[K + q + K * t], n);
                 }
             }
         }
@@ -401,12 +418,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
     tc_fence_before();
     __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) ws_stamp(4);
     if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
     }
-    // ---- N-sharded run: the last CTA to get here pushes this rank's counts into every rank's inbox ----
-    if (p.x_fused) {
+    // ---- the last CTA to get here sums the replicas into the count vector and, in inbox mode, pushes the sums as
+    //      tagged words into every rank's inbox (its own included) ----
+    {
         __shared__ int last_sh;
         __threadfence();                 // this CTA's count atomics are performed before its ticket
         __syncthreads();
@@ -418,15 +437,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         __syncthreads();
         if (last_sh) {
             __threadfence();
-            const int n = K + K * P, world = p.x_world, s = p.x_seq[0] + j;
-            const int *gcnt = p.counts + (size_t)(j & 1) * n;
-            const size_t off = x_slot_off(s, world, p.x_rank, (size_t)p.x_cap);
+            const int n = K + K * P, world = p.x_world, s = world >= 1 ? p.x_seq[0] + j : 0;
+            int *gcnt = p.counts + (size_t)(j & 1) * n;
+            const size_t off = world >= 1 ? x_slot_off(s, world, p.x_rank, (size_t)p.x_cap) : 0;
             for (int e = tid; e < n; e += WS_THREADS) {
-                const int v = __ldcg(gcnt + e);
+                int v = 0;
+#pragma unroll 8
+                for (int r = 0; r < WS_REP; ++r) v += __ldcg(p.ws_rep + (size_t)r * n + e);
+#pragma unroll 8
+                for (int r = 0; r < WS_REP; ++r) p.ws_rep[(size_t)r * n + e] = 0;          // zero for the next sweep
+                gcnt[e] = v;
                 for (int r = 0; r < world; ++r) x_store(p.x_peer[r] + off + e, v, s);   // (count, tag) in one 8-byte store
             }
         }
     }
+    if (blockIdx.x == 0 && tid == 0) ws_stamp(5);
 }
 
 template <int NCH>
@@ -448,6 +473,9 @@ bool big_tc_supported(const BigParams &p) {
 }
 
 size_t ws_b1_bytes(int P) { return (size_t)ws_nch(P) * WS_B1_ROW; }
+size_t ws_rep_bytes(int K, int P) { return (size_t)WS_REP * ((size_t)K + (size_t)K * P) * sizeof(int); }
+
+cudaError_t ws_trace_read(unsigned long long out[8]) { return cudaMemcpyFromSymbol(out, g_ws_trace, 8 * sizeof(unsigned long long)); }
 
 cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     if (!p.ws_b1 || !p.ws_s0) return cudaErrorInvalidValue;

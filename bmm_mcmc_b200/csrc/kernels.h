@@ -142,6 +142,7 @@ struct BigParams {
     // s0_k = sum_d log(1 - theta_kd), written by the update kernel so that the sweep's prologue is a copy
     unsigned char *ws_b1;             // [ws_b1_bytes(P)] or nullptr
     double *ws_s0;                    // [32]
+    int *ws_rep;                      // [ws_rep_bytes(K, P)] replicas of the count vector (zero between launches)
     // Counts handed from the sweep kernel to the update kernel through an inbox of tagged words: over peer memory on
     // an N-sharded run (dist.cu), through a local inbox (x_world = 1) on one GPU -- the tags make the hand-over
     // self-synchronising, so the update kernel can be launched before the sweep kernel has drained.
@@ -187,6 +188,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st);   // seq[0] = seq[1]; seq[1] += n_sweeps
 size_t ws_b1_bytes(int P);
+size_t ws_rep_bytes(int K, int P);
+cudaError_t ws_trace_read(unsigned long long out[8]);   // phase stamps of the last tensor-sweep launch (diagnostic)
 cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st);   // operand image from w1 / w0 (initial state)
 bool big_tables_fit_smem(int K, int P, int precision);
 int big_replay_max_k();

@@ -170,6 +170,10 @@ int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t 
 /* _bmmmcmc_rdirichlet_cpp (full_gibbs.cpp:10-27) with an explicit Philox seed.                    */
 int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out);
 
+/* Diagnostic (no reference counterpart): %globaltimer stamps in ns of CTA 0 of the last tensor-path z-sweep launch --
+ * [0] entry, [1] pipeline start, [2] first tile drawn, [3] last tile drawn, [4] counts flushed, [5] exit.            */
+int bmm_debug_ws_trace(uint64_t out[8]);
+
 /* ---- probes --------------------------------------------------------------------------------- */
 /* One uncollapsed z-sweep at a given state (full_gibbs.cpp:87-133): log-likelihood and
  * conditional-probability matrices (N x K cm each; either may be NULL).                           */
