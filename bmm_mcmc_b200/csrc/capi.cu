@@ -1217,12 +1217,23 @@ int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t 
 }
 
 /* diagnostic: %globaltimer stamps (ns) of CTA 0 of the last tensor-sweep launch, see kern_big_ws.cu */
-int bmm_debug_ws_trace(uint64_t out[8]) {
+int bmm_debug_ws_trace(uint64_t out[32]) {
     if (!out) return fail(BMM_ERR_INVALID, "out is NULL");
     CU(cudaDeviceSynchronize());
-    unsigned long long t[8];
+    unsigned long long t[32];
     CU(bmm::ws_trace_read(t));
-    for (int i = 0; i < 8; ++i) out[i] = t[i];
+    CU(bmm::upd_trace_read(t + 16));
+    for (int i = 0; i < 32; ++i) out[i] = t[i];
+    return BMM_OK;
+}
+
+/* diagnostic: per CTA of the last tensor-sweep launch, out[2b] = (entry ns << 10) | SM id, out[2b + 1] = counts flushed ns */
+int bmm_debug_ws_cta(uint64_t out[320]) {
+    if (!out) return fail(BMM_ERR_INVALID, "out is NULL");
+    CU(cudaDeviceSynchronize());
+    unsigned long long t[320];
+    CU(bmm::ws_cta_read(t));
+    for (int i = 0; i < 320; ++i) out[i] = t[i];
     return BMM_OK;
 }
 

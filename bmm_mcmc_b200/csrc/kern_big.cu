@@ -160,6 +160,15 @@ __global__ void __launch_bounds__(BIG_THREADS) big_sweep_kernel(const BigParams 
 
 constexpr int UPD_THREADS = 256;
 
+// diagnostic stamps of the update kernel (ns): per sweep parity [0] block 0 start, [1] block 0 has its counts, [2] block 0
+// end, [3] last block start, [4] last block end
+__device__ unsigned long long g_upd_trace[16];
+__device__ __forceinline__ void upd_stamp(int j, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_upd_trace[8 * (j & 1) + slot] = t;
+}
+
 // One launch per sweep, after the z-sweep: blocks 0..K-1 own one cluster each (theta_k., its log tables and, for
 // the tensor path, row k of the operand image), block K draws pi / sticks / alpha, writes the history rows and
 // zeroes the next sweep's count buffer.  On an N-sharded run over peer memory every thread sums, over the ranks, the
@@ -177,6 +186,8 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
     int *cur = p.counts + (size_t)(j & 1) * (K + KP);
     const uint32_t chain = (uint32_t)p.chain_offset;
     const double alpha_prev = *p.alpha_cur;
+    if (tid == 0 && blockIdx.x == 0) upd_stamp(j, 0);
+    if (tid == 0 && blockIdx.x == gridDim.x - 1) upd_stamp(j, 3);
     // the next sweep kernel may start its prologue now; it waits for this grid before it reads the tables
     griddep_launch();
     // Inbox mode without relabelling needs nothing from the predecessor but the tagged words themselves; otherwise wait
@@ -216,6 +227,7 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
         // ---------------- cluster block: theta_kd ~ Beta(beta + V_kd, gamma + c_k - V_kd) ----------------
         const int k = blk;
         const int ck = count_of(k);
+        if (tid == 0 && blk == 0) upd_stamp(j, 1);
         for (int d0 = 0; d0 < P; d0 += UPD_THREADS) {
             const int d = d0 + tid;
             if (d < P) {
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
                 if (tid == 0) p.ws_s0[k] = a;
             }
         }
+        if (tid == 0 && blk == 0) upd_stamp(j, 2);
         griddep_wait();     // this grid must not complete before the sweep kernel in front has (see the end of the kernel)
         return;
     }
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
         if (p.pi_out && j >= p.burnin) p.pi_out[(j - p.burnin) + (size_t)S * k] = pk;
     }
     if (tid == 0 && p.alpha_out && j >= p.burnin) p.alpha_out[j - p.burnin] = *p.alpha_cur;
+    if (tid == 0) upd_stamp(j, 4);
     // In inbox mode nothing above waited for the sweep kernel itself, only for its tagged words.  Whatever follows in the
     // stream is ordered after THIS grid, so this grid completes only once the sweep kernel has (its allocation history
     // is read by the layout kernels, its count buffer is zeroed two sweeps later).
@@ -473,6 +487,8 @@ cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st) {
     g_launches++;
     return cudaGetLastError();
 }
+
+cudaError_t upd_trace_read(unsigned long long out[16]) { return cudaMemcpyFromSymbol(out, g_upd_trace, 16 * sizeof(unsigned long long)); }
 
 cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st) {
     if (!p.ws_b1) return cudaSuccess;

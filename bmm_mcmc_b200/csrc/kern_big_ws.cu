@@ -34,16 +34,18 @@ constexpr int WS_NA = WS_NA_CFG;      // GEMM1 accumulators (64 TMEM columns eac
 constexpr int WS_NB = WS_NB_CFG;      // one-hot stages
 constexpr int WS_NEPI = WS_NEPI_CFG;  // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
-constexpr int WS_REP = 32;    // replicas of the count vector the CTAs flush into
+constexpr int WS_REP = 16;    // replicas of the count vector the CTAs flush into
 
 // Phase stamps of the last launch (CTA 0; %globaltimer, ns): [0] entry, [1] tables loaded / pipeline start, [2] first
 // tile's allocation drawn, [3] last tile drawn (epilogue warpgroup 0), [4] counts flushed, [5] exit.  Diagnostic only
 // (bmm_debug_ws_trace): six timer reads per launch.
-__device__ unsigned long long g_ws_trace[8];
+__device__ unsigned long long g_ws_trace[16];     // [sweep parity][8]
+__device__ int g_ws_trace_j;
+__device__ unsigned long long g_ws_cta[2 * 160];  // per CTA of the last launch: entry and "counts flushed" stamps, + SM id
 __device__ __forceinline__ void ws_stamp(int slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_ws_trace[slot] = t;
+    g_ws_trace[8 * (g_ws_trace_j & 1) + slot] = t;
 }
 constexpr int WS_CHUNK = 2048;
 constexpr int WS_B2_BYTES = (WS_KC / 8) * WS_CHUNK;   // 8 KB
@@ -90,7 +92,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
     const uint32_t all_done = b2_free + 8 * WS_NB;
 
     // ---- prologue ----
-    if (blockIdx.x == 0 && tid == 0) ws_stamp(0);
+    if (blockIdx.x == 0 && tid == 0) { g_ws_trace_j = j; ws_stamp(0); }
+    if (tid == 0 && blockIdx.x < 160) {
+        unsigned long long t; unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_ws_cta[2 * blockIdx.x] = ((t & 0x3FFFFFFFFFFFFFull) << 10) | sm;
+    }
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -399,10 +407,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         if (ok && T > 0) ok = mbar_wait(all_done, 0u);
         if (ok && T > 0) {
             tc_fence_after();
-            // Every CTA adds its counts to one of WS_REP replicas of the count vector: with a single copy all 148 CTAs
-            // hit the same 65 cache lines at the same moment and the L2 atomic units serialise them (13 us per launch,
-            // measured with the phase stamps); the last CTA sums the replicas.
-            int *rep = p.ws_rep + (size_t)(blockIdx.x % WS_REP) * (K + K * P);
+            // The CTA's counts are staged in shared memory (the A ring is idle by now) in the layout of the count
+            // vector, c_k then V_kd at K + k + K d, and added to global memory by ONE bulk reduction below.
+            int *stage = (int *)smem;
             uint32_t v[32];
             tmem_ld32(acc2 + ((uint32_t)((warp & 3) * 32) << 16), v);
             tmem_ld_wait();
@@ -410,48 +417,89 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const int n = (int)(__uint_as_float(v[q]) + 0.5f);
-                    if (q < K && n) atomicAdd(t == ONES ? &rep[q] : &rep[K + q + K * t], n);
+                    if (q < K) stage[t == ONES ? q : K + q + K * t] = n;
                 }
             }
+            fence_async_smem();
         }
     }
     if (!ok) *p.status = -10;  // BMM_ERR_TIMEOUT
     tc_fence_before();
     __syncthreads();
     if (blockIdx.x == 0 && tid == 0) ws_stamp(4);
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    if (tid == 0 && blockIdx.x < 160) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_ws_cta[2 * blockIdx.x + 1] = t;
     }
     // ---- the last CTA to get here sums the replicas into the count vector and, in inbox mode, pushes the sums as
     //      tagged words into every rank's inbox (its own included) ----
     {
         __shared__ int last_sh;
-        __threadfence();                 // this CTA's count atomics are performed before its ticket
-        __syncthreads();
+        // Every CTA adds its counts to one of WS_REP replicas of the count vector with a single cp.reduce.async.bulk
+        // (UBLKRED: the copy engine performs the additions at the L2 in 16-byte pieces).  The first version issued 2080
+        // scalar atomics per CTA into ONE copy: all 148 CTAs hit the same 65 cache lines at the same moment and the
+        // fence behind them took 13 us per launch (7.6 us with 16 replicas), measured with the phase stamps.
         if (tid == 0) {
+            const int n = K + K * P, nstride = (n + 3) & ~3;
+            int *rep = p.ws_rep + (size_t)(blockIdx.x % WS_REP) * nstride;
+            if (ok && T > 0) {
+                const int nb = (n & ~3) * 4;
+                if (nb) {
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;"
+                                 :: "l"(rep), "r"(smem_u32(smem)), "r"(nb) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                for (int e = n & ~3; e < n; ++e) atomicAdd(&rep[e], ((const int *)smem)[e]);
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+            __threadfence();             // this CTA's additions are performed before its ticket
+            if (blockIdx.x == 0) ws_stamp(6);
             const unsigned ticket = atomicAdd(p.x_done, 1u);
             last_sh = ticket == gridDim.x - 1;
             if (last_sh) *p.x_done = 0u;         // ready for the next launch (stream order)
         }
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) ws_stamp(7);
         if (last_sh) {
             __threadfence();
-            const int n = K + K * P, world = p.x_world, s = world >= 1 ? p.x_seq[0] + j : 0;
+            const int n = K + K * P, nstride = (n + 3) & ~3, world = p.x_world, s = world >= 1 ? p.x_seq[0] + j : 0;
             int *gcnt = p.counts + (size_t)(j & 1) * n;
             const size_t off = world >= 1 ? x_slot_off(s, world, p.x_rank, (size_t)p.x_cap) : 0;
-            for (int e = tid; e < n; e += WS_THREADS) {
-                int v = 0;
-#pragma unroll 8
-                for (int r = 0; r < WS_REP; ++r) v += __ldcg(p.ws_rep + (size_t)r * n + e);
-#pragma unroll 8
-                for (int r = 0; r < WS_REP; ++r) p.ws_rep[(size_t)r * n + e] = 0;          // zero for the next sweep
-                gcnt[e] = v;
-                for (int r = 0; r < world; ++r) x_store(p.x_peer[r] + off + e, v, s);   // (count, tag) in one 8-byte store
+            // this is a serial step of the whole GPU: four elements per thread with all their replica loads in flight at once
+            // (64 independent L2 loads), not one dependent round trip after another
+            for (int e0 = tid; e0 < n; e0 += 4 * WS_THREADS) {
+                int v[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r = 0; r < WS_REP; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = e0 + q * WS_THREADS;
+                        if (e < n) v[q] += __ldcg(p.ws_rep + (size_t)r * nstride + e);
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e0 + q * WS_THREADS;
+                    if (e < n) {
+                        gcnt[e] = v[q];
+                        for (int r = 0; r < world; ++r) x_store(p.x_peer[r] + off + e, v[q], s);   // (count, tag) in one 8-byte store
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < WS_REP; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = e0 + q * WS_THREADS;
+                        if (e < n) p.ws_rep[(size_t)r * nstride + e] = 0;          // zero for the next sweep
+                    }
             }
         }
     }
     if (blockIdx.x == 0 && tid == 0) ws_stamp(5);
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 template <int NCH>
@@ -473,9 +521,10 @@ bool big_tc_supported(const BigParams &p) {
 }
 
 size_t ws_b1_bytes(int P) { return (size_t)ws_nch(P) * WS_B1_ROW; }
-size_t ws_rep_bytes(int K, int P) { return (size_t)WS_REP * ((size_t)K + (size_t)K * P) * sizeof(int); }
+size_t ws_rep_bytes(int K, int P) { return (size_t)WS_REP * (((size_t)K + (size_t)K * P + 3) & ~(size_t)3) * sizeof(int); }
 
-cudaError_t ws_trace_read(unsigned long long out[8]) { return cudaMemcpyFromSymbol(out, g_ws_trace, 8 * sizeof(unsigned long long)); }
+cudaError_t ws_cta_read(unsigned long long out[320]) { return cudaMemcpyFromSymbol(out, g_ws_cta, 320 * sizeof(unsigned long long)); }
+cudaError_t ws_trace_read(unsigned long long out[16]) { return cudaMemcpyFromSymbol(out, g_ws_trace, 16 * sizeof(unsigned long long)); }
 
 cudaError_t launch_big_sweep_ws(const BigParams &p, int j, int sm_count, cudaStream_t st) {
     if (!p.ws_b1 || !p.ws_s0) return cudaErrorInvalidValue;

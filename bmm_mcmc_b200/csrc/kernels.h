@@ -189,7 +189,9 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st);   // seq[0] = seq[1]; seq[1] += n_sweeps
 size_t ws_b1_bytes(int P);
 size_t ws_rep_bytes(int K, int P);
-cudaError_t ws_trace_read(unsigned long long out[8]);   // phase stamps of the last tensor-sweep launch (diagnostic)
+cudaError_t ws_trace_read(unsigned long long out[16]);   // phase stamps of the last two tensor-sweep launches (diagnostic)
+cudaError_t ws_cta_read(unsigned long long out[320]);
+cudaError_t upd_trace_read(unsigned long long out[16]);  // ... and of the last two update launches
 cudaError_t launch_ws_table(const BigParams &p, cudaStream_t st);   // operand image from w1 / w0 (initial state)
 bool big_tables_fit_smem(int K, int P, int precision);
 int big_replay_max_k();

@@ -170,9 +170,13 @@ int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t 
 /* _bmmmcmc_rdirichlet_cpp (full_gibbs.cpp:10-27) with an explicit Philox seed.                    */
 int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out);
 
-/* Diagnostic (no reference counterpart): %globaltimer stamps in ns of CTA 0 of the last tensor-path z-sweep launch --
- * [0] entry, [1] pipeline start, [2] first tile drawn, [3] last tile drawn, [4] counts flushed, [5] exit.            */
-int bmm_debug_ws_trace(uint64_t out[8]);
+/* Diagnostic (no reference counterpart): %globaltimer stamps in ns of the last two sweeps of the tensor grid path.
+ * out[8 * (j & 1) + s], z-sweep kernel CTA 0: s = 0 entry, 1 pipeline start, 2 first tile drawn, 3 last tile drawn,
+ * 4 counts flushed, 5 exit.  out[16 + 8 * (j & 1) + s], update kernel: s = 0 block 0 start, 1 block 0 has its counts,
+ * 2 block 0 end, 3 last block start, 4 last block end.                                                               */
+int bmm_debug_ws_trace(uint64_t out[32]);
+/* ... and per CTA b of the last launch: out[2b] = (entry ns << 10) | SM id, out[2b + 1] = counts-flushed ns.      */
+int bmm_debug_ws_cta(uint64_t out[320]);
 
 /* ---- probes --------------------------------------------------------------------------------- */
 /* One uncollapsed z-sweep at a given state (full_gibbs.cpp:87-133): log-likelihood and

@@ -1,0 +1,4 @@
+BMM_SWEEP_EVENTS=0 python tools/jobs/ws_trace.py 1250000 > gpurun_out/n_trace.txt 2>&1
+BMM_SWEEP_EVENTS=0 BMM_PDL=0 python tools/jobs/ws_trace.py 1250000 >> gpurun_out/n_trace.txt 2>&1
+BMM_SWEEP_EVENTS=0 BMM_GRAPH=0 python tools/jobs/ws_trace.py 1250000 >> gpurun_out/n_trace.txt 2>&1
+cat gpurun_out/n_trace.txt
