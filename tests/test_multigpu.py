@@ -68,13 +68,17 @@ dist.destroy_process_group()
 def test_n_sharded_equals_unsharded(tmp_path, p2p):
     """p2p = 1: counts exchanged by the one-shot push over IPC-mapped peer memory instead of NCCL."""
     import bmm_mcmc_b200 as B
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, BMM_ROOT=ROOT, BMM_OUT=str(tmp_path), BMM_P2P=p2p)
-    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                    "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], check=True, env=env,
-                   timeout=300)
+    for attempt in range(3):        # a probed "free" port can be taken again before torchrun binds it
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], env=env, timeout=300,
+                           capture_output=True, text=True)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
+    assert r.returncode == 0, r.stderr[-3000:]
     r = [np.load(tmp_path / ("rank%d.npz" % i)) for i in range(2)]
     rng = np.random.default_rng(3)
     N, P, K = 40_001, 64, 16
