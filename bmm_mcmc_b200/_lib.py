@@ -35,7 +35,7 @@ class Args(C.Structure):
         ("burnin", C.c_int32), ("relabel", C.c_int32), ("burnrelabel", C.c_int32), ("debug", C.c_int32),
         ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("seed", C.c_uint64), ("precision", C.c_int32),
         ("device", C.c_int32), ("flags", C.c_uint32), ("replay", C.POINTER(Replay)),
-        ("n_global", C.c_int64), ("row_offset", C.c_int64),
+        ("n_global", C.c_int64), ("row_offset", C.c_int64), ("thin", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

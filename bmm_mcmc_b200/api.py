@@ -109,7 +109,7 @@ def _chain_cm(C_, shape, dtype, pinned=False):
 def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
                 compact_z=False, stable_softmax=False, chain_offset=0, grid_path=False, no_z_history=False,
-                n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
+                n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, thin=1):
     """ctypes bmm_args / bmm_init for one call; returns (args, init, keepalive)."""
     N, P = X.shape
     args = _lib.Args()
@@ -120,6 +120,7 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     args.n_chains, args.chain_offset, args.seed = int(chains), int(chain_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
     args.precision = {"fp64": _lib.BMM_FP64, "fp32": _lib.BMM_FP32}[precision]
     args.device = int(device)
+    args.thin = int(thin)
     args.flags = ((_lib.FLAG_COMPACT_Z if compact_z else 0) | (_lib.FLAG_STABLE_SOFTMAX if stable_softmax else 0) |
                   (_lib.FLAG_GRID_PATH if grid_path else 0) | (_lib.FLAG_NO_Z_HISTORY if no_z_history else 0) |
                   (_lib.FLAG_NO_TENSOR if no_tensor else 0) | (_lib.FLAG_STEPHENS_FIXED if stephens_fixed else 0))
@@ -149,9 +150,15 @@ def _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relab
     return args, init, keep
 
 
-def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=False):
-    """Caller-side output buffers in the reference's returned-list layout; returns (dict, bmm_out, status)."""
+def kept_sweeps(nsamples, burnin, thin=1):
+    """Rows of the returned histories: every thin-th post-burn-in sweep (thin = 1: all of them, as the reference)."""
     S = nsamples - burnin
+    return (S + thin - 1) // thin if thin > 1 else S
+
+
+def _alloc_out(sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=False, thin=1):
+    """Caller-side output buffers in the reference's returned-list layout; returns (dict, bmm_out, status)."""
+    S = kept_sweeps(nsamples, burnin, thin)
     zt = np.uint8 if compact_z else np.int32
     res = {}
     out = _lib.Out()
@@ -208,16 +215,16 @@ class Plan:
     def __init__(self, sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                  chains=1, seed=0, device=0, precision="fp64", init_pi=None, init_theta=None, init_z=None,
                  compact_z=False, chain_offset=0, probes=(), stable_softmax=False, grid_path=False,
-                 no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
+                 no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, thin=1):
         self.L = _lib.lib()
         self.X = _as_X(X)
         self.meta = dict(sampler=sampler, Cn=int(chains), N=self.X.shape[0], P=self.X.shape[1], K=int(K),
                          nsamples=int(nsamples), burnin=int(burnin), relabel=bool(relabel), compact_z=compact_z,
-                         probes=probes, no_z=bool(no_z_history))
+                         probes=probes, no_z=bool(no_z_history), thin=int(thin))
         args, init, self._keep = _build_args(sampler, self.X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel,
                                              burnrelabel, False, chains, seed, device, precision, init_pi, init_theta,
                                              init_z, None, compact_z, stable_softmax, chain_offset, grid_path,
-                                             no_z_history, n_global, row_offset, no_tensor, stephens_fixed)
+                                             no_z_history, n_global, row_offset, no_tensor, stephens_fixed, thin)
         if "probs" in probes:
             args.flags |= 0x100
         if "loglik" in probes:
@@ -253,7 +260,7 @@ class Plan:
     def alloc_out(self, pinned=False):
         m = self.meta
         return _alloc_out(m["sampler"], m["Cn"], m["N"], m["P"], m["K"], m["nsamples"], m["burnin"], m["relabel"],
-                          m["compact_z"], m["probes"], pinned, no_z=m["no_z"])
+                          m["compact_z"], m["probes"], pinned, no_z=m["no_z"], thin=m["thin"])
 
     def fetch(self, bufs=None, pinned=False):
         res, out, status = bufs if bufs is not None else self.alloc_out(pinned)
@@ -275,16 +282,16 @@ class Plan:
 def _run(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
          chains, seed, device, precision, init_pi=None, init_theta=None, init_z=None, replay=None,
          compact_z=False, stable_softmax=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
-         grid_path=False, no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False):
+         grid_path=False, no_z_history=False, n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, thin=1):
     L = _lib.lib()
     N, P = X.shape
     Cn = int(chains)
     args, init, keep = _build_args(sampler, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel,
                                    debug, chains, seed, device, precision, init_pi, init_theta, init_z, replay,
                                    compact_z, stable_softmax, chain_offset, grid_path, no_z_history, n_global,
-                                   row_offset, no_tensor, stephens_fixed)
+                                   row_offset, no_tensor, stephens_fixed, thin)
     res, out, status = out_bufs if out_bufs is not None else _alloc_out(
-        sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=no_z_history)
+        sampler, Cn, N, P, K, nsamples, burnin, relabel, compact_z, probes, pinned, no_z=no_z_history, thin=thin)
     if sampler == _lib.SAMPLER_DP:
         rc = L.bmm_gibbs_dp(C.byref(args), C.byref(out))
     else:
@@ -311,11 +318,14 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                initial_pi=None, initial_theta=None, replay=None, compact_z=False, stable_softmax=False,
                probes=(), chain_offset=0, pinned=False, out_bufs=None, grid_path=False, no_z_history=False,
-               n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, _sampler=None):
+               n_global=0, row_offset=0, no_tensor=False, stephens_fixed=False, thin=1, _sampler=None):
     """Full Gibbs sampler for a finite Bernoulli mixture model (R/utils.R:64-78 -> full_gibbs.cpp:32).
 
     `stephens_fixed=True` (BMM_FLAG_STEPHENS_FIXED, not the reference's behaviour) relabels with the corrected
-    Stephens steps: inverse permutation for the column re-ordering, log p in the online cost, running-mean Q."""
+    Stephens steps: inverse permutation for the column re-ordering, log p in the online cost, running-mean Q.
+
+    `thin=k` keeps every k-th post-burn-in sweep in all returned histories (the reference keeps every sweep,
+    full_gibbs.cpp:52-57); `probes=("z_freq", "z_last")` adds the posterior summaries a large run keeps instead."""
     X = _as_X(data)
     N, P = X.shape
     burnin, burnrelabel, alpha = _defaults(nsamples, burnin, burnrelabel, alpha, clamp=_sampler is None)
@@ -336,7 +346,7 @@ def gibbs_full(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, bur
                 device, precision, init_pi=np.ascontiguousarray(initial_pi), init_theta=np.ascontiguousarray(initial_theta),
                 replay=replay, compact_z=compact_z, stable_softmax=stable_softmax, probes=probes, chain_offset=chain_offset,
                 pinned=pinned, out_bufs=out_bufs, grid_path=grid_path, no_z_history=no_z_history, n_global=n_global,
-                row_offset=row_offset, no_tensor=no_tensor, stephens_fixed=stephens_fixed)
+                row_offset=row_offset, no_tensor=no_tensor, stephens_fixed=stephens_fixed, thin=thin)
 
 
 def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None,
@@ -351,7 +361,7 @@ def gibbs_stickbreaking(data, nsamples, maxK, alpha=None, beta=0.5, gamma=0.5, a
 def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1, burnin=None, relabel=False,
                     burnrelabel=50, debug=False, *, chains=1, seed=0, device=0, precision="fp64", rng=None,
                     initial_K=None, replay=None, compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None,
-                    stephens_fixed=False):
+                    stephens_fixed=False, thin=1):
     """Collapsed Gibbs sampler for a finite mixture (R/utils.R:37-47 -> collapsed_gibbs.cpp:24)."""
     X = _as_X(data)
     N, P = X.shape
@@ -362,15 +372,15 @@ def gibbs_collapsed(data, nsamples, K, alpha=None, beta=0.5, gamma=0.5, a=1, b=1
     initial_K = np.ascontiguousarray(np.asarray(initial_K, dtype=np.int32).reshape(chains, N))
     return _run(_lib.SAMPLER_COLLAPSED, X, nsamples, K, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, init_z=initial_K, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed, thin=thin)
 
 
 def gibbs_dp(data, nsamples, alpha=None, a=1, b=1, beta=0.5, gamma=0.5, burnin=None, relabel=False,
              burnrelabel=50, maxK=30, debug=False, *, chains=1, seed=0, device=0, precision="fp64", replay=None,
-             compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None, stephens_fixed=False):
+             compact_z=False, probes=(), chain_offset=0, pinned=False, out_bufs=None, stephens_fixed=False, thin=1):
     """Collapsed Gibbs sampler for the DP (CRP) infinite mixture (R/utils.R:23-30 -> collapsed_gibbs_dp.cpp:27)."""
     X = _as_X(data)
     burnin, burnrelabel, alpha = _defaults(nsamples, burnin, burnrelabel, alpha)
     return _run(_lib.SAMPLER_DP, X, nsamples, maxK, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, replay=replay, compact_z=compact_z, probes=probes,
-                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed)
+                chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed, thin=thin)

@@ -131,7 +131,7 @@ struct VecHash {
 struct bmm_plan {
     int sampler = 0;
     bmm_args a{};
-    int C = 1, N = 0, P = 0, K = 0, W = 0, U = 0, S = 0, ns = 0;
+    int C = 1, N = 0, P = 0, K = 0, W = 0, U = 0, S = 0, ns = 0, thin = 1;   // S = kept sweeps (hist_count)
     bool relabel = false, replay = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -191,6 +191,7 @@ int check_args(int sampler, const bmm_args *a, const bmm_init *init) {
     if (a->nsamples < 2) return fail(BMM_ERR_INVALID, "nsamples must be >= 2");
     if (a->K < 1 || a->K > 255) return fail(BMM_ERR_INVALID, "K / maxK must be in 1..255");
     if (a->burnin < 0 || a->burnin >= a->nsamples) return fail(BMM_ERR_INVALID, "burnin must be in [0, nsamples)");
+    if (a->thin < 0) return fail(BMM_ERR_INVALID, "thin must be >= 0 (0 / 1 = keep every sweep)");
     if (a->relabel) {
         // the reference's behaviour is undefined otherwise
         if (a->burnin < 2) return fail(BMM_ERR_INVALID, "relabel needs burnin >= 2 (Q is initialised at sweep burnin-1)");
@@ -317,7 +318,7 @@ int create_full(bmm_plan *pl, const bmm_init *init) {
     }
     bmm::FullParams &f = pl->fp;
     f.N = N; f.P = P; f.K = K; f.U = U; f.W = W;
-    f.nsamples = ns; f.burnin = a.burnin; f.relabel = pl->relabel; f.burnrelabel = a.burnrelabel;
+    f.nsamples = ns; f.burnin = a.burnin; f.relabel = pl->relabel; f.burnrelabel = a.burnrelabel; f.thin = pl->thin;
     f.stickbreaking = pl->sampler == BMM_SAMPLER_STICKBREAKING;
     f.alpha0 = a.alpha; f.beta = a.beta; f.gamma = a.gamma; f.a = a.a; f.b = a.b;
     f.seed = a.seed; f.chain_offset = a.chain_offset; f.flags = a.flags; f.use_hist = use_hist;
@@ -397,7 +398,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     pl->sm_count = prop.multiProcessorCount;
     bmm::BigParams &b = pl->bp;
     b.N_global = n_global; b.row_offset = a.row_offset; b.N_local = N; b.P = P; b.K = K; b.W = W;
-    b.nsamples = ns; b.burnin = a.burnin; b.stickbreaking = pl->sampler == BMM_SAMPLER_STICKBREAKING;
+    b.nsamples = ns; b.burnin = a.burnin; b.stickbreaking = pl->sampler == BMM_SAMPLER_STICKBREAKING; b.thin = pl->thin;
     b.precision = a.precision; b.tables_in_smem = bmm::big_tables_fit_smem(K, P, a.precision); b.keep_history = keep;
     b.alpha0 = a.alpha; b.beta = a.beta; b.gamma = a.gamma; b.a = a.a; b.b = a.b;
     b.seed = a.seed; b.chain_offset = a.chain_offset; b.flags = a.flags;
@@ -500,8 +501,9 @@ int sweep_back(bmm_plan *pl, int j) {
                                  pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
         if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
             return fail(BMM_ERR_NCCL, bmm::dist_error());
+        const int slot = bmm::hist_slot(j, burnin, pl->thin);
         CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
-                                   pl->perm_out.as<int>() + (j - burnin), pl->S, pl->stream));
+                                   slot >= 0 ? pl->perm_out.as<int>() + slot : nullptr, pl->S, pl->stream));
         if (st_fixed) CU(bmm::launch_grid_invert_perm(1, K, pl->perm_cur.as<int>(), pl->perm_inv.as<int>(), pl->stream));
         CU(bmm::launch_grid_qupdate(N, K, pl->Qf.as<float>(), pl->probs_f32.as<float>(),
                                     st_fixed ? pl->perm_inv.as<int>() : pl->perm_cur.as<int>(), j, pl->sm_count, pl->stream, st_fixed));
@@ -706,7 +708,7 @@ int create_collapsed(bmm_plan *pl, const bmm_init *init) {
     bmm::CollapsedParams &q = pl->cp;
     q.N = N; q.P = P; q.K = K; q.W = W;
     q.nsamples = ns; q.burnin = a.burnin; q.relabel = pl->relabel; q.burnrelabel = a.burnrelabel; q.dp = dp;
-    q.fp32 = a.precision == BMM_FP32;
+    q.fp32 = a.precision == BMM_FP32; q.thin = pl->thin;
     q.alpha0 = a.alpha; q.beta = a.beta; q.gamma = a.gamma; q.a = a.a; q.b = a.b;
     q.seed = a.seed; q.chain_offset = a.chain_offset; q.flags = a.flags;
     q.xbits = pl->xbits.as<uint32_t>();
@@ -873,7 +875,9 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
     bmm_plan *pl = new bmm_plan();
     pl->sampler = sampler; pl->a = *args;
     pl->C = args->n_chains < 1 ? 1 : args->n_chains;
-    pl->N = args->N; pl->P = args->P; pl->K = args->K; pl->ns = args->nsamples; pl->S = args->nsamples - args->burnin;
+    pl->N = args->N; pl->P = args->P; pl->K = args->K; pl->ns = args->nsamples;
+    pl->thin = args->thin > 1 ? args->thin : 1;
+    pl->S = bmm::hist_count(args->nsamples, args->burnin, pl->thin);
     pl->relabel = args->relabel != 0; pl->replay = args->replay != nullptr;
     int rc = BMM_OK;
     cudaError_t e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
@@ -947,7 +951,7 @@ int bmm_plan_run(bmm_plan *pl) {
     CU(cudaEventRecord(pl->evk1, pl->stream));
     const int eb = pl->deb;
     if (pl->z_orig.p)
-        CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->K, pl->zhist.as<uint8_t>(),
+        CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->thin, pl->K, pl->zhist.as<uint8_t>(),
                                   pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
                                   pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
     CU(cudaEventRecord(pl->evs[4], pl->stream));
@@ -1061,6 +1065,23 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
         }
     }
     CU(d2h(out->counts, pl->counts_out, ns * (K + K * P) * 4));
+    std::vector<uint8_t> zlast_chain;
+    if (!pl->grid_path) {
+        // posterior summaries of the chain-parallel paths (f2): allocation counts over the kept sweeps (relabelled when
+        // relabel), last sweep's allocations -- what a caller keeps instead of the S x N histories
+        if (out->z_freq) {
+            const DevBuf &zsrc = pl->relabel ? pl->z_rel : pl->z_orig;
+            if (!zsrc.p) return fail(BMM_ERR_INVALID, "z_freq needs the allocation history on the device");
+            if (!pl->zfreq.p) CU(pl->zfreq.alloc(C * N * K * 4, false));
+            CU(bmm::launch_chain_zfreq((int)C, (int)N, (int)S, (int)K, zsrc.p, pl->deb, pl->zfreq.as<unsigned>(), pl->stream));
+            CU(d2h(out->z_freq, pl->zfreq, C * N * K * 4));
+        }
+        if (out->z_last && pl->zhist.p) {
+            zlast_chain.resize(C * N);
+            CU(cudaMemcpy2DAsync(zlast_chain.data(), N, pl->zhist.as<uint8_t>() + (ns - 1) * N, ns * N, N, C,
+                                 cudaMemcpyDeviceToHost, pl->stream));
+        }
+    }
     if (pl->grid_path) {
         CU(d2h(out->z_freq, pl->zfreq, N * K * 4));
         if (out->z_last && pl->zhist.p) {   // bytes -> int32 through a small staging vector
@@ -1072,6 +1093,7 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     CU(d2h(out->status, pl->status, C * 4));
     CU(cudaStreamSynchronize(pl->stream));
     for (size_t i = 0; i < zlast_host.size(); ++i) out->z_last[i] = (int32_t)zlast_host[i];
+    for (size_t i = 0; i < zlast_chain.size(); ++i) out->z_last[i] = (int32_t)zlast_chain[i];
     if (!qf_host.empty())   // grid path keeps Q as row-major float; the ABI returns N x K column-major double
         for (size_t i = 0; i < N; ++i)
             for (size_t k = 0; k < K; ++k) out->Q_final[i + N * k] = (double)qf_host[i * K + k];

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
     __shared__ double ag[4];
     __shared__ double sh_w0[128];
     __shared__ int sh_c[256];
-    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = ns - p.burnin, tid = threadIdx.x;
+    const int K = p.K, P = p.P, KP = K * P, ns = p.nsamples, S = hist_count(ns, p.burnin, p.thin), tid = threadIdx.x;
+    const int sidx = hist_slot(j, p.burnin, p.thin);
     const int blk = blockIdx.x;
     const bool replay = p.rtheta != nullptr;
     int *cur = p.counts + (size_t)(j & 1) * (K + KP);
@@ -243,9 +244,9 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
                 p.theta_cur[e] = th;
                 p.w1[e] = l1;
                 p.w0[e] = l0;
-                if (p.theta_out && j >= p.burnin) p.theta_out[(size_t)KP * (j - p.burnin) + e] = th;
-                if (p.theta_rel_out && j >= p.burnin)   // theta_rel[perm[k], :] = theta[k, :] (full_gibbs.cpp:221-223)
-                    p.theta_rel_out[(size_t)KP * (j - p.burnin) + p.perm_cur[k] + (size_t)K * d] = th;
+                if (p.theta_out && sidx >= 0) p.theta_out[(size_t)KP * sidx + e] = th;
+                if (p.theta_rel_out && sidx >= 0)   // theta_rel[perm[k], :] = theta[k, :] (full_gibbs.cpp:221-223)
+                    p.theta_rel_out[(size_t)KP * sidx + p.perm_cur[k] + (size_t)K * d] = th;
                 if (p.ws_b1) {
                     ws_store_cell(p.ws_b1, k, d, l1, l0);
                     sh_w0[d] = l0;
@@ -336,9 +337,9 @@ __global__ void __launch_bounds__(UPD_THREADS) big_update_kernel(const BigParams
     for (int k = tid; k < K; k += blockDim.x) {
         const double pk = p.pi_cur[k];
         p.lpi[k] = log(pk);
-        if (p.pi_out && j >= p.burnin) p.pi_out[(j - p.burnin) + (size_t)S * k] = pk;
+        if (p.pi_out && sidx >= 0) p.pi_out[sidx + (size_t)S * k] = pk;
     }
-    if (tid == 0 && p.alpha_out && j >= p.burnin) p.alpha_out[j - p.burnin] = *p.alpha_cur;
+    if (tid == 0 && p.alpha_out && sidx >= 0) p.alpha_out[sidx] = *p.alpha_cur;
     if (tid == 0) upd_stamp(j, 4);
     // In inbox mode nothing above waited for the sweep kernel itself, only for its tagged words.  Whatever follows in the
     // stream is ordered after THIS grid, so this grid completes only once the sweep kernel has (its allocation history
@@ -361,7 +362,7 @@ __global__ void ws_table_kernel(const BigParams p) {
 
 // Log tables of the initial state (sweep 1 reads theta_0, pi_0); iteration 0 of the histories.
 __global__ void big_init_kernel(const BigParams p) {
-    const int K = p.K, P = p.P, KP = K * P, S = p.nsamples - p.burnin;
+    const int K = p.K, P = p.P, KP = K * P, S = hist_count(p.nsamples, p.burnin, p.thin);
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + KP; t += gridDim.x * blockDim.x) {
         if (t < K) {
             const double pk = p.pi_cur[t];

@@ -69,7 +69,7 @@ __device__ inline double *stash_target(const CollapsedParams &p, int c, int j) {
 template <bool DP = false>
 __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s, int c, int j, double *alpha_sh,
                                             int Kalpha, const int *used, int nused) {
-    const int lane = threadIdx.x, K = p.K, P = p.P, N = p.N, ns = p.nsamples, S = ns - p.burnin;
+    const int lane = threadIdx.x, K = p.K, P = p.P, N = p.N, ns = p.nsamples, S = hist_count(ns, p.burnin, p.thin);
     const size_t NK = (size_t)N * K;
     if (p.relabel) {
         // window sweeps were stashed straight into their cube slice (see stash_target)
@@ -79,8 +79,8 @@ __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s,
                                   p.assign_ws + (size_t)c * assign_ws_bytes(K), (p.flags & 64u) != 0);  // BMM_FLAG_STEPHENS_FIXED
         }
     }
-    if (j >= p.burnin) {
-        const int sidx = j - p.burnin;
+    const int sidx = hist_slot(j, p.burnin, p.thin);
+    if (sidx >= 0) {
         const size_t KP = (size_t)K * P;
         // theta point estimates S_kd / N_k (collapsed_gibbs.cpp:205-219; NaN for empty clusters;
         // dp: only used labels are written, the rest stay 0: collapsed_gibbs_dp.cpp:77,266-281)
@@ -103,7 +103,7 @@ __device__ inline void collapsed_after_sweep(const CollapsedParams &p, CSmem &s,
             al = update_alpha_dev<DP>(st, al, p.a, p.b, N, Kalpha);
         }
         *alpha_sh = al;
-        if (j >= p.burnin) p.alpha_out[(size_t)c * S + (j - p.burnin)] = al;
+        if (sidx >= 0) p.alpha_out[(size_t)c * S + sidx] = al;
     }
     __syncthreads();
 }
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(32) collapsed_kernel(const CollapsedParams p) 
     for (int k = lane; k < K; k += 32) s.perm[k] = k;
     if (lane == 0) alpha_sh = p.alpha_cur[c];
     __syncthreads();
-    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * hist_count(ns, p.burnin, p.thin)] = alpha_sh;
     double alpha_tab = -1.0;
     const uint2 key = make_uint2((uint32_t)p.seed, chain);
     const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32) collapsed_fast_kernel(const CollapsedParam
     if (lane < K) Nk = p.cnt[((size_t)c * K + lane) * P1 + P];
     if (lane == 0) alpha_sh = p.alpha_cur[c];
     __syncthreads();
-    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * hist_count(ns, p.burnin, p.thin)] = alpha_sh;
     double alpha_tab = -1.0;
     const uint2 key = make_uint2((uint32_t)p.seed, chain);
     const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(32) collapsed_prod_kernel(const CollapsedParam
     }
     if (lane == 0) alpha_sh = p.alpha_cur[c];
     __syncthreads();
-    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * hist_count(ns, p.burnin, p.thin)] = alpha_sh;
     const uint2 key = make_uint2((uint32_t)p.seed, chain);
     const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
 
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(32) dp_kernel(const CollapsedParams p) {
     __syncthreads();
     const uint2 key = make_uint2((uint32_t)p.seed, chain);
     const uint32_t sid = ST_Z ^ ((uint32_t)(p.seed >> 32) << 8);
-    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * (ns - p.burnin)] = alpha_sh;
+    if (p.j_begin == 1 && p.burnin == 0 && lane == 0) p.alpha_out[(size_t)c * hist_count(ns, p.burnin, p.thin)] = alpha_sh;
     const double RHS_newk = P * (log(p.beta) - log(p.beta + p.gamma));  // (:71)
     // Philox mode, when the products stay inside the double range: the conditional in product form, as in
     // collapsed_prod_kernel -- N_k prod_d (beta + S_kd | gamma + N_k - S_kd) (beta + gamma + N_k)^-P for an existing

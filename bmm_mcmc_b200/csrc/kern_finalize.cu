@@ -9,15 +9,15 @@ namespace bmm {
 namespace {
 
 template <typename OutT>
-__global__ void finalize_z_kernel(int N, int nsamples, int burnin, int K, const uint8_t *__restrict__ zhist,
+__global__ void finalize_z_kernel(int N, int nsamples, int burnin, int thin, int K, const uint8_t *__restrict__ zhist,
                                   const int *__restrict__ perm_out, OutT *__restrict__ z_orig, OutT *__restrict__ z_rel) {
     __shared__ uint8_t tile[32][33];
-    const int c = blockIdx.z, S = nsamples - burnin;
+    const int c = blockIdx.z, S = hist_count(nsamples, burnin, thin);
     const int i0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
     const uint8_t *src = zhist + ((size_t)c * nsamples + burnin) * N;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int s = s0 + r, i = i0 + threadIdx.x;
-        tile[r][threadIdx.x] = (s < S && i < N) ? src[(size_t)s * N + i] : 0;
+        tile[r][threadIdx.x] = (s < S && i < N) ? src[(size_t)s * thin * N + i] : 0;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -33,11 +33,11 @@ __global__ void finalize_z_kernel(int N, int nsamples, int burnin, int K, const 
 
 // Byte-wide output with N and S multiples of 4: 64 x 64 tiles, 32-bit loads along the observations and
 // 32-bit stores along the sweeps (the 1-byte-per-thread version above reached ~1 TB/s of the 6.4).
-__global__ void __launch_bounds__(256) finalize_z_u8x4_kernel(int N, int nsamples, int burnin, int K,
+__global__ void __launch_bounds__(256) finalize_z_u8x4_kernel(int N, int nsamples, int burnin, int thin, int K,
                                                               const uint8_t *__restrict__ zhist, const int *__restrict__ perm_out,
                                                               uint8_t *__restrict__ z_orig, uint8_t *__restrict__ z_rel) {
     __shared__ uint8_t tile[64][68];
-    const int c = blockIdx.z, S = nsamples - burnin, t = threadIdx.x;
+    const int c = blockIdx.z, S = hist_count(nsamples, burnin, thin), t = threadIdx.x;
     const int i0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
     const uint8_t *src = zhist + ((size_t)c * nsamples + burnin) * N;
     {
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) finalize_z_u8x4_kernel(int N, int nsample
         for (int r = t >> 4; r < 64; r += 16) {
             const int s = s0 + r, i = i0 + 4 * col4;
             uint32_t v = 0u;
-            if (s < S && i < N) v = *(const uint32_t *)(src + (size_t)s * N + i);   // N % 4 == 0: i + 3 < N
+            if (s < S && i < N) v = *(const uint32_t *)(src + (size_t)s * thin * N + i);   // N % 4 == 0: i + 3 < N
             *(uint32_t *)&tile[r][4 * col4] = v;
         }
     }
@@ -79,9 +79,10 @@ __global__ void expand_rows_kernel(int N, int U, int K, const int *__restrict__ 
 
 }  // namespace
 
-cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
+cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int thin, int K, const uint8_t *zhist,
                               const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st) {
-    const int S = nsamples - burnin;
+    if (thin < 1) thin = 1;
+    const int S = hist_count(nsamples, burnin, thin);
     if (S <= 0 || N <= 0) return cudaSuccess;
     dim3 block(32, 8);
     for (int c0 = 0; c0 < n_chains; c0 += 65535) {
@@ -91,14 +92,47 @@ cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int
         const int *pm = perm_out ? perm_out + (size_t)c0 * S * K : nullptr;
         const size_t off = (size_t)c0 * S * N;
         if (elem_bytes == 4)
-            finalize_z_kernel<int32_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+            finalize_z_kernel<int32_t><<<grid, block, 0, st>>>(N, nsamples, burnin, thin, K, zh, pm,
                 z_orig ? (int32_t *)z_orig + off : nullptr, z_rel ? (int32_t *)z_rel + off : nullptr);
         else if (N % 4 == 0 && S % 4 == 0)
-            finalize_z_u8x4_kernel<<<dim3((N + 63) / 64, (S + 63) / 64, nc), 256, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+            finalize_z_u8x4_kernel<<<dim3((N + 63) / 64, (S + 63) / 64, nc), 256, 0, st>>>(N, nsamples, burnin, thin, K, zh, pm,
                 z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
         else
-            finalize_z_kernel<uint8_t><<<grid, block, 0, st>>>(N, nsamples, burnin, K, zh, pm,
+            finalize_z_kernel<uint8_t><<<grid, block, 0, st>>>(N, nsamples, burnin, thin, K, zh, pm,
                 z_orig ? (uint8_t *)z_orig + off : nullptr, z_rel ? (uint8_t *)z_rel + off : nullptr);
+        g_launches++;
+    }
+    return cudaGetLastError();
+}
+
+// chain-parallel posterior summary: one thread per (chain, observation) walks its column of the kept history
+template <typename T>
+__global__ void chain_zfreq_kernel(int N, int S, int K, const T *__restrict__ z, unsigned *__restrict__ zfreq) {
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const T *col = z + (size_t)c * S * N + (size_t)S * i;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        unsigned cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < S; ++s) {
+            const int r = (int)col[s] - 1 - k0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cnt[q] += (r == q) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (k0 + q < K) zfreq[(size_t)c * N * K + i + (size_t)N * (k0 + q)] = cnt[q];
+    }
+}
+
+cudaError_t launch_chain_zfreq(int n_chains, int N, int S, int K, const void *z, int elem_bytes, unsigned *zfreq, cudaStream_t st) {
+    if (n_chains < 1 || N < 1 || S < 1) return cudaSuccess;
+    for (int c0 = 0; c0 < n_chains; c0 += 65535) {
+        const int nc = n_chains - c0 < 65535 ? n_chains - c0 : 65535;
+        dim3 grid((N + 127) / 128, nc);
+        const size_t off = (size_t)c0 * S * N;
+        if (elem_bytes == 4) chain_zfreq_kernel<int32_t><<<grid, 128, 0, st>>>(N, S, K, (const int32_t *)z + off, zfreq + (size_t)c0 * N * K);
+        else chain_zfreq_kernel<uint8_t><<<grid, 128, 0, st>>>(N, S, K, (const uint8_t *)z + off, zfreq + (size_t)c0 * N * K);
         g_launches++;
     }
     return cudaGetLastError();

@@ -50,7 +50,7 @@ __device__ __forceinline__ void full_chain_body(const FullParams &p) {
     full_layout(p, smem_raw, &s);
     const int c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int K = p.K, P = p.P, U = p.U, N = p.N, W = p.W, KP = K * P, ns = p.nsamples;
-    const int S = ns - p.burnin;
+    const int S = hist_count(ns, p.burnin, p.thin);
     const size_t UK = (size_t)U * K;
     const uint32_t chain = (uint32_t)(p.chain_offset + c);
     const bool replay = p.ru != nullptr;
@@ -279,8 +279,8 @@ __device__ __forceinline__ void full_chain_body(const FullParams &p) {
             phase_f(tid, nthr, [] { __syncthreads(); });
         }
         __syncthreads();
-        if (j >= p.burnin) {
-            const int sidx = j - p.burnin;
+        const int sidx = hist_slot(j, p.burnin, p.thin);
+        if (sidx >= 0) {
             for (int t = tid; t < KP; t += nthr) {
                 p.theta_out[(size_t)c * KP * S + (size_t)KP * sidx + t] = s.theta[t];
                 if (p.relabel) {

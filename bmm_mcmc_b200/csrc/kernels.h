@@ -8,6 +8,20 @@ namespace bmm {
 // Counter of kernel launches made by this library (bmm_launch_count()).
 extern unsigned long long g_launches;
 
+// History thinning (f2): the returned histories keep every thin-th post-burn-in sweep, j = burnin + t * thin
+// (the reference keeps them all: full_gibbs.cpp:52-57,233-248).  hist_slot: index of sweep j in the kept histories
+// or -1; hist_count: number of kept sweeps.
+__host__ __device__ inline int hist_slot(int j, int burnin, int thin) {
+    const int r = j - burnin;
+    if (r < 0) return -1;
+    if (thin <= 1) return r;
+    return (r % thin) ? -1 : r / thin;
+}
+__host__ __device__ inline int hist_count(int nsamples, int burnin, int thin) {
+    const int S = nsamples - burnin;
+    return thin > 1 ? (S + thin - 1) / thin : S;
+}
+
 // cudaFuncSetAttribute is per device: remember, per kernel, the value already set on each device.
 struct FuncAttrCache {
     int set[64] = {};
@@ -30,6 +44,7 @@ struct FuncAttrCache {
 struct FullParams {
     int N, P, K, U, W;            // W = 32-bit words per row
     int nsamples, burnin, relabel, burnrelabel, stickbreaking;
+    int thin;                     // history thinning (hist_slot)
     int j_begin, j_end;           // sweeps [j_begin, j_end)
     double alpha0, beta, gamma, a, b;
     unsigned long long seed;
@@ -76,6 +91,7 @@ struct CollapsedParams {
     int nsamples, burnin, relabel, burnrelabel, dp;
     int j_begin, j_end;
     int fp32;                     // BMM_FP32: single-precision weights in the product-form kernel
+    int thin;                     // history thinning (hist_slot)
     double alpha0, beta, gamma, a, b;
     unsigned long long seed;
     int chain_offset;
@@ -115,6 +131,7 @@ struct BigParams {
     long long N_global, row_offset;   // this rank holds observations [row_offset, row_offset + N_local)
     int N_local, P, K, W;
     int nsamples, burnin, stickbreaking, precision;
+    int thin;                         // history thinning (hist_slot)
     int tables_in_smem;               // K*P log tables + count histogram fit shared memory
     int keep_history;                 // zhist holds every sweep ([nsamples][N_local]) or only the current one
     double alpha0, beta, gamma, a, b;
@@ -245,8 +262,11 @@ cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long s
 // ---- history layout conversion (kern_finalize.cu) --------------------------------------------
 // zhist [c][nsamples][N] uint8 -> R layout [c][S x N cm]; optional relabelling through perm_out.
 // elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).
-cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int K, const uint8_t *zhist,
+cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int thin, int K, const uint8_t *zhist,
                               const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st);
+// posterior summary of the chain-parallel paths: zfreq[c][i + N*k] = number of kept sweeps with z[c][s, i] == k + 1;
+// z is the R-layout history [c][S x N cm] of elem_bytes-wide labels
+cudaError_t launch_chain_zfreq(int n_chains, int N, int S, int K, const void *z, int elem_bytes, unsigned *zfreq, cudaStream_t st);
 // expand a per-row matrix [c][U*K] to per-observation [c][N*K]
 cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
                                cudaStream_t st);

@@ -102,6 +102,12 @@ typedef struct bmm_args {
      * ranks of bmm_dist_init each sweep.  0 = not sharded (n_global = N).                         */
     int64_t n_global;
     int64_t row_offset;
+    /* History thinning: keep every thin-th post-burn-in sweep (j = burnin + t * thin) in ALL returned histories
+     * (pi, alpha, permutations, z, theta, ...), i.e. S = ceil((nsamples - burnin) / thin) everywhere below.
+     * 0 / 1 = keep every sweep, the reference's behaviour (full_gibbs.cpp:52-57,233-248).  The sampler and the
+     * online relabelling still run every sweep; only the storage is thinned.                              */
+    int32_t thin;
+    int32_t reserved_;
 } bmm_args;
 
 /* Initial state, drawn by the R wrappers before entering C++ (R/utils.R:42,68-74,98-103). */

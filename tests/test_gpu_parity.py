@@ -855,3 +855,66 @@ def test_grid_posterior_summaries(datasets, relabel):
     h = B.gibbs_full(X, ns, K, probes=("z_freq", "z_last"), no_z_history=True, **kw)
     assert "z" not in h and np.array_equal(h["z_freq"], g["z_freq"]) and np.array_equal(h["z_last"], g["z_last"])
     _close(h["theta"], g["theta"], rtol=0)
+
+
+@pytest.mark.parametrize("sampler", ["full", "stickbreaking", "collapsed", "dp", "grid", "grid_tensor"])
+def test_thinning_keeps_every_kth_sweep(datasets, sampler):
+    """thin = k (f2): every returned history holds the sweeps burnin, burnin + k, ... of the un-thinned run -- same
+    chain, same relabelling (which still runs every sweep), a k-th of the storage."""
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    ns, burnin, thin = 48, 11, 3
+    kw = dict(burnin=burnin, relabel=True, burnrelabel=4, seed=13)
+    if sampler in ("full", "stickbreaking", "grid", "grid_tensor"):
+        f = B.gibbs_stickbreaking if sampler == "stickbreaking" else B.gibbs_full
+        kw.update(chains=1 if sampler.startswith("grid") else 2, grid_path=sampler.startswith("grid"),
+                  precision="fp32" if sampler == "grid_tensor" else "fp64")
+        run = lambda **e: f(X, ns, 4, **kw, **e)
+    elif sampler == "collapsed":
+        kw.update(chains=2)
+        run = lambda **e: B.gibbs_collapsed(X, ns, 3, **kw, **e)
+    else:
+        kw.update(chains=2)
+        run = lambda **e: B.gibbs_dp(X, ns, maxK=12, **kw, **e)
+    full = run()
+    thinned = run(thin=thin)
+    S = ns - burnin
+    keep = np.arange(0, S, thin)
+    assert set(full) == set(thinned)
+    for k, v in full.items():
+        multi = kw["chains"] > 1
+        if k in ("theta", "theta_original"):
+            want = v[..., keep]
+        elif multi:
+            want = v[:, keep]
+        else:
+            want = v[keep]
+        assert thinned[k].shape == want.shape, (k, thinned[k].shape, want.shape)
+        assert np.array_equal(thinned[k], want, equal_nan=True), (sampler, k)
+
+
+@pytest.mark.parametrize("sampler,relabel", [("full", True), ("collapsed", False), ("dp", True)])
+def test_chain_path_posterior_summaries(datasets, sampler, relabel):
+    """z_freq / z_last on the chain-parallel paths (f2): allocation counts over the kept sweeps (relabelled when
+    relabel) and the last sweep's allocations, equal to the same summaries computed from the returned history."""
+    _need_gpu()
+    X = datasets["K2_N100_P5"]
+    N = X.shape[0]
+    ns, burnin, C_ = 40, 10, 3
+    kw = dict(burnin=burnin, relabel=relabel, burnrelabel=4, seed=3, chains=C_, probes=("z_freq", "z_last"), thin=2)
+    if sampler == "full":
+        K = 3
+        g = B.gibbs_full(X, ns, K, **kw)
+    elif sampler == "collapsed":
+        K = 3
+        g = B.gibbs_collapsed(X, ns, K, **kw)
+    else:
+        K = 10
+        g = B.gibbs_dp(X, ns, maxK=K, **kw)
+    assert g["z_freq"].shape == (C_, N, K) and g["z_last"].shape == (C_, N)
+    freq = np.stack([(g["z"] == k + 1).sum(1) for k in range(K)], axis=2)
+    assert np.array_equal(g["z_freq"], freq)
+    zo = g["z_original"] if relabel else g["z"]
+    if (ns - 1 - burnin) % 2 == 0:      # the last sweep is a kept one
+        assert np.array_equal(g["z_last"], zo[:, -1])
+    assert g["z_last"].min() >= 1 and g["z_last"].max() <= K
