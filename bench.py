@@ -743,6 +743,7 @@ def main():
         r = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    d2h = int(_lib.lib().bmm_fetch_bytes())     # counted by the library over the last call's device-to-host copies
     zmax = int(r["z"][0, -1].max())
     assert 1 <= zmax <= K
 
@@ -789,13 +790,15 @@ def main():
         "config": {"workload": "%s, %d chains/GPU, nsamples=%d burnin=%d, relabel=%s burnrelabel=%d"
                                % (WL["label"], C_, ns, burnin, relabel, br),
                    "chains_per_gpu": C_, "nsamples": ns, "parallelism": "chains split across GPUs, no collective",
-                   "l2": "per-step histories (%.1f GB written) exceed the 126 MB L2; no explicit flush" % (d2h / 1e9 + C_ * ns * N / 1e9)},
+                   "l2": "per-step histories (%.1f GB written on the device) exceed the 126 MB L2; no explicit flush" % (2 * C_ * ns * N / 1e9)},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "allocation updates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "host_output_bytes_per_step": int(host_out),
                 "ms_per_step": 1e3 * tm[2] / a.steps,
-                "api": "bmm_mcmc_b200.gibbs_%s -> bmm_gibbs_%s (C ABI), pinned host output buffers; the S x N int32 "
-                       "allocation matrices cross PCIe as bytes and are widened on the host" % (smp, smp)},
+                "api": "bmm_mcmc_b200.gibbs_%s -> bmm_gibbs_%s (C ABI), pinned host output buffers; d2h bytes counted by the "
+                       "library: most chains' allocations cross PCIe as one byte each, sweep segment by sweep segment while "
+                       "the later sweeps run, and the host widens them to the two int32 matrices (z = perm[z_original]); the "
+                       "remaining chains are widened on the device and DMA'd" % (smp, smp)},
         "gpu_launches": launches,
         "roofline": roofline,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,

@@ -56,7 +56,7 @@ EXPORTS = [
     "bmm_gibbs_full", "bmm_gibbs_stickbreaking", "bmm_gibbs_collapsed", "bmm_gibbs_dp", "bmm_stephens_batch",
     "bmm_stephens_online", "bmm_stephens_batch_ex", "bmm_stephens_online_ex", "bmm_assign", "bmm_assign_warp", "bmm_grid_cost", "bmm_rdirichlet", "bmm_debug_ws_trace", "bmm_debug_ws_cta", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
     "bmm_plan_sync", "bmm_plan_elapsed_ms", "bmm_plan_fetch", "bmm_plan_destroy", "bmm_dist_unique_id",
-    "bmm_dist_init", "bmm_dist_finalize", "bmm_dist_p2p_local", "bmm_dist_p2p_attach", "bmm_dist_p2p_detach", "bmm_plan_kernel_ms", "bmm_host_alloc", "bmm_host_free", "bmm_release_cache", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_version",
+    "bmm_dist_init", "bmm_dist_finalize", "bmm_dist_p2p_local", "bmm_dist_p2p_attach", "bmm_dist_p2p_detach", "bmm_plan_kernel_ms", "bmm_host_alloc", "bmm_host_free", "bmm_release_cache", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_fetch_bytes", "bmm_version",
 ]
 
 _lib = None
@@ -79,6 +79,7 @@ def lib():
         L.bmm_last_error.restype = C.c_char_p
         L.bmm_version.restype = C.c_char_p
         L.bmm_launch_count.restype = C.c_uint64
+        L.bmm_fetch_bytes.restype = C.c_uint64
         L.bmm_plan_create.argtypes = [C.c_int32, C.POINTER(Args), C.POINTER(Init), C.POINTER(C.c_void_p)]
         for f in ("bmm_plan_run", "bmm_plan_sync", "bmm_plan_destroy"):
             getattr(L, f).argtypes = [C.c_void_p]

@@ -30,10 +30,13 @@ namespace bmm {
 bool full_rows_fit_smem(int U, int K);
 }
 extern "C" void bmm_widen_u8_i32(const uint8_t *src, int32_t *dst, size_t n, int threads);  // host_widen.cpp
+extern "C" void bmm_widen_runs_u8_i32(const uint8_t *src, size_t x0, size_t n, int L, int S, int s_off, int N, int K,
+                                      const int32_t *perm, int32_t *dst_z, int32_t *dst_zo, int threads);
 
 namespace {
 
 thread_local std::string g_err;
+thread_local uint64_t g_fetch_bytes = 0;   // device-to-host bytes of this thread's last bmm_plan_fetch
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -141,6 +144,14 @@ struct bmm_plan {
     bmm::BigParams bp{};
     bool grid_path = false;       // one chain over the whole GPU (kern_big.cu)
     int deb = 4;                  // bytes per allocation of the device-side R-layout z (1: widened on the host)
+    bool derive_z = false;        // only z_original crosses PCIe; the host applies `permutations` while widening
+    // Download of the chain-parallel paths when the host widens (deb == 1): the allocations travel as bytes, one buffer per
+    // sweep segment, so that a segment is copied and widened while the next one is still being sampled.  (Widening a share
+    // of the chains on the device and DMA-ing their int32 matrices beside the host workers was measured and lost: the
+    // link of the GPU boxes moves ~25 GB/s, the 12 workers write ~130-150 GB/s.)
+    std::vector<int> seg_slot;    // nseg + 1 boundaries in kept-history slots
+    std::vector<cudaEvent_t> seg_ev;
+    cudaStream_t copy_stream = nullptr;
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of the timed sweep kernels of the last run (grid path)
     int ev_stride = 1;            // every ev_stride-th sweep kernel is bracketed by events (0: none)
@@ -178,6 +189,8 @@ struct bmm_plan {
         if (evk1) cudaEventDestroy(evk1);
         for (auto &e : evs) if (e) cudaEventDestroy(e);
         for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : seg_ev) if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto &g : gexec) if (g) cudaGraphExecDestroy(g);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -764,8 +777,13 @@ struct Staging {
 std::mutex g_stage_m;                 // one download at a time per process: the staging buffers are shared
 std::map<int, Staging> g_stages;      // per device (events belong to the device they were created on)
 
-int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
-    if (!dst || !src.p || n == 0) return BMM_OK;
+// Bytes [0, n) of `src` -- one sweep segment (L of the S kept sweeps, starting at s_off) of `rows` (chain, observation)
+// pairs -- through the pinned staging buffers into the int32 matrices.  perm == NULL: dst_zo receives the widened bytes.
+// perm != NULL: the bytes are z_original; dst_zo receives them and dst_z the relabelled allocations (either may be NULL).
+// The copies run on `cs`, which the caller has ordered after the kernels that produce `src`.
+int fetch_widen(bmm_plan *pl, cudaStream_t cs, const uint8_t *src, size_t n, int L, int s_off, const int32_t *perm,
+                int32_t *dst_z, int32_t *dst_zo) {
+    if ((!dst_z && !dst_zo) || !src || n == 0) return BMM_OK;
     const size_t CH = (size_t)32 << 20;
     std::lock_guard<std::mutex> lock(g_stage_m);
     Staging &g_stage = g_stages[pl->a.device];
@@ -792,15 +810,17 @@ int fetch_widen(bmm_plan *pl, int32_t *dst, const DevBuf &src, size_t n) {
     const size_t nch = (n + CH - 1) / CH;
     auto issue = [&](size_t c) -> cudaError_t {
         const size_t lo = c * CH, cnt = lo + CH <= n ? CH : n - lo;
-        cudaError_t e = cudaMemcpyAsync(g_stage.buf[c & 1], (const uint8_t *)src.p + lo, cnt, cudaMemcpyDeviceToHost, pl->stream);
-        return e != cudaSuccess ? e : cudaEventRecord(g_stage.ev[c & 1], pl->stream);
+        cudaError_t e = cudaMemcpyAsync(g_stage.buf[c & 1], src + lo, cnt, cudaMemcpyDeviceToHost, cs);
+        g_fetch_bytes += cnt;
+        return e != cudaSuccess ? e : cudaEventRecord(g_stage.ev[c & 1], cs);
     };
     CU(issue(0));
     for (size_t c = 0; c < nch; ++c) {
         if (c + 1 < nch) CU(issue(c + 1));
         CU(cudaEventSynchronize(g_stage.ev[c & 1]));
         const size_t lo = c * CH, cnt = lo + CH <= n ? CH : n - lo;
-        bmm_widen_u8_i32(g_stage.buf[c & 1], dst + lo, cnt, threads);
+        if (L == pl->S && !perm) bmm_widen_u8_i32(g_stage.buf[c & 1], dst_zo + lo, cnt, threads);
+        else bmm_widen_runs_u8_i32(g_stage.buf[c & 1], lo, cnt, L, pl->S, s_off, pl->N, pl->K, perm, dst_z, dst_zo, threads);
     }
     return BMM_OK;
 }
@@ -858,6 +878,7 @@ extern "C" {
 const char *bmm_last_error(void) { return g_err.c_str(); }
 const char *bmm_version(void) { return "bmm-mcmc_b200 0.1 (sm_100a)"; }
 uint64_t bmm_launch_count(void) { return bmm::g_launches; }
+uint64_t bmm_fetch_bytes(void) { return g_fetch_bytes; }
 
 int bmm_device_count(void) {
     int n = 0;
@@ -906,11 +927,37 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
         const bool widen_dflt = wenv ? wenv[0] != '0' : local_ranks <= 2;
         const bool widen = !(args->flags & BMM_FLAG_COMPACT_Z) && zelems >= ((size_t)8 << 20) && widen_dflt;
         pl->deb = ((args->flags & BMM_FLAG_COMPACT_Z) || widen) ? 1 : 4;
+        // z = perm[z_original] (full_gibbs.cpp:171-174): with host widening the relabelled matrix is derived on the host from
+        // the original one and the permutations instead of crossing PCIe as well (BMM_FETCH_DERIVE=0 ships both)
+        const char *denv = getenv("BMM_FETCH_DERIVE");
+        pl->derive_z = widen && pl->relabel && !pl->grid_path && pl->K <= 16 && !(denv && denv[0] == '0');
         const size_t eb = (size_t)pl->deb;
         const bool no_z = pl->grid_path && (args->flags & BMM_FLAG_NO_Z_HISTORY);
         cudaError_t e2 = cudaSuccess;
-        e2 = no_z ? cudaSuccess : pl->z_orig.alloc(zelems * eb, false);
-        if (e2 == cudaSuccess && pl->relabel) e2 = pl->z_rel.alloc(zelems * eb, false);
+        pl->seg_slot = {0, pl->S};
+        if (widen && !pl->grid_path) {
+            // Sweep segments, on 64-slot boundaries, at least 256 slots each.  Measured on C2 (S = 1800, run 37 ms) in one
+            // session: 1 / 2 / 3 segments 159-170 / 155-159 / 144-146 ms per call; a boundary that does not fall on a cache
+            // line of the output (S * 4 bytes per run need not be a multiple of 64) costs two partial-line streaming stores
+            // per (chain, observation) run, which is what limits the count.
+            const char *senv = getenv("BMM_FETCH_SEGMENTS");
+            int nseg = senv ? atoi(senv) : (pl->S >= 1024 ? 4 : pl->S / 256);
+            if (pl->thin != 1 || nseg < 1) nseg = 1;
+            pl->seg_slot.assign(1, 0);
+            for (int g = 1; g < nseg; ++g) {
+                const int b = (int)(((long long)pl->S * g / nseg) & ~63LL);
+                if (b > pl->seg_slot.back() && b < pl->S) pl->seg_slot.push_back(b);
+            }
+            pl->seg_slot.push_back(pl->S);
+            if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking);
+            for (size_t g = 0; g + 1 < pl->seg_slot.size() && e2 == cudaSuccess; ++g) {
+                cudaEvent_t ev;
+                e2 = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e2 == cudaSuccess) pl->seg_ev.push_back(ev);
+            }
+        }
+        if (e2 == cudaSuccess && !no_z) e2 = pl->z_orig.alloc(zelems * eb, false);
+        if (e2 == cudaSuccess && pl->relabel && !pl->derive_z) e2 = pl->z_rel.alloc(zelems * eb, false);
         if (e2 != cudaSuccess) rc = fail(BMM_ERR_CUDA, std::string("history allocation: ") + cudaGetErrorString(e2));
     }
     if (!rc) rc = snapshot_state(pl);
@@ -932,28 +979,48 @@ int bmm_plan_run(bmm_plan *pl) {
         TRY(run_big(pl));
         CU(cudaEventRecord(pl->evs[1], pl->stream));
         CU(cudaEventRecord(pl->evs[2], pl->stream));
-    } else if (pl->relabel) {
-        TRY(run_segment(pl, 1, burnin));
-        CU(cudaEventRecord(pl->evs[1], pl->stream));
-        const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
-        CU(bmm::launch_stephens_batch(pl->C, pl->U, pl->K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
-                                      pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(),
-                                      pl->logQ.as<double>(), pl->sb_perm.as<int>(), pl->sb_cost.as<double>(),
-                                      pl->sb_ws.as<char>(), pl->stream, (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
-        CU(cudaEventRecord(pl->evs[2], pl->stream));
-        TRY(run_segment(pl, burnin, ns));
     } else {
-        CU(cudaEventRecord(pl->evs[1], pl->stream));
-        CU(cudaEventRecord(pl->evs[2], pl->stream));
-        TRY(run_segment(pl, 1, ns));
+        if (pl->relabel) {
+            TRY(run_segment(pl, 1, burnin));
+            CU(cudaEventRecord(pl->evs[1], pl->stream));
+            const bool full = pl->sampler == BMM_SAMPLER_FULL || pl->sampler == BMM_SAMPLER_STICKBREAKING;
+            CU(bmm::launch_stephens_batch(pl->C, pl->U, pl->K, pl->a.burnrelabel, full ? pl->wt.as<int>() : nullptr,
+                                          pl->cube.as<double>(), pl->logp.as<double>(), pl->Q.as<double>(),
+                                          pl->logQ.as<double>(), pl->sb_perm.as<int>(), pl->sb_cost.as<double>(),
+                                          pl->sb_ws.as<char>(), pl->stream, (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0));
+            CU(cudaEventRecord(pl->evs[2], pl->stream));
+        } else {
+            CU(cudaEventRecord(pl->evs[1], pl->stream));
+            CU(cudaEventRecord(pl->evs[2], pl->stream));
+        }
+        // the kept sweeps, one launch per download segment (a single one unless the host widens, see bmm_plan_create);
+        // a finished segment of the host-widened chains is laid out at once so that its download can start
+        const size_t nseg = pl->seg_slot.size() - 1;
+        int j0 = pl->relabel ? burnin : 1;
+        for (size_t g = 0; g < nseg; ++g) {
+            const int j1 = g + 1 == nseg ? ns : burnin + pl->seg_slot[g + 1];      // segments exist only with thin == 1
+            TRY(run_segment(pl, j0, j1));
+            j0 = j1 > j0 ? j1 : j0;
+            if (nseg > 1) {
+                if (pl->z_orig.p) {
+                    const size_t off = (size_t)pl->C * pl->N * pl->seg_slot[g];
+                    CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->thin, pl->K, pl->zhist.as<uint8_t>(),
+                                              pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.as<uint8_t>() + off,
+                                              pl->z_rel.p ? pl->z_rel.as<uint8_t>() + off : nullptr, 1, pl->stream,
+                                              pl->seg_slot[g], pl->seg_slot[g + 1]));
+                }
+                CU(cudaEventRecord(pl->seg_ev[g], pl->stream));
+            }
+        }
     }
     CU(cudaEventRecord(pl->evs[3], pl->stream));
     CU(cudaEventRecord(pl->evk1, pl->stream));
     const int eb = pl->deb;
-    if (pl->z_orig.p)
+    const bool split = !pl->grid_path && pl->seg_slot.size() > 2;
+    if (pl->z_orig.p && !split)
         CU(bmm::launch_finalize_z(pl->C, pl->N, ns, burnin, pl->thin, pl->K, pl->zhist.as<uint8_t>(),
                                   pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->z_orig.p,
-                                  pl->relabel ? pl->z_rel.p : nullptr, eb, pl->stream));
+                                  pl->relabel && !pl->derive_z ? pl->z_rel.p : nullptr, eb, pl->stream));
     CU(cudaEventRecord(pl->evs[4], pl->stream));
     CU(cudaEventRecord(pl->ev1, pl->stream));
     pl->ran = true;
@@ -1019,11 +1086,40 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
     if (!pl || !out) return fail(BMM_ERR_INVALID, "plan/out is NULL");
     if (!pl->ran) return fail(BMM_ERR_INVALID, "plan has not run");
     CU(cudaSetDevice(pl->a.device));
-    CU(cudaStreamSynchronize(pl->stream));
+    g_fetch_bytes = 0;
     const size_t C = pl->C, S = pl->S, N = pl->N, K = pl->K, P = pl->P, ns = pl->ns;
     const size_t eb = (pl->a.flags & BMM_FLAG_COMPACT_Z) ? 1 : 4;
+    if (pl->deb == 1 && eb == 4 && !pl->grid_path) {
+        // Host-widened chain paths: the allocation matrices are downloaded segment by segment while the later sweeps are
+        // still running on the plan's stream.
+        const size_t nseg = pl->seg_slot.size() - 1;
+        std::vector<int32_t> perm_host;
+        int32_t *perm = nullptr;
+        if (pl->derive_z) {
+            perm = out->permutations;
+            if (!perm) { perm_host.resize(C * S * K); perm = perm_host.data(); }
+        }
+        int32_t *dz = pl->relabel ? out->z : nullptr, *dzo = pl->relabel ? out->z_original : out->z;
+        for (size_t g = 0; g < nseg; ++g) {
+            const int s0 = pl->seg_slot[g], L = pl->seg_slot[g + 1] - s0;
+            CU(cudaStreamWaitEvent(pl->copy_stream, nseg > 1 ? pl->seg_ev[g] : pl->ev1, 0));
+            if (perm) {   // this segment's permutations are final: the whole (small) array again, rows < s0 + L are valid
+                CU(cudaMemcpyAsync(perm, pl->perm_out.p, C * S * K * 4, cudaMemcpyDeviceToHost, pl->copy_stream));
+                g_fetch_bytes += C * S * K * 4;
+                CU(cudaStreamSynchronize(pl->copy_stream));
+            }
+            const size_t off = C * N * (size_t)s0, n = C * N * (size_t)L;
+            if (pl->derive_z) TRY(fetch_widen(pl, pl->copy_stream, pl->z_orig.as<uint8_t>() + off, n, L, s0, perm, dz, dzo));
+            else {
+                if (pl->relabel) TRY(fetch_widen(pl, pl->copy_stream, pl->z_rel.as<uint8_t>() + off, n, L, s0, nullptr, nullptr, dz));
+                TRY(fetch_widen(pl, pl->copy_stream, pl->z_orig.as<uint8_t>() + off, n, L, s0, nullptr, nullptr, dzo));
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(pl->stream));
     auto d2h = [&](void *dst, const DevBuf &src, size_t bytes) -> cudaError_t {
         if (!dst || !src.p || bytes == 0) return cudaSuccess;
+        g_fetch_bytes += bytes;
         return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, pl->stream);
     };
     CU(d2h(out->pi, pl->pi_out, C * S * K * 8));
@@ -1039,12 +1135,12 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
         if (!widen) CU(d2h(out->z, pl->z_orig, C * S * N * eb));
         CU(d2h(out->theta, pl->theta_out, C * K * P * S * 8));
     }
-    if (widen) {
+    if (widen && pl->grid_path) {     // one chain over the whole GPU: a single segment, after the run
         if (pl->relabel) {
-            TRY(fetch_widen(pl, out->z, pl->z_rel, C * S * N));
-            TRY(fetch_widen(pl, out->z_original, pl->z_orig, C * S * N));
+            TRY(fetch_widen(pl, pl->stream, pl->z_rel.as<uint8_t>(), C * S * N, (int)S, 0, nullptr, nullptr, out->z));
+            TRY(fetch_widen(pl, pl->stream, pl->z_orig.as<uint8_t>(), C * S * N, (int)S, 0, nullptr, nullptr, out->z_original));
         } else {
-            TRY(fetch_widen(pl, out->z, pl->z_orig, C * S * N));
+            TRY(fetch_widen(pl, pl->stream, pl->z_orig.as<uint8_t>(), C * S * N, (int)S, 0, nullptr, nullptr, out->z));
         }
     }
     CU(d2h(out->probs, pl->probs_out, C * ns * N * K * 8));
@@ -1070,10 +1166,10 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
         // posterior summaries of the chain-parallel paths (f2): allocation counts over the kept sweeps (relabelled when
         // relabel), last sweep's allocations -- what a caller keeps instead of the S x N histories
         if (out->z_freq) {
-            const DevBuf &zsrc = pl->relabel ? pl->z_rel : pl->z_orig;
-            if (!zsrc.p) return fail(BMM_ERR_INVALID, "z_freq needs the allocation history on the device");
+            if (!pl->zhist.p) return fail(BMM_ERR_INVALID, "z_freq needs the allocation history on the device");
             if (!pl->zfreq.p) CU(pl->zfreq.alloc(C * N * K * 4, false));
-            CU(bmm::launch_chain_zfreq((int)C, (int)N, (int)S, (int)K, zsrc.p, pl->deb, pl->zfreq.as<unsigned>(), pl->stream));
+            CU(bmm::launch_chain_zfreq((int)C, (int)N, (int)ns, pl->a.burnin, pl->thin, (int)K, pl->zhist.as<uint8_t>(),
+                                       pl->relabel ? pl->perm_out.as<int>() : nullptr, pl->zfreq.as<unsigned>(), pl->stream));
             CU(d2h(out->z_freq, pl->zfreq, C * N * K * 4));
         }
         if (out->z_last && pl->zhist.p) {
@@ -1114,6 +1210,7 @@ int bmm_plan_destroy(bmm_plan *pl) {
         // the blocks go back to the free list on delete: nothing of this plan may still be running on them
         cudaSetDevice(pl->a.device);
         if (pl->stream) cudaStreamSynchronize(pl->stream);
+        if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
         delete pl;
     }
     return BMM_OK;

@@ -263,10 +263,11 @@ cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long s
 // zhist [c][nsamples][N] uint8 -> R layout [c][S x N cm]; optional relabelling through perm_out.
 // elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).
 cudaError_t launch_finalize_z(int n_chains, int N, int nsamples, int burnin, int thin, int K, const uint8_t *zhist,
-                              const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st);
-// posterior summary of the chain-parallel paths: zfreq[c][i + N*k] = number of kept sweeps with z[c][s, i] == k + 1;
-// z is the R-layout history [c][S x N cm] of elem_bytes-wide labels
-cudaError_t launch_chain_zfreq(int n_chains, int N, int S, int K, const void *z, int elem_bytes, unsigned *zfreq, cudaStream_t st);
+                              const int *perm_out, void *z_orig, void *z_rel, int elem_bytes, cudaStream_t st, int s_lo = 0, int s_hi = -1);
+// posterior summary of the chain-parallel paths: zfreq[c][i + N*k] = number of kept sweeps whose (relabelled, when perm is
+// given) allocation of observation i is k + 1; reads the raw history [c][nsamples][N]
+cudaError_t launch_chain_zfreq(int n_chains, int N, int nsamples, int burnin, int thin, int K, const uint8_t *zhist, const int *perm,
+                               unsigned *zfreq, cudaStream_t st);
 // expand a per-row matrix [c][U*K] to per-observation [c][N*K]
 cudaError_t launch_expand_rows(int n_chains, int N, int U, int K, const int *rowid, const double *src, double *dst,
                                cudaStream_t st);

@@ -233,6 +233,7 @@ int bmm_release_cache(void);
 const char *bmm_last_error(void);
 int bmm_device_count(void);
 uint64_t bmm_launch_count(void);   /* kernels launched by this library so far */
+uint64_t bmm_fetch_bytes(void);    /* device-to-host bytes moved by the calling thread's last bmm_plan_fetch (or one-shot gibbs call) */
 const char *bmm_version(void);
 
 #ifdef __cplusplus

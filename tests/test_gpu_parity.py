@@ -606,16 +606,43 @@ def test_dp_philox_posterior(oracle, datasets):
 
 
 def test_fetch_widening_equals_direct(datasets, monkeypatch):
-    """Large int32 z outputs travel as bytes and are widened on the host: same arrays as the direct int32 download."""
+    """Large int32 z outputs travel as bytes and are widened on the host: same arrays as the direct int32 download.
+    With relabelling only z_original crosses PCIe and z = perm[z_original] (full_gibbs.cpp:171-174) is derived on the
+    host while widening; BMM_FETCH_DERIVE=0 ships both matrices."""
     _need_gpu()
     X = datasets["K3_N1000_P5"]
     kw = dict(burnin=20, relabel=True, burnrelabel=10, chains=64, seed=8)
-    a = B.gibbs_full(X, 200, 3, **kw)                    # 64 * 180 * 1000 = 11.5M allocations: staged + widened
+    a = B.gibbs_full(X, 200, 3, **kw)                    # 64 * 180 * 1000 = 11.5M allocations: staged + widened, z derived
+    monkeypatch.setenv("BMM_FETCH_DERIVE", "0")
+    c = B.gibbs_full(X, 200, 3, **kw)                    # both matrices as bytes
     monkeypatch.setenv("BMM_FETCH_WIDEN", "0")
-    b = B.gibbs_full(X, 200, 3, **kw)
+    b = B.gibbs_full(X, 200, 3, **kw)                    # both matrices as int32
     for k in ("z", "z_original", "permutations", "theta", "pi"):
         assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(c[k], b[k]), k
     assert a["z"].dtype == np.int32 and a["z"].min() >= 1 and a["z"].max() <= 3
+    s_idx = np.arange(a["z"].shape[1])[None, :, None]
+    c_idx = np.arange(64)[:, None, None]
+    assert np.array_equal(a["z"], a["permutations"][c_idx, s_idx, a["z_original"] - 1] + 1)
+
+
+@pytest.mark.parametrize("sampler", ["full", "collapsed", "dp"])
+def test_fetch_derived_z_odd_shapes(datasets, monkeypatch, sampler):
+    """The host-derived relabelled matrix for history lengths and chain counts that are not multiples of the vector
+    width or the staging chunk (runs split across chunks and workers), with thinning and the z_freq summary."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"][:997]
+    kw = dict(burnin=9, relabel=True, burnrelabel=5, chains=61, seed=5, thin=1, probes=("z_freq",))
+    ns = 9 + 187
+    run = {"full": lambda: B.gibbs_full(X, ns, 3, **kw), "collapsed": lambda: B.gibbs_collapsed(X, ns, 3, **kw),
+           "dp": lambda: B.gibbs_dp(X, ns, maxK=12, **kw)}[sampler]
+    a = run()                                            # 61 * 187 * 997 = 11.4M allocations
+    monkeypatch.setenv("BMM_FETCH_WIDEN", "0")
+    b = run()
+    for k in ("z", "z_original", "permutations", "z_freq"):
+        assert np.array_equal(a[k], b[k]), k
+    K = a["permutations"].shape[-1]
+    assert np.array_equal(a["z_freq"], np.stack([(a["z"] == k + 1).sum(1) for k in range(K)], axis=2))
 
 
 @pytest.mark.parametrize("name,K", [("K3_N1000_P5", 3), ("K2_N1000_P5", 2)])
