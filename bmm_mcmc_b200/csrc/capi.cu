@@ -164,6 +164,14 @@ struct bmm_plan {
     DevBuf x_inbox, x_peer_arr, x_seq;   // single-GPU inbox of the tensor path (x_world = 1)
     DevBuf w1, w0, lpi, gsc, counts, counts_out, lp_table, lp_bias, cnt_ws;
     DevBuf probs_f32, Qf, cube_f, cost_acc, perm_cur;   // grid-path relabelling (float, row-major N x K)
+    DevBuf sb_vws;                // warm-start potentials of the batch step's M assignments, (K + 1) doubles each
+    bool fused_relabel = false;   // tensor path: online relabelling in one pass over Q per sweep (kern_big_ws_relabel.cu)
+    // ... whose assignment solve (one warp, ~0.16 ms at K = 32) runs on a side stream beside the parameter update and the next
+    // z-sweep; the sweep then leaves one SM to it (its CTAs take a whole SM's registers)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool assign_inflight = false;
+    DevBuf Qt, b1_hist, bias_hist;
     DevBuf zfreq;                 // grid-path posterior summary [N x K cm] uint32
     // data
     DevBuf rowbits, rowid, wt, xbits, logB, logG, logBG, logN, rBGP;
@@ -191,6 +199,9 @@ struct bmm_plan {
         for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
         for (auto &e : seg_ev) if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         for (auto &g : gexec) if (g) cudaGraphExecDestroy(g);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -390,7 +401,19 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
         CU(cudaMemGetInfo(&free_b, &total_b));
         if ((2 + (size_t)a.burnrelabel) * NK * 4 > free_b / 2)
             return fail(BMM_ERR_UNSUPPORTED, "relabel on the grid path: burnrelabel x N x K probabilities do not fit the device; lower burnrelabel");
-        CU(pl->probs_f32.alloc(NK * 4)); CU(pl->Qf.alloc(NK * 4)); CU(pl->cube_f.alloc((size_t)a.burnrelabel * NK * 4));
+        // shapes of the tensor sweep (big_tc_supported): P is recomputed instead of stored, Q streams once per sweep
+        const char *fenv = getenv("BMM_RELABEL_FUSED");
+        pl->fused_relabel = a.precision == BMM_FP32 && !(a.flags & (BMM_FLAG_NO_TENSOR | BMM_FLAG_PROBE_LOGLIK)) && !getenv("BMM_NO_TC") &&
+                            K <= 32 && P <= 112 && !a.replay && !(fenv && fenv[0] == '0');
+        if (pl->fused_relabel) {
+            CU(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+            CU(pl->Qt.alloc(bmm::wsr_q_tiled_bytes(N), false));
+            CU(pl->b1_hist.alloc(2 * bmm::ws_b1_bytes(P)));
+            CU(pl->bias_hist.alloc(2 * 32 * sizeof(float)));
+        } else CU(pl->probs_f32.alloc(NK * 4));
+        CU(pl->Qf.alloc(NK * 4)); CU(pl->cube_f.alloc((size_t)a.burnrelabel * NK * 4));
         CU(pl->cost_acc.alloc(((size_t)K * K + K) * 8));
         CU(pl->perm_cur.alloc((size_t)K * 4));
         CU(pl->sb_perm.alloc((size_t)a.burnrelabel * K * 4));
@@ -398,6 +421,7 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
         CU(pl->perm_out.alloc((size_t)S * K * 4));
         CU(pl->theta_rel_out.alloc(KP * S * 8));
         CU(pl->assign_ws.alloc(bmm::assign_ws_bytes(K)));
+        CU(pl->sb_vws.alloc((size_t)a.burnrelabel * (K + 1) * sizeof(double)));
     }
     if (a.replay) {
         const bmm_replay *r = a.replay;
@@ -423,7 +447,9 @@ int create_big(bmm_plan *pl, const bmm_init *init) {
     b.theta_out = pl->theta_out.as<double>(); b.pi_out = pl->pi_out.as<double>(); b.alpha_out = pl->alpha_out.as<double>();
     b.probs_out = pl->probs_out.as<double>(); b.loglik_out = pl->loglik_out.as<double>();
     b.counts_out = pl->counts_out.as<int>();
-    b.probs_f32 = nullptr; b.perm_cur = pl->perm_cur.as<int>(); b.theta_rel_out = pl->theta_rel_out.as<double>();
+    // single-pass relabelling: the relabelled theta history is produced at the end of the run from the permutation history,
+    // so the update kernel need not wait for the sweep's assignment
+    b.probs_f32 = nullptr; b.perm_cur = pl->perm_cur.as<int>(); b.theta_rel_out = pl->fused_relabel ? nullptr : pl->theta_rel_out.as<double>();
     if (a.precision == BMM_FP32 && !(a.flags & BMM_FLAG_NO_TENSOR) && K <= 128 && (K > 32 || P > 112)) {
         CU(pl->lp_table.alloc(bmm::big_lp_table_bytes(P)));
         CU(pl->lp_bias.alloc(128 * 8));
@@ -487,12 +513,12 @@ int sweep_front(bmm_plan *pl, int j) {
     bmm::BigParams bj = b;
     if (pl->relabel) {   // where this sweep's probabilities go (full_gibbs.cpp:146-156)
         if (j < burnin && j >= burnin - M) bj.probs_f32 = pl->cube_f.as<float>() + (size_t)(j - burnin + M) * NK;
-        else if (j >= burnin) bj.probs_f32 = pl->probs_f32.as<float>();
+        else if (j >= burnin && !pl->fused_relabel) bj.probs_f32 = pl->probs_f32.as<float>();
     }
     if (b.ru) CU(bmm::launch_big_replay_load(bj, j, pl->stream));
     const bool timed = pl->ev_stride > 0 && (j % pl->ev_stride) == 0;
     if (timed) CU(cudaEventRecordWithFlags(pl->sweep_ev[2 * j], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
-    CU(bmm::launch_big_sweep(bj, j, pl->sm_count, pl->stream));
+    CU(bmm::launch_big_sweep(bj, j, pl->assign_inflight && pl->sm_count > 8 ? pl->sm_count - 1 : pl->sm_count, pl->stream));
     if (timed) CU(cudaEventRecordWithFlags(pl->sweep_ev[2 * j + 1], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
     if (pl->sharded) {   // counts of all ranks: pushed over peer memory when attached (consumed by the update kernel), else NCCL
         int *cj = pl->counts.as<int>() + (size_t)(j & 1) * ncnt;
@@ -503,13 +529,66 @@ int sweep_front(bmm_plan *pl, int j) {
     return BMM_OK;
 }
 
+// One pass of the fused online relabelling: j in [burnin, ns) accumulates sweep j's cost matrix and applies the Q update of
+// sweep j - 1; j == ns only applies the last update and returns Q to its row-major form.
+int relabel_pass(bmm_plan *pl, int j) {
+    const bmm::BigParams &b = pl->bp;
+    const int burnin = pl->a.burnin, ns = pl->ns;
+    const bool st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) != 0;
+    bmm::WsRelabelParams r{};
+    r.N_local = b.N_local; r.P = b.P; r.K = b.K; r.W = b.W;
+    r.xbits = b.xbits; r.b1_cur = b.ws_b1; r.lpi = b.lpi; r.s0 = b.ws_s0;
+    r.b1_hist = pl->b1_hist.as<unsigned char>(); r.bias_hist = pl->bias_hist.as<float>();
+    r.hist_prev = (j - 1) & 1; r.hist_next = j < ns ? (j & 1) : -1;
+    r.perm = st_fixed ? pl->perm_inv.as<int>() : pl->perm_cur.as<int>();
+    r.upd = j > burnin; r.do_cost = j < ns;
+    const float sn = (float)(j - 1), inv = 1.f / (float)j;       // the pending update is sweep j - 1's (stephens.cpp:92)
+    r.cq = sn * inv; r.cp = st_fixed ? inv : sn * inv;
+    r.q_in_rowmajor = j == burnin; r.q_out_rowmajor = j == ns;
+    r.q_direct = getenv("BMM_WSR_QDIRECT") != nullptr;
+    r.Q_rm = pl->Qf.as<float>(); r.Q_tiled = pl->Qt.as<float>();
+    r.cost_out = pl->cost_acc.as<double>(); r.status = pl->status.as<int>();
+    if (r.do_cost) CU(cudaMemsetAsync(pl->cost_acc.p, 0, pl->cost_acc.bytes, pl->stream));
+    CU(bmm::launch_big_relabel_ws(r, pl->sm_count, pl->stream));
+    return BMM_OK;
+}
+
+// the side stream's assignment solve must have finished before anything on the main stream reads perm_cur
+int join_assign(bmm_plan *pl) {
+    if (pl->assign_inflight) {
+        CU(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
+        pl->assign_inflight = false;
+    }
+    return BMM_OK;
+}
+
 int sweep_back(bmm_plan *pl, int j) {
     const bmm::BigParams &b = pl->bp;
     const int burnin = pl->a.burnin, K = b.K;
     const long long N = b.N_local;
     const int st_fixed = (pl->a.flags & BMM_FLAG_STEPHENS_FIXED) ? 1 : 0;
     const int cost_tc = (pl->a.precision == BMM_FP32 && !(pl->a.flags & BMM_FLAG_NO_TENSOR)) ? 1 : 0;
-    if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
+    if (pl->relabel && j >= burnin && pl->fused_relabel) {
+        TRY(join_assign(pl));                    // this pass applies the permutation of sweep j - 1
+        TRY(relabel_pass(pl, j));
+        if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
+            return fail(BMM_ERR_NCCL, bmm::dist_error());
+        const int slot = bmm::hist_slot(j, burnin, pl->thin);
+        static const bool fork = !(getenv("BMM_ASSIGN_FORK") && getenv("BMM_ASSIGN_FORK")[0] == '0');
+        cudaStream_t as = fork ? pl->side : pl->stream;
+        if (fork) {
+            CU(cudaEventRecord(pl->ev_fork, pl->stream));
+            CU(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+        }
+        CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), pl->perm_cur.as<int>(),
+                                   slot >= 0 ? pl->perm_out.as<int>() + slot : nullptr, pl->S, as));
+        if (st_fixed) CU(bmm::launch_grid_invert_perm(1, K, pl->perm_cur.as<int>(), pl->perm_inv.as<int>(), as));
+        if (fork) {
+            CU(cudaEventRecord(pl->ev_join, pl->side));
+            pl->assign_inflight = true;
+        }
+        if (pl->zfreq.p) TRY(join_assign(pl));   // the summary below reads perm_cur
+    } else if (pl->relabel && j >= burnin) {       // my_stephens_online (full_gibbs.cpp:166-175)
         CU(bmm::launch_grid_cost(N, K, pl->probs_f32.as<float>(), pl->Qf.as<float>(), st_fixed, pl->cost_acc.as<double>(),
                                  pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
         if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
@@ -554,8 +633,8 @@ int batch_relabel_big(bmm_plan *pl) {
                                      pl->sm_count, pl->stream, cost_tc, pl->status.as<int>()));
             if (pl->sharded && bmm::dist_allreduce_f64(pl->cost_acc.as<double>(), (size_t)K * K + K, pl->stream))
                 return fail(BMM_ERR_NCCL, bmm::dist_error());
-            CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->assign_ws.as<char>(), nullptr, sbp + (size_t)t * K, 1,
-                                       pl->stream, flag));
+            CU(bmm::launch_grid_assign(K, pl->cost_acc.as<double>(), pl->sb_vws.as<char>() + (size_t)t * (K + 1) * sizeof(double), nullptr,
+                                       sbp + (size_t)t * K, 1, pl->stream, flag));
         }
         int changed = 1;   // every rank sees the same all-reduced costs, hence the same flag
         CU(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
@@ -585,6 +664,12 @@ int enqueue_segment(bmm_plan *pl, int seg, int jsplit) {
     } else {
         TRY(sweep_back(pl, jsplit));
         for (int j = jsplit + 1; j < ns; ++j) { TRY(sweep_front(pl, j)); TRY(sweep_back(pl, j)); }
+        if (pl->fused_relabel) {
+            TRY(join_assign(pl));
+            TRY(relabel_pass(pl, ns));      // the last sweep's Q update, Q back in row-major form
+            CU(bmm::launch_grid_theta_rel(b.K, b.P, pl->S, pl->theta_out.as<double>(), pl->perm_out.as<int>(),
+                                          pl->theta_rel_out.as<double>(), pl->sm_count, pl->stream));
+        }
     }
     return BMM_OK;
 }
@@ -844,6 +929,10 @@ int snapshot_state(bmm_plan *pl) {
     // sweep 1 when burnrelabel > burnin; the DP sampler writes only the columns of live labels and never clears
     // probs_sample, collapsed_gibbs_dp.cpp:91-92,195-199), the DP theta histories (:77-78), the status words
     pl->zero_at_run = {&pl->status, &pl->cube, &pl->cube_f, &pl->probs_sample, &pl->Q, &pl->logQ};
+    if (pl->grid_path) {          // warm-start state of the assignment solver: every run starts cold, like the first
+        pl->zero_at_run.push_back(&pl->assign_ws);
+        pl->zero_at_run.push_back(&pl->sb_vws);
+    }
     if (pl->sampler == BMM_SAMPLER_DP) {
         pl->zero_at_run.push_back(&pl->theta_out);
         pl->zero_at_run.push_back(&pl->theta_rel_out);

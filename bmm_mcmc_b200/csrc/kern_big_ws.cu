@@ -11,6 +11,7 @@
 //                softmax, Philox inverse-CDF draw, 1-byte allocation, one-hot row -> B2 stage
 //
 // Replaces /root/reference/src/full_gibbs.cpp:87-157,182-200 (stickbreaking.cpp:70-140,164-186).
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -25,13 +26,13 @@ namespace {
 #define WS_NA_CFG 4
 #endif
 #ifndef WS_NB_CFG
-#define WS_NB_CFG 4
+#define WS_NB_CFG 6
 #endif
 #ifndef WS_NEPI_CFG
 #define WS_NEPI_CFG 3
 #endif
 constexpr int WS_NA = WS_NA_CFG;      // GEMM1 accumulators (64 TMEM columns each)
-constexpr int WS_NB = WS_NB_CFG;      // one-hot stages
+constexpr int WS_NB = WS_NB_CFG;      // one-hot stages: a multiple of WS_NEPI, so that a stage always comes back to the same warpgroup
 constexpr int WS_NEPI = WS_NEPI_CFG;  // epilogue warpgroups (4 at 80 registers/thread measured no faster)
 constexpr int WS_THREADS = 256 + 128 * WS_NEPI;
 constexpr int WS_REP = 16;    // replicas of the count vector the CTAs flush into
@@ -248,8 +249,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         // words are handed out by shuffles, instead of every lane evaluating its own block for every tile.
         const bool shared_rng = (p.row_offset & 3) == 0;
         uint4 rnd4 = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t prevz = 0xFFFFFFFFu;       // the label this thread last stored in each of the (at most 4) one-hot stages
-        static_assert(WS_NB <= 4, "prevz holds one byte per one-hot stage");
+        // The label this thread last stored in each one-hot stage.  Tile k uses stage k % NB and warpgroup k % NEPI; only with
+        // NB a multiple of NEPI is row t of a stage always written by the same thread -- with 4 stages under 3 warpgroups a
+        // stage went round the warpgroups, each cleared only its own previous entry, and from the fifth tile of a CTA on the
+        // rows carried stale ones into the count contraction (caught by test_grid_tensor_kernels_many_tiles_per_cta).
+        unsigned long long prevz = ~0ull;
+        static_assert(WS_NB <= 8 && WS_NB % WS_NEPI == 0 && WS_NB >= WS_NEPI, "prevz holds one byte per one-hot stage; stages must not migrate between warpgroups");
         int a = e % WS_NA, b = e % WS_NB;                       // tile k uses accumulator k % NA, one-hot stage k % NB
         uint32_t ph_a = (uint32_t)((e / WS_NA) & 1), ph_b = (uint32_t)((e / WS_NB) & 1);
         int it = 0;
@@ -388,11 +393,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
             {   // one-hot row of this observation in stage b: clear the entry this thread set there last time (the
                 // stages start zeroed and row t of a stage is only ever written by this thread), set the new one
                 unsigned char *row = smem + L::B2_OFF + b * WS_B2_BYTES + t * 16;
-                const uint32_t pz = (prevz >> (8 * b)) & 0xFFu;
+                const uint32_t pz = (uint32_t)(prevz >> (8 * b)) & 0xFFu;
                 if (pz != 0xFFu) *(unsigned short *)(row + (pz >> 3) * WS_CHUNK + (pz & 7u) * 2) = 0;
-                const uint32_t nz = valid ? (uint32_t)z : 0xFFu;
+                const unsigned long long nz = valid ? (unsigned long long)z : 0xFFull;
                 if (valid) *(unsigned short *)(row + (z >> 3) * WS_CHUNK + (z & 7) * 2) = 0x3C00;
-                prevz = (prevz & ~(0xFFu << (8 * b))) | (nz << (8 * b));
+                prevz = (prevz & ~(0xFFull << (8 * b))) | (nz << (8 * b));
             }
             fence_async_smem();
             mbar_arrive(b2_full + 8 * b);
@@ -509,6 +514,7 @@ cudaError_t launch_ws_nch(const BigParams &p, int j, int sm_count, cudaStream_t 
     if (cudaError_t e = attr.ensure_smem(big_sweep_ws_kernel<NCH>, (int)L::TOTAL)) return e;
     const long long ntiles = ((long long)p.N_local + 127) / 128;
     long long ctas = ntiles < sm_count ? ntiles : sm_count;
+    if (const char *e = getenv("BMM_GRID_MAX_CTAS")) { const int cap = atoi(e); if (cap > 0 && ctas > cap) ctas = cap; }   // tests: many tiles per CTA
     if (ctas < 1) ctas = 1;
     g_launches++;
     return launch_pdl(big_sweep_ws_kernel<NCH>, dim3((unsigned)ctas), dim3(WS_THREADS), (size_t)L::TOTAL, st, p, j);

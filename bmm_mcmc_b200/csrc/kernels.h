@@ -204,6 +204,30 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 cudaError_t launch_x_begin_run(int *seq, int n_sweeps, cudaStream_t st);   // seq[0] = seq[1]; seq[1] += n_sweeps
+
+// Single-pass online relabelling of the tensor path (kern_big_ws_relabel.cu): pass j recomputes p_j and p_{j-1} from the
+// packed rows, applies the pending Q update, and accumulates G(k,l) = sum_i log q_ik p_il into cost_out.
+struct WsRelabelParams {
+    long long N_local;
+    int P, K, W;
+    const uint32_t *xbits;            // [N_local][W]
+    const unsigned char *b1_cur;      // operand image of this sweep's table (BigParams::ws_b1)
+    const double *lpi, *s0;           // this sweep's log pi and s0 (BigParams::lpi, ws_s0)
+    unsigned char *b1_hist;           // [2][ws_b1_bytes(P)] images of past sweeps (kept by CTA 0)
+    float *bias_hist;                 // [2][32] their biases
+    int hist_prev, hist_next;         // which copy holds the pending update's table; which one receives this sweep's (-1: none)
+    const int *perm;                  // [K] column order of the pending update: perm_{j-1} (its inverse in the fixed mode)
+    int upd, do_cost;                 // apply the pending update; accumulate the cost matrix
+    float cq, cp;                     // Q' = cq * Q + cp * p[:, perm]
+    int q_in_rowmajor, q_out_rowmajor;
+    int q_direct;                     // diagnostic: read the Q tiles straight from global memory instead of through the bulk-copy ring
+    float *Q_rm;                      // row-major [N_local][K] (batch step's output / final result)
+    float *Q_tiled;                   // [tiles of 128 rows][8][128][4 floats]
+    double *cost_out;                 // [K*K] G at k + K*l (+= ; the s_l block behind it stays zero)
+    int *status;
+};
+size_t wsr_q_tiled_bytes(long long N);
+cudaError_t launch_big_relabel_ws(const WsRelabelParams &p, int sm_count, cudaStream_t st);
 size_t ws_b1_bytes(int P);
 size_t ws_rep_bytes(int K, int P);
 cudaError_t ws_trace_read(unsigned long long out[16]);   // phase stamps of the last two tensor-sweep launches (diagnostic)
@@ -247,6 +271,8 @@ cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t 
 cudaError_t launch_grid_qmean(long long N, int K, int M, const float *cube, const int *perm, float *Q, int sm_count,
                               cudaStream_t st);
 cudaError_t launch_grid_identity_perm(int n, int K, int *perm, cudaStream_t st);
+// relabelled theta history from the original one and the permutation history, all kept sweeps in one launch
+cudaError_t launch_grid_theta_rel(int K, int P, int S, const double *theta, const int *perm, double *theta_rel, int sm_count, cudaStream_t st);
 // posterior summary: zfreq[i + N*perm[z_i - 1]] += 1 over one sweep's allocations (perm may be nullptr)
 cudaError_t launch_grid_zfreq(long long N, int K, const uint8_t *z, const int *perm, unsigned *zfreq, int sm_count, cudaStream_t st);
 

@@ -698,6 +698,98 @@ def test_grid_relabel_large_k_tensor_path():
     assert got <= best + 1e-4 * abs(best), (got, best)
 
 
+def _online_relabel_check(g, X, K, burnin, M, oracle, fixed=False):
+    """Follow the relabelling of a grid-path run on the host in float64 from the probabilities the kernels reported: batch
+    Q (stephens.cpp:6-64), then per kept sweep the online cost (:78-80) with the oracle's assignment (reference lp_solve)
+    and the Q update (:87-92) along the permutation the GPU chose.  The GPU's permutation must be optimal for the host's
+    cost at every sweep (identical when the optimum is unique), and its final Q must be the host's."""
+    from oracle import pyoracle as O
+    N = X.shape[0]
+    ns = g["probs"].shape[0]
+    cube = np.stack([g["probs"][j] for j in range(burnin - M, burnin)], axis=2)       # N x K x M
+    q, _ = O.stephens_batch(cube)
+    same = 0
+    for j in range(burnin, ns):
+        pj = g["probs"][j]
+        perm_o, q_o, cost = O.stephens_online(q, pj, j, use_ref=O.has_ref())
+        perm_g = g["permutations"][j - burnin]
+        assert np.array_equal(np.sort(perm_g), np.arange(K))
+        got = float(sum(cost[perm_g[l], l] for l in range(K)))
+        best = float(sum(cost[perm_o[l], l] for l in range(K)))
+        assert got <= best + 1e-7 * max(1.0, abs(best)), (j, got, best)
+        same += int(np.array_equal(perm_g, perm_o))
+        q = j * (q + pj[:, perm_g]) / (j + 1)                                         # quirks 3, 5
+    assert same >= (ns - burnin) // 2          # ties aside, the very permutation of the oracle
+    np.testing.assert_allclose(g["Q_final"], q, rtol=3e-4)
+    assert np.array_equal(g["z"], np.take_along_axis(g["permutations"], g["z_original"] - 1, 1) + 1)
+
+
+@pytest.mark.parametrize("sampler,N,P,K", [("full", 3000, 64, 8), ("stickbreaking", 20_000 + 77, 64, 32), ("full", 1111, 20, 5),
+                                            ("full", 4096, 100, 24)])
+def test_grid_tensor_relabel_single_pass(oracle, monkeypatch, sampler, N, P, K):
+    """Online relabelling of the tensor path in one pass over Q per sweep (kern_big_ws_relabel.cu: probabilities recomputed
+    on tcgen05 instead of stored, Q update deferred into the next sweep's pass, K x K contraction on tcgen05) against the
+    oracle's Stephens step fed with the reported probabilities, and against the three-pass kernels it replaces."""
+    _need_gpu()
+    rng = np.random.default_rng(N + K)
+    Kt = min(K, 8)
+    th_true = rng.uniform(0.1, 0.9, (Kt, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, Kt, N)]).astype(np.int32)
+    burnin, M, ns = 6, 3, 15
+    run = B.gibbs_full if sampler == "full" else B.gibbs_stickbreaking
+    kw = dict(alpha=1.0, burnin=burnin, relabel=True, burnrelabel=M, seed=5, precision="fp32", probes=("probs", "Q_final"),
+              grid_path=True)
+    g = run(X, ns, K, **kw)
+    _online_relabel_check(g, X, K, burnin, M, oracle)
+    monkeypatch.setenv("BMM_RELABEL_FUSED", "0")
+    h = run(X, ns, K, **kw)                     # probabilities stored, cost kernel, Q update kernel
+    assert np.array_equal(g["z_original"], h["z_original"])
+    _online_relabel_check(h, X, K, burnin, M, oracle)
+    np.testing.assert_allclose(g["Q_final"], h["Q_final"], rtol=3e-4)
+    if np.array_equal(g["permutations"], h["permutations"]):
+        assert np.array_equal(g["z"], h["z"]) and np.array_equal(g["theta"], h["theta"])
+
+
+def test_grid_tensor_kernels_many_tiles_per_cta(oracle, monkeypatch):
+    """The warp-specialised tensor kernels (z-sweep and single-pass relabelling) with every mbarrier ring wrapping many
+    times: the grid is capped at 3 CTAs, so each CTA walks ~50 tiles (a full-size run has 528 per CTA; with the usual one
+    or two tiles per CTA of a test-sized input no ring ever wraps)."""
+    _need_gpu()
+    rng = np.random.default_rng(99)
+    N, P, K = 20_000 + 77, 64, 32
+    th_true = rng.uniform(0.1, 0.9, (8, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, 8, N)]).astype(np.int32)
+    burnin, M, ns = 6, 3, 13
+    kw = dict(alpha=1.0, burnin=burnin, relabel=True, burnrelabel=M, seed=5, precision="fp32", probes=("probs", "Q_final", "counts"),
+              grid_path=True)
+    ref = B.gibbs_stickbreaking(X, ns, K, **kw)
+    monkeypatch.setenv("BMM_GRID_MAX_CTAS", "3")
+    g = B.gibbs_stickbreaking(X, ns, K, **kw)
+    assert np.array_equal(g["z_original"], ref["z_original"])          # tile -> CTA mapping does not enter the draws
+    assert np.array_equal(g["counts"][burnin:], _host_counts(g["z_original"], X, K))    # sufficient statistics of the kept sweeps
+    _online_relabel_check(g, X, K, burnin, M, oracle)
+    np.testing.assert_allclose(g["Q_final"], ref["Q_final"], rtol=3e-4)
+
+
+def test_grid_tensor_relabel_single_pass_fixed_mode(monkeypatch):
+    """The same single-pass kernel in the correctness-fixed Stephens mode (inverse permutation, running-mean Q): equal to
+    the three-pass kernels."""
+    _need_gpu()
+    rng = np.random.default_rng(77)
+    N, P, K = 5000 + 3, 64, 6
+    th_true = rng.uniform(0.1, 0.9, (K, P))
+    X = (rng.random((N, P)) < th_true[rng.integers(0, K, N)]).astype(np.int32)
+    kw = dict(alpha=1.0, burnin=5, relabel=True, burnrelabel=3, seed=8, precision="fp32", probes=("Q_final",), grid_path=True,
+              stephens_fixed=True)
+    g = B.gibbs_full(X, 16, K, **kw)
+    monkeypatch.setenv("BMM_RELABEL_FUSED", "0")
+    h = B.gibbs_full(X, 16, K, **kw)
+    assert np.array_equal(g["z_original"], h["z_original"])
+    assert np.array_equal(g["permutations"], h["permutations"])
+    assert np.array_equal(g["z"], h["z"])
+    np.testing.assert_allclose(g["Q_final"], h["Q_final"], rtol=3e-4)
+
+
 def test_assign_warp_jv_matches_lpsolve(oracle):
     """The warp-parallel Jonker-Volgenant solver of the grid path (through bmm_stephens-style cost) equals lp_solve."""
     _need_gpu()
