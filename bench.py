@@ -466,7 +466,26 @@ def run_grid(a):
             "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
             "kernel": "%s (%d rows, %d B/update)" % (kname, n_local, bytes_per_update),
             "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))}
-    if 2 * K * P / bytes_per_update > 1e3 * pk["bf16_tflops_sustained"] / pk["hbm_gbs"]:
+    if relabel and kern[2] > 0:
+        # with relabelling the dominant kernel is the single-pass relabelling kernel: Q once in, once out (fp32) plus the
+        # packed row per update (2*K*4 + ceil(P/8) bytes), HBM-bound
+        rb = 2 * K * 4 + (P + 7) // 8
+        rdur = kern[2] / a.steps / (ns - burnin) / 1e3
+        racc = n_local * rb / rdur / 1e9
+        rtraffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                tr = json.load(f).get("big_relabel_ws_kernel", {})
+            if tr.get("n") == n_local:
+                rtraffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": racc, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": racc / pk["hbm_gbs"],
+                "traffic": rtraffic, "peak_source": pk_src,
+                "kernel": "big_relabel_ws_kernel (%d rows, %d B/update: Q read + Q written in fp32, packed row)" % (n_local, rb),
+                "kernel_ms": rdur * 1e3, "kernel_share_of_step": float(kern[2] / max(kern[:3].sum() + kern[3], 1e-9)),
+                "sweep_kernel_ms": dur_s * 1e3}
+    elif 2 * K * P / bytes_per_update > 1e3 * pk["bf16_tflops_sustained"] / pk["hbm_gbs"]:
         # arithmetic intensity above the ridge (C5: 2044 flop/B vs 216): the tensor pipe bounds it
         flops = 2.0 * K * P * n_local          # algorithmic: one K x P contraction per update
         tf = flops / dur_s / 1e12
@@ -495,8 +514,8 @@ def run_grid(a):
         "gpu_launches": launches,
         "roofline": roof,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,
-                  "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "params_allreduce_relabel": kern[1] / a.steps,
-                                 "finalize_layout": kern[3] / a.steps}},
+                  "kernels_ms": {"sweep_kernels": kern[0] / a.steps, "relabel_kernels": kern[2] / a.steps,
+                                 "params_allreduce_assign_other": kern[1] / a.steps, "finalize_layout": kern[3] / a.steps}},
     }
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = grid_cpu_baseline(w)[0]
@@ -538,20 +557,26 @@ def sharded_leg(rank, world, local, dist, steps=3, warmup=2):
            "exchange": ("tagged 8-byte words pushed over IPC-mapped NVLink peer memory by the sweep kernel's last CTA, "
                         "summed by the parameter-update kernel" if p2p else ("NCCL all-reduce" if world > 1 else "none (one GPU)")),
            "comm_nranks": world}
-    for name, ns, burnin, relabel, br in (("relabel_off", 31, 1, False, 0), ("relabel_on", 26, 6, True, 1)):
+    for name, ns, burnin, relabel, br in (("relabel_off", 31, 1, False, 0), ("relabel_on", 62, 2, True, 1)):
         plan = api.Plan(_lib.SAMPLER_STICKBREAKING, X, ns, K, chains=1, seed=2026, device=local, init_pi=ip, init_theta=th,
                         precision="fp32", compact_z=True, grid_path=True, alpha=w["alpha"], beta=0.5, gamma=0.5, a=1.0, b=1.0,
                         burnin=burnin, relabel=relabel, burnrelabel=br, **shard)
         clocks = ClockSampler(local)
         clocks.launch()
+        t_w = 0.0
         for _ in range(warmup):
             plan.run(); plan.sync()
+            t_w = plan.elapsed_ms()[0]
+        # at 8 GPUs a step lasts a few milliseconds: repeat it until the timed region covers ~1.5 s, so that the clock
+        # sampler (one nvidia-smi query per ~0.2 s) sees it; every rank derives the same count from the max step time
+        t_w = _max_over_ranks(t_w, dist)
+        nrep = int(min(400, max(steps, np.ceil(1500.0 / max(t_w, 1e-3)))))
         if dist:
             dist.barrier()
         clocks.start()
         l0 = L.bmm_launch_count()
         dev_ms, kern = 0.0, np.zeros(4)
-        for _ in range(steps):
+        for _ in range(nrep):
             plan.run(); plan.sync()
             dev_ms += plan.elapsed_ms()[0]
             kern += np.array(plan.kernel_ms())
@@ -562,16 +587,19 @@ def sharded_leg(rank, world, local, dist, steps=3, warmup=2):
         plan.check()
         plan.close()
         dev_ms = _max_over_ranks(dev_ms, dist)
-        sweeps = (ns - 1) * steps
+        sweeps = (ns - 1) * nrep
         sweep_us = 1e3 * kern[0] / sweeps
         other_us = 1e3 * (kern[1]) / sweeps
+        relabel_us = 1e3 * kern[2] / ((ns - burnin) * nrep) if relabel else 0.0
         n_local = hi - lo
         bytes_upd = (P + 7) // 8 + 1 + (2 * K * 4 if relabel else 0)       # X row + z (+ Q read and write)
         out[name] = {
             "value": N * sweeps / (dev_ms / 1e3), "unit": "allocation updates/s", "nsamples": ns, "burnin": burnin,
-            "steps": steps, "ms_per_sweep": dev_ms / sweeps, "sweep_kernel_us": sweep_us,
-            "exchange_us": other_us, "exchange_note": "everything of a sweep that is not the z-sweep kernel: count exchange + "
-            "parameter update" + (" + cost contraction, assignment, Q update" if relabel else "") + ", per sweep, this rank",
+            "steps": nrep, "ms_per_sweep": dev_ms / sweeps, "sweep_kernel_us": sweep_us,
+            "exchange_us": other_us, "exchange_note": "everything of a sweep that is neither the z-sweep kernel nor the relabelling "
+            "kernel: count exchange + parameter update" + (" + cost all-reduce, assignment, batch initialisation of Q (amortised)"
+                                                          if relabel else "") + ", per sweep, this rank",
+            "relabel_kernel_us": relabel_us,
             "hbm_frac": n_local * bytes_upd / (dev_ms / 1e3 / sweeps) / 1e9 / pk["hbm_gbs"],
             "hbm_bytes_per_update": bytes_upd,
             "tensor_frac": 2.0 * K * P * n_local / (sweep_us * 1e-6) / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
@@ -766,20 +794,23 @@ def main():
     per_sweep_hist = (2 if relabel else 1) * K * P * 8 + K * 8 + 8 + (K * 4 if relabel else 0)
     bytes_launch = C_ * (sweeps2 * N * 1 + S * per_sweep_hist)
     dur_s = kern[2] / a.steps / 1e3
-    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_fast_kernel", "dp": "dp_kernel"}[smp]
+    kname = {"full": "full_chain_kernel", "collapsed": "collapsed_prod_kernel", "dp": "dp_kernel"}[smp]
     achieved = bytes_launch / dur_s / 1e9
     traffic = None   # dram bytes of the dominant launch from the committed ncu --set full capture of this configuration
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f).get(kname, {})
         if tr.get("workload") == a.workload and tr.get("chains") == C_ and tr.get("nsamples") == ns:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            if tr.get("sweeps_in_launch"):       # the capture is one segment launch: scale to the step's post-burn-in sweeps
+                traffic = int(traffic * sweeps2 / tr["sweeps_in_launch"])
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": int(bytes_launch),
                 "peak_source": pk_src,
-                "kernel": "%s (sweeps %d..%d, %d chains)" % (kname, burnin if relabel else 1, ns - 1, C_),
+                "kernel": "%s (sweeps %d..%d, %d chains; launched per download segment, the segments' layout kernels "
+                          "are inside kernel_ms)" % (kname, burnin if relabel else 1, ns - 1, C_),
                 "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[2] / max(kern.sum(), 1e-9)),
                 "note": "C1-C3 are on-chip (issue/latency) bound by construction: chain state lives in shared "
                         "memory and only the 1 B/update history reaches HBM (SURVEY 8d); see extra.kernels_ms"}
@@ -796,9 +827,9 @@ def main():
                 "d2h_bytes_per_step": int(d2h), "host_output_bytes_per_step": int(host_out),
                 "ms_per_step": 1e3 * tm[2] / a.steps,
                 "api": "bmm_mcmc_b200.gibbs_%s -> bmm_gibbs_%s (C ABI), pinned host output buffers; d2h bytes counted by the "
-                       "library: most chains' allocations cross PCIe as one byte each, sweep segment by sweep segment while "
-                       "the later sweeps run, and the host widens them to the two int32 matrices (z = perm[z_original]); the "
-                       "remaining chains are widened on the device and DMA'd" % (smp, smp)},
+                       "library: with one or two ranks per host the allocations cross PCIe as one byte each, sweep segment by "
+                       "sweep segment while the later sweeps run, and the host widens them to the two int32 matrices "
+                       "(z = perm[z_original]); with more ranks the device widens and the int32 matrices are DMA'd" % (smp, smp)},
         "gpu_launches": launches,
         "roofline": roofline,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,

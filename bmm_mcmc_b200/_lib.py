@@ -54,7 +54,7 @@ class Out(C.Structure):
 
 EXPORTS = [
     "bmm_gibbs_full", "bmm_gibbs_stickbreaking", "bmm_gibbs_collapsed", "bmm_gibbs_dp", "bmm_stephens_batch",
-    "bmm_stephens_online", "bmm_stephens_batch_ex", "bmm_stephens_online_ex", "bmm_assign", "bmm_assign_warp", "bmm_grid_cost", "bmm_rdirichlet", "bmm_debug_ws_trace", "bmm_debug_ws_cta", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
+    "bmm_stephens_online", "bmm_stephens_batch_ex", "bmm_stephens_online_ex", "bmm_assign", "bmm_assign_warp", "bmm_grid_cost", "bmm_rdirichlet", "bmm_predictive", "bmm_debug_ws_trace", "bmm_debug_ws_cta", "bmm_full_condprob", "bmm_plan_create", "bmm_plan_run",
     "bmm_plan_sync", "bmm_plan_elapsed_ms", "bmm_plan_fetch", "bmm_plan_destroy", "bmm_dist_unique_id",
     "bmm_dist_init", "bmm_dist_finalize", "bmm_dist_p2p_local", "bmm_dist_p2p_attach", "bmm_dist_p2p_detach", "bmm_plan_kernel_ms", "bmm_host_alloc", "bmm_host_free", "bmm_release_cache", "bmm_last_error", "bmm_device_count", "bmm_launch_count", "bmm_fetch_bytes", "bmm_version",
 ]

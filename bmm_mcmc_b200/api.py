@@ -384,3 +384,36 @@ def gibbs_dp(data, nsamples, alpha=None, a=1, b=1, beta=0.5, gamma=0.5, burnin=N
     return _run(_lib.SAMPLER_DP, X, nsamples, maxK, alpha, beta, gamma, a, b, burnin, relabel, burnrelabel, debug,
                 chains, seed, device, precision, replay=replay, compact_z=compact_z, probes=probes,
                 chain_offset=chain_offset, pinned=pinned, out_bufs=out_bufs, stephens_fixed=stephens_fixed, thin=thin)
+
+
+def predictive(fit, newdata, membership=True):
+    """Posterior predictive distribution of new 0/1 rows under a fitted `gibbs_full` / `gibbs_stickbreaking` model -- the
+    reference's TODO list names it ("Implement predictive distribution", /root/reference/TODO:6), it has no reference code.
+
+    `fit` is the list a sampler returned (`theta` K x P x S, `pi` S x K; with `chains > 1` the chains' draws are pooled).
+    Returns `log_pred[m] = log 1/S sum_s sum_k pi_k prod_d theta_kd^x (1 - theta_kd)^(1 - x)` and, with `membership`,
+    the M x K responsibilities averaged over the draws (relabelled draws give label-consistent columns)."""
+    X = np.asfortranarray(np.asarray(newdata, dtype=np.int32))
+    if X.ndim != 2:
+        raise ValueError("newdata must be an M x P matrix")
+    if "pi" not in fit:
+        raise ValueError("predictive() needs the pi history of an uncollapsed sampler (gibbs_full / gibbs_stickbreaking)")
+    th, pi = np.asarray(fit["theta"], dtype=np.float64), np.asarray(fit["pi"], dtype=np.float64)
+    if th.ndim == 4:        # chains x K x P x S -> K x P x (chains * S)
+        th = np.concatenate(list(th), axis=2)
+        pi = np.concatenate(list(pi), axis=0)
+    K, P, S = th.shape
+    M = X.shape[0]
+    if X.shape[1] != P or pi.shape != (S, K):
+        raise ValueError("newdata / theta / pi shapes do not match")
+    th_cm = np.ascontiguousarray(th.transpose(2, 1, 0))      # memory order k + K d + K P s
+    pi_cm = np.ascontiguousarray(pi.T)                        # S x K column-major
+    lp = np.zeros(M)
+    mem = np.zeros((K, M)) if membership else None
+    L = _lib.lib()
+    _lib.check(L.bmm_predictive(_p(X, C.c_int32), M, P, K, S, _p(th_cm, C.c_double), _p(pi_cm, C.c_double),
+                                _p(lp, C.c_double), _p(mem, C.c_double) if membership else None))
+    out = {"log_pred": lp}
+    if membership:
+        out["membership"] = np.ascontiguousarray(mem.T)
+    return out

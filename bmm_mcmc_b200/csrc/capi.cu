@@ -154,6 +154,7 @@ struct bmm_plan {
     cudaStream_t copy_stream = nullptr;
     int sm_count = 148;
     std::vector<cudaEvent_t> sweep_ev;   // start/stop of the timed sweep kernels of the last run (grid path)
+    std::vector<cudaEvent_t> relabel_ev; // ... and of the single-pass relabelling kernels, same stride
     int ev_stride = 1;            // every ev_stride-th sweep kernel is bracketed by events (0: none)
     bool sharded = false;         // rows of one chain block-partitioned over the ranks of bmm_dist_init
     bool x_p2p = false;           // counts exchanged over peer memory (else NCCL)
@@ -197,6 +198,7 @@ struct bmm_plan {
         if (evk1) cudaEventDestroy(evk1);
         for (auto &e : evs) if (e) cudaEventDestroy(e);
         for (auto &e : sweep_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : relabel_ev) if (e) cudaEventDestroy(e);
         for (auto &e : seg_ev) if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -549,7 +551,10 @@ int relabel_pass(bmm_plan *pl, int j) {
     r.Q_rm = pl->Qf.as<float>(); r.Q_tiled = pl->Qt.as<float>();
     r.cost_out = pl->cost_acc.as<double>(); r.status = pl->status.as<int>();
     if (r.do_cost) CU(cudaMemsetAsync(pl->cost_acc.p, 0, pl->cost_acc.bytes, pl->stream));
+    const bool timed = j < ns && pl->ev_stride > 0 && (j % pl->ev_stride) == 0 && pl->relabel_ev.size() >= (size_t)2 * ns;
+    if (timed) CU(cudaEventRecordWithFlags(pl->relabel_ev[2 * j], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
     CU(bmm::launch_big_relabel_ws(r, pl->sm_count, pl->stream));
+    if (timed) CU(cudaEventRecordWithFlags(pl->relabel_ev[2 * j + 1], pl->stream, pl->capturing ? cudaEventRecordExternal : 0));
     return BMM_OK;
 }
 
@@ -717,6 +722,11 @@ int run_big(bmm_plan *pl) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         pl->sweep_ev.push_back(e);
+    }
+    while (pl->fused_relabel && pl->relabel_ev.size() < (size_t)2 * ns) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        pl->relabel_ev.push_back(e);
     }
     if (!pl->relabel) return run_segment_big(pl, 0, ns);
     TRY(run_segment_big(pl, 0, burnin - 1));
@@ -1148,7 +1158,20 @@ int bmm_plan_kernel_ms(bmm_plan *pl, float ms_out[4]) {
             ++timed;
         }
         sweeps = timed ? sweeps * (float)(pl->ns - 1) / (float)timed : 0.f;
-        ms_out[0] = sweeps; ms_out[1] = total - sweeps; ms_out[2] = 0.f;
+        // [2]: the single-pass relabelling kernels of sweeps burnin .. ns - 1 (same scaling)
+        float rel = 0.f;
+        int rtimed = 0;
+        const int nrel = pl->ns - pl->a.burnin;
+        if (pl->fused_relabel && pl->relabel_ev.size() >= (size_t)2 * pl->ns)
+            for (int j = pl->a.burnin; j < pl->ns; ++j) {
+                if (pl->ev_stride <= 0 || (j % pl->ev_stride) != 0) continue;
+                float t = 0.f;
+                CU(cudaEventElapsedTime(&t, pl->relabel_ev[2 * j], pl->relabel_ev[2 * j + 1]));
+                rel += t;
+                ++rtimed;
+            }
+        rel = rtimed ? rel * (float)nrel / (float)rtimed : 0.f;
+        ms_out[0] = sweeps; ms_out[1] = total - sweeps - rel; ms_out[2] = rel;
     }
     return BMM_OK;
 }
@@ -1453,6 +1476,28 @@ int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out)
     CU(od.alloc((size_t)K * 8));
     CU(bmm::launch_rdirichlet(K, ad.as<double>(), seed, od.as<double>(), 0));
     CU(cudaMemcpy(out, od.p, (size_t)K * 8, cudaMemcpyDeviceToHost));
+    return BMM_OK;
+}
+
+int bmm_predictive(const int32_t *Xnew, int32_t M, int32_t P, int32_t K, int32_t S, const double *theta, const double *pi,
+                   double *log_pred, double *membership) {
+    if (!Xnew || !theta || !pi || !log_pred || M < 1 || P < 1 || K < 1 || K > 255 || S < 1)
+        return fail(BMM_ERR_INVALID, "bad predictive arguments");
+    if (bmm_device_count() < 1) return fail(BMM_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    std::vector<uint32_t> bits;
+    int W;
+    TRY(pack_rows(Xnew, M, P, bits, W));
+    DevBuf xb, th, pd, tab, lp, mem;
+    TRY(upload(xb, bits.data(), bits.size()));
+    TRY(upload(th, theta, (size_t)K * P * S));
+    TRY(upload(pd, pi, (size_t)S * K));
+    CU(tab.alloc((size_t)S * K * (2 * P + 1) * 8, false));
+    CU(lp.alloc((size_t)M * 8, false));
+    if (membership) CU(mem.alloc((size_t)M * K * 8));
+    CU(bmm::launch_predict(M, P, W, K, S, xb.as<uint32_t>(), th.as<double>(), pd.as<double>(), tab.as<double>(), lp.as<double>(),
+                           membership ? mem.as<double>() : nullptr, 0));
+    CU(cudaMemcpy(log_pred, lp.p, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    if (membership) CU(cudaMemcpy(membership, mem.p, (size_t)M * K * 8, cudaMemcpyDeviceToHost));
     return BMM_OK;
 }
 

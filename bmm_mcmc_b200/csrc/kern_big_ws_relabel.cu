@@ -39,8 +39,11 @@
 namespace bmm {
 namespace {
 
+// Epilogue warpgroups for P <= 64.  Measured at C4 (N = 1e7, P = 64, K = 32), kernel alone under ncu / 40-sweep step:
+// three warpgroups (96 registers, three cost stages, three Q tiles in flight) 573 us / 42.1 ms; two warpgroups (110
+// registers, two cost stages, six Q tiles) 667 us / 42.8 ms.
 #ifndef WSR_NEPI_CFG
-#define WSR_NEPI_CFG 2
+#define WSR_NEPI_CFG 3
 #endif
 constexpr int WSR_NA = 6;                 // GEMM1 accumulators, 64 TMEM columns each (cur | prev); the cost accumulator takes the last 128
 constexpr int WSR_QTILE = 128 * WS_KC * 4;

@@ -285,6 +285,11 @@ cudaError_t launch_stephens_online(int U, int K, double *Q, double *logQ, const 
 cudaError_t launch_assign(int K, int batch, const double *cost, int *solution, char *ws, cudaStream_t st);
 cudaError_t launch_rdirichlet(int K, const double *alpha_m, unsigned long long seed, double *out, cudaStream_t st);
 
+// ---- posterior predictive distribution from the kept draws (kern_predict.cu) ------------------
+// tab: scratch of S * K * (2 P + 1) doubles; member (optional, zeroed by the caller): M x K column-major
+cudaError_t launch_predict(int M, int P, int W, int K, int S, const uint32_t *xbits, const double *theta, const double *pi,
+                           double *tab, double *logpred, double *member, cudaStream_t st);
+
 // ---- history layout conversion (kern_finalize.cu) --------------------------------------------
 // zhist [c][nsamples][N] uint8 -> R layout [c][S x N cm]; optional relabelling through perm_out.
 // elem_bytes = 4 (int32) or 1 (uint8, BMM_FLAG_COMPACT_Z).

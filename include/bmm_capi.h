@@ -175,6 +175,13 @@ int bmm_assign_warp(int32_t K, const double *cost, int32_t *perm);
 int bmm_grid_cost(int64_t N, int32_t K, const float *p, const float *q, int32_t use_logp, int32_t tensor, double *out);
 /* _bmmmcmc_rdirichlet_cpp (full_gibbs.cpp:10-27) with an explicit Philox seed.                    */
 int bmm_rdirichlet(int32_t K, const double *alpha_m, uint64_t seed, double *out);
+/* Posterior predictive distribution of a fitted model (no reference counterpart: /root/reference/TODO:6 lists it as
+ * "Implement predictive distribution").  Xnew: M x P int32 column-major 0/1 rows; theta: K x P x S and pi: S x K
+ * column-major, the kept draws as gibbs_full / gibbs_stickbreaking return them (full_gibbs.cpp:233-248).
+ * log_pred[m] = log( 1/S sum_s sum_k pi_k^(s) prod_d theta_kd^(s)^x (1 - theta_kd^(s))^(1 - x) );
+ * membership (optional, M x K column-major) = the responsibilities averaged over the draws.             */
+int bmm_predictive(const int32_t *Xnew, int32_t M, int32_t P, int32_t K, int32_t S, const double *theta, const double *pi,
+                   double *log_pred, double *membership);
 
 /* Diagnostic (no reference counterpart): %globaltimer stamps in ns of the last two sweeps of the tensor grid path.
  * out[8 * (j & 1) + s], z-sweep kernel CTA 0: s = 0 entry, 1 pipeline start, 2 first tile drawn, 3 last tile drawn,

@@ -53,3 +53,20 @@ gibbs_stickbreaking <- function(data, nsamples, maxK, alpha = NULL, beta = 0.5, 
     gibbs_stickbreaking_cpp(data, w0, theta0, nsamples, maxK, d$alpha, beta, gamma, a, b, d$burnin,
                             relabel, d$burnrelabel, debug)
 }
+
+#' Posterior predictive distribution of new observations
+#'
+#' Not in the reference (its TODO file lists "Implement predictive distribution"): for every row of
+#' \code{newdata}, the log of the posterior predictive probability averaged over the kept draws of an
+#' uncollapsed sampler, and the cluster responsibilities averaged over the draws.
+#'
+#' @param obj The list returned by \code{gibbs_full} or \code{gibbs_stickbreaking}.
+#' @param newdata An M x P 0/1 integer matrix.
+#' @return A list with \code{log_pred} (length M) and \code{membership} (M x K).
+#' @export
+predict_gibbs <- function(obj, newdata) {
+    if (is.null(obj$pi)) stop("predict_gibbs needs the pi history of gibbs_full / gibbs_stickbreaking")
+    newdata <- as.matrix(newdata)
+    storage.mode(newdata) <- "integer"
+    predictive_cpp(newdata, obj$theta, obj$pi)
+}

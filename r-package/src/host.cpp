@@ -146,3 +146,18 @@ NumericMatrix rdirichlet_cpp(NumericVector alpha_m) {
     if (bmm_rdirichlet(K, alpha_m.begin(), philox_seed(), out.begin()) != BMM_OK) stop(bmm_last_error());
     return out;
 }
+
+// Posterior predictive distribution (no reference counterpart; the reference's TODO:6 lists it).  theta: K x P x S array
+// and pi: S x K matrix as gibbs_full / gibbs_stickbreaking return them; newdata: M x P 0/1 integer matrix.
+// [[Rcpp::export]]
+List predictive_cpp(IntegerMatrix newdata, NumericVector theta, NumericMatrix pi) {
+    IntegerVector dim = theta.attr("dim");
+    if (dim.size() != 3) stop("theta must be a K x P x S array");
+    const int K = dim[0], P = dim[1], S = dim[2], M = newdata.nrow();
+    if (newdata.ncol() != P || pi.nrow() != S || pi.ncol() != K) stop("newdata / theta / pi dimensions do not match");
+    NumericVector logpred(M);
+    NumericMatrix member(M, K);
+    if (bmm_predictive(newdata.begin(), M, P, K, S, theta.begin(), pi.begin(), logpred.begin(), member.begin()) != BMM_OK)
+        stop(bmm_last_error());
+    return List::create(Named("log_pred") = logpred, Named("membership") = member);
+}

@@ -1037,3 +1037,46 @@ def test_chain_path_posterior_summaries(datasets, sampler, relabel):
     if (ns - 1 - burnin) % 2 == 0:      # the last sweep is a kept one
         assert np.array_equal(g["z_last"], zo[:, -1])
     assert g["z_last"].min() >= 1 and g["z_last"].max() <= K
+
+
+def test_predictive_distribution(datasets):
+    """Posterior predictive distribution from the kept draws (the reference only lists it in its TODO file, so
+    the check is the definition itself in float64): log 1/S sum_s sum_k pi_k prod_d theta^x (1 - theta)^(1 - x) and the
+    draw-averaged responsibilities, single chain and pooled chains, P above one packed word."""
+    _need_gpu()
+    X = datasets["K3_N1000_P5"]
+    fit = B.gibbs_full(X, 120, 3, burnin=20, relabel=True, burnrelabel=5, seed=4)
+    new = np.array([[a, b, c, d, e] for a in (0, 1) for b in (0, 1) for c in (0, 1) for d in (0, 1) for e in (0, 1)], dtype=np.int32)
+
+    def host(theta, pi, Xn):
+        K, P, S = theta.shape
+        ll = (Xn[:, None, :, None] * np.log(theta)[None] + (1 - Xn)[:, None, :, None] * np.log1p(-theta)[None]).sum(2)   # M x K x S
+        lw = ll + np.log(pi.T)[None]                                                                                    # M x K x S
+        mx = lw.max(1, keepdims=True)
+        per_draw = mx[:, 0] + np.log(np.exp(lw - mx).sum(1))                                                            # M x S
+        resp = np.exp(lw - per_draw[:, None, :]).mean(2)
+        m2 = per_draw.max(1, keepdims=True)
+        return m2[:, 0] + np.log(np.exp(per_draw - m2).mean(1)), resp
+
+    g = B.predictive(fit, new)
+    lp, resp = host(fit["theta"], fit["pi"], new)
+    np.testing.assert_allclose(g["log_pred"], lp, rtol=1e-10)
+    np.testing.assert_allclose(g["membership"], resp, rtol=1e-9, atol=1e-14)
+    assert abs(np.exp(g["log_pred"]).sum() - 1.0) < 1e-9            # the 32 patterns of P = 5 exhaust the sample space
+    np.testing.assert_allclose(g["membership"].sum(1), 1.0, rtol=1e-12)
+    # pooled chains
+    fit4 = B.gibbs_full(X, 60, 3, burnin=10, chains=4, seed=9)
+    g4 = B.predictive(fit4, new, membership=False)
+    lp4, _ = host(np.concatenate(list(fit4["theta"]), axis=2), np.concatenate(list(fit4["pi"]), axis=0), new)
+    np.testing.assert_allclose(g4["log_pred"], lp4, rtol=1e-10)
+    # P = 70 (three packed words), stick-breaking
+    rng = np.random.default_rng(1)
+    th = rng.uniform(0.1, 0.9, (4, 70))
+    Xb = (rng.random((600, 70)) < th[rng.integers(0, 4, 600)]).astype(np.int32)
+    fb = B.gibbs_stickbreaking(Xb, 40, 6, alpha=1.0, burnin=10, seed=2)
+    gb = B.predictive(fb, Xb[:50])
+    lpb, respb = host(fb["theta"], fb["pi"], Xb[:50])
+    np.testing.assert_allclose(gb["log_pred"], lpb, rtol=1e-10)
+    np.testing.assert_allclose(gb["membership"], respb, rtol=1e-8, atol=1e-14)
+    with pytest.raises(ValueError):
+        B.predictive(B.gibbs_collapsed(X, 30, 3, seed=1), new)
