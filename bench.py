@@ -846,6 +846,8 @@ def main():
         line["extra"]["collapsed_1024"] = collapsed_leg(rank, world, local, dist)
     if rank == 0 and world == 1 and not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
+        if a.workload == "c2":
+            line["extra"]["cpu_optimised"] = cpu_optimised(value, e2e_val)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
@@ -853,6 +855,30 @@ def main():
     if dist:
         dist.destroy_process_group()
     return 0
+
+
+def cpu_optimised(gpu_value, gpu_e2e):
+    """SURVEY 8d's optional row: the GPU path's ALGORITHM (de-duplicated rows, hoisted log tables, count histograms, one
+    uniform per allocation, online relabelling on the patterns) on the host cores (oracle/opt_cpu.cpp, -O3), so that the
+    algorithmic and the hardware share of the speed-up over the reference can be told apart."""
+    try:
+        import bmm_mcmc_b200 as B
+        from oracle import pyoracle as O
+        X = B.load_dataset(DATASET)
+        N = X.shape[0]
+        cores = os.cpu_count() or 1
+        O.opt_cpu_full_gibbs(X, K, 50, 5, cores, cores)                      # warm-up: threads, page faults
+        s1 = O.opt_cpu_full_gibbs(X, K, NSAMPLES, BURNIN, 2, 1)
+        one = N * (NSAMPLES - 1) * 2 / s1
+        chains = 32 * cores
+        sa = O.opt_cpu_full_gibbs(X, K, NSAMPLES, BURNIN, chains, cores)
+        allc = N * (NSAMPLES - 1) * chains / sa
+        return {"value": allc, "unit": "allocation updates/s", "cores": cores, "one_core": one, "kind": "port-optimised",
+                "sample": "%d chains x %d sweeps on %d threads (%.2f s); keeps the byte-wide allocation history per chain, "
+                          "returns no int32 matrices" % (chains, NSAMPLES - 1, cores, sa),
+                "gpu_device_over_all_cores": gpu_value / allc, "gpu_e2e_over_all_cores": gpu_e2e / allc}
+    except Exception as e:      # a baseline that cannot be built must not take the bench line with it
+        return {"unavailable": repr(e)[:200]}
 
 
 def _guarded_main():

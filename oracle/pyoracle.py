@@ -32,6 +32,9 @@ def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("oracle.cpp", "rrng.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    opt = os.path.join(_HERE, "libopt_cpu.so")
+    if force or not os.path.exists(opt) or os.path.getmtime(os.path.join(_HERE, "opt_cpu.cpp")) > os.path.getmtime(opt):
+        subprocess.check_call(["make", "-C", _HERE, "libopt_cpu.so"], stdout=subprocess.DEVNULL)
     ref_out = [os.path.join(_HERE, "_ref", f) for f in ("liblpsolve_ref.so", "libbmm_ref.so")]
     ref_src = [os.path.join(_HERE, "build_ref.sh"), os.path.join(_HERE, "rrng.h")] + \
         [os.path.join(_HERE, "shim", f) for f in ("RcppArmadillo.h", "ref_capi.cpp", "RcppArmadilloExtensions/sample.h")]
@@ -269,3 +272,18 @@ def gibbs_dp(X, nsamples, alpha=0.0, beta=0.5, gamma=0.5, a=1.0, b=1.0, burnin=N
         raise RuntimeError("oracle sampler rc=%d" % rc)
     r.update(nsamples=nsamples, burnin=burnin, relabel=relabel)
     return r
+
+
+def opt_cpu_full_gibbs(X, K, nsamples, burnin, chains, threads):
+    """Bench baseline (oracle/opt_cpu.cpp): `chains` chains of the count-maintaining, row-deduplicated CPU sampler with
+    online relabelling on `threads` host threads; returns wall seconds."""
+    import ctypes as C
+    build()
+    L = C.CDLL(os.path.join(_HERE, "libopt_cpu.so"))
+    L.opt_cpu_full_gibbs.restype = C.c_double
+    L.opt_cpu_full_gibbs.argtypes = [C.c_void_p] + [C.c_int] * 7
+    Xf = np.asfortranarray(X, dtype=np.int32)
+    s = L.opt_cpu_full_gibbs(Xf.ctypes.data, Xf.shape[0], Xf.shape[1], int(K), int(nsamples), int(burnin), int(chains), int(threads))
+    if s < 0:
+        raise RuntimeError("opt_cpu_full_gibbs: unsupported shape")
+    return s

@@ -182,3 +182,13 @@ def test_golden_outputs_unchanged(oracle, datasets):
                 assert np.array_equal(val, ref), (name, key)
             else:
                 np.testing.assert_allclose(val, ref, rtol=1e-12, atol=0, equal_nan=True, err_msg="%s %s" % (name, key))
+
+
+def test_optimised_cpu_baseline_runs(datasets):
+    """bench.py's extra.cpu_optimised leg (oracle/opt_cpu.cpp): builds, runs a few chains on two threads, rejects shapes it
+    does not cover.  It is only ever timed, never compared."""
+    from oracle import pyoracle as O
+    X = datasets["K3_N1000_P5"]
+    assert O.opt_cpu_full_gibbs(X, 3, 60, 10, 4, 2) > 0.0
+    with pytest.raises(RuntimeError):
+        O.opt_cpu_full_gibbs(np.zeros((10, 70), dtype=np.int32), 3, 10, 2, 1, 1)
