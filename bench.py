@@ -827,9 +827,8 @@ def main():
                 "d2h_bytes_per_step": int(d2h), "host_output_bytes_per_step": int(host_out),
                 "ms_per_step": 1e3 * tm[2] / a.steps,
                 "api": "bmm_mcmc_b200.gibbs_%s -> bmm_gibbs_%s (C ABI), pinned host output buffers; d2h bytes counted by the "
-                       "library: with one or two ranks per host the allocations cross PCIe as one byte each, sweep segment by "
-                       "sweep segment while the later sweeps run, and the host widens them to the two int32 matrices "
-                       "(z = perm[z_original]); with more ranks the device widens and the int32 matrices are DMA'd" % (smp, smp)},
+                       "library: the allocations cross PCIe as one byte each, sweep segment by sweep segment while the later "
+                       "sweeps run, and the host widens them to the two int32 matrices (z = perm[z_original])" % (smp, smp)},
         "gpu_launches": launches,
         "roofline": roofline,
         "extra": {"wall_ms_per_step": 1e3 * tm[1] / a.steps,

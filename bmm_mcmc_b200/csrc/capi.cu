@@ -1016,14 +1016,15 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
         // R-layout allocation histories are produced on the device by the finalize kernel
         // int32 output larger than a few MB: keep bytes on the device and widen on the host (fetch_z)
         const size_t zelems = (size_t)pl->C * pl->S * pl->N;
-        // Widening on the host moves a quarter of the bytes over PCIe but every rank's workers write the int32 matrices
-        // through the same host memory system: measured on the 8-GPU box (C2, 15 GB of int32 per rank and step) the call
-        // took 1035 ms with 8 ranks against 190 ms with one.  Each GPU has its own PCIe link, so with more than two
-        // ranks per host the device widens and the int32 matrices are DMA'd as they are.  BMM_FETCH_WIDEN=0/1 overrides.
+        // Widening on the host moves an eighth (a quarter without relabelling) of the bytes over PCIe; the int32 matrices are
+        // then written by the host cores.  With several ranks per host the ranks share those cores (fetch_widen divides the
+        // workers by LOCAL_WORLD_SIZE) and, above all, the host's memory: measured on the 8-GPU box (C2, 14.7 GB of int32 per
+        // rank and step, 118 GB per step over all ranks) the call takes 899 ms with host widening on 3 or 4 workers per rank
+        // against 1356 ms with device widening and int32 DMA -- either way ~100-140 GB/s into host memory is the limit, and
+        // the device-side widening costs 6 ms of the 37 ms run as well.  (Round 1 measured the opposite with 12 workers per
+        // rank oversubscribing the 32 cores.)  BMM_FETCH_WIDEN=0 keeps the int32 DMA path.
         const char *wenv = getenv("BMM_FETCH_WIDEN");
-        int local_ranks = 1;
-        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) local_ranks = atoi(lw) > 0 ? atoi(lw) : 1;
-        const bool widen_dflt = wenv ? wenv[0] != '0' : local_ranks <= 2;
+        const bool widen_dflt = wenv ? wenv[0] != '0' : true;
         const bool widen = !(args->flags & BMM_FLAG_COMPACT_Z) && zelems >= ((size_t)8 << 20) && widen_dflt;
         pl->deb = ((args->flags & BMM_FLAG_COMPACT_Z) || widen) ? 1 : 4;
         // z = perm[z_original] (full_gibbs.cpp:171-174): with host widening the relabelled matrix is derived on the host from

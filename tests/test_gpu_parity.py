@@ -750,13 +750,14 @@ def test_grid_tensor_relabel_single_pass(oracle, monkeypatch, sampler, N, P, K):
         assert np.array_equal(g["z"], h["z"]) and np.array_equal(g["theta"], h["theta"])
 
 
-def test_grid_tensor_kernels_many_tiles_per_cta(oracle, monkeypatch):
+@pytest.mark.parametrize("N,P,K", [(20_000 + 77, 64, 32), (9_000 + 5, 100, 24), (12_000 + 3, 20, 7)])
+def test_grid_tensor_kernels_many_tiles_per_cta(oracle, monkeypatch, N, P, K):
     """The warp-specialised tensor kernels (z-sweep and single-pass relabelling) with every mbarrier ring wrapping many
-    times: the grid is capped at 3 CTAs, so each CTA walks ~50 tiles (a full-size run has 528 per CTA; with the usual one
-    or two tiles per CTA of a test-sized input no ring ever wraps)."""
+    times: the grid is capped at 3 CTAs, so each CTA walks 25-50 tiles (a full-size run has 528 per CTA; with the usual one
+    or two tiles per CTA of a test-sized input no ring ever wraps).  P = 100 runs the two-warpgroup layout of the
+    relabelling kernel, P = 20 the shallowest operand stages."""
     _need_gpu()
     rng = np.random.default_rng(99)
-    N, P, K = 20_000 + 77, 64, 32
     th_true = rng.uniform(0.1, 0.9, (8, P))
     X = (rng.random((N, P)) < th_true[rng.integers(0, 8, N)]).astype(np.int32)
     burnin, M, ns = 6, 3, 13

@@ -64,13 +64,16 @@ dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("p2p", ["0", "1"])
-def test_n_sharded_equals_unsharded(tmp_path, p2p):
-    """p2p = 1: counts exchanged by the one-shot push over IPC-mapped peer memory instead of NCCL."""
+@pytest.mark.parametrize("p2p,cap", [("0", ""), ("1", ""), ("1", "4")])
+def test_n_sharded_equals_unsharded(tmp_path, p2p, cap):
+    """p2p = 1: counts exchanged by the one-shot push over IPC-mapped peer memory instead of NCCL.  cap = 4: the ranks'
+    tensor kernels run on 4 CTAs each (~40 tiles per CTA: every mbarrier ring wraps), the unsharded comparison on 148."""
     import bmm_mcmc_b200 as B
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, BMM_ROOT=ROOT, BMM_OUT=str(tmp_path), BMM_P2P=p2p)
+    if cap:
+        env["BMM_GRID_MAX_CTAS"] = cap
     for attempt in range(3):        # a probed "free" port can be taken again before torchrun binds it
         s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
