@@ -289,13 +289,17 @@ __global__ void grid_assign_kernel(int K, double *acc, int cost_in_smem, int *pe
     }
 }
 
+// Index type of the element-wise relabelling kernels: 32-bit while N * K allows it (a 64-bit division per element by the
+// run-time K held grid_qmean_kernel at 1.5 TB/s)
 // fixed (BMM_FLAG_STEPHENS_FIXED): perm is the inverse permutation and Q' the running mean (j Q + p) / (j + 1)
+template <typename I>
 __global__ void grid_qupdate_kernel(long long N, int K, float *__restrict__ Q, const float *__restrict__ P,
                                     const int *__restrict__ perm, int sample_num, int fixed) {
     const float sn = (float)sample_num, inv = 1.f / (float)(sample_num + 1);
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N * K; e += (long long)gridDim.x * blockDim.x) {
-        const long long i = e / K;
-        const int k = (int)(e % K);
+    const I total = (I)(N * K), step = (I)((long long)gridDim.x * blockDim.x);
+    for (I e = (I)((long long)blockIdx.x * blockDim.x + threadIdx.x); e < total; e += step) {
+        const I i = e / (I)K;
+        const int k = (int)(e - i * (I)K);
         const float pr = P[i * K + perm[k]];
         Q[e] = fixed ? (sn * Q[e] + pr) * inv : sn * (Q[e] + pr) * inv;   // (stephens.cpp:87-92)
     }
@@ -314,13 +318,15 @@ __global__ void grid_clamp_kernel(long long n, float *p) {
 }
 
 // batch: Q[:, k] = mean_t cube[t][:, perm[t][k]] (stephens.cpp:37-43); perm is [M][K]
+template <typename I>
 __global__ void grid_qmean_kernel(long long N, int K, int M, const float *__restrict__ cube, const int *__restrict__ perm,
                                   float *__restrict__ Q) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N * K; e += (long long)gridDim.x * blockDim.x) {
-        const long long i = e / K;
-        const int k = (int)(e % K);
+    const I total = (I)(N * K), step = (I)((long long)gridDim.x * blockDim.x);
+    for (I e = (I)((long long)blockIdx.x * blockDim.x + threadIdx.x); e < total; e += step) {
+        const I i = e / (I)K;
+        const int k = (int)(e - i * (I)K);
         float acc = 0.f;
-        for (int t = 0; t < M; ++t) acc += cube[(size_t)t * N * K + i * K + perm[t * K + k]];
+        for (int t = 0; t < M; ++t) acc += cube[(size_t)t * N * K + (size_t)i * K + perm[t * K + k]];
         Q[e] = acc / (float)M;
     }
 }
@@ -397,7 +403,8 @@ cudaError_t launch_grid_invert_perm(int n, int K, const int *perm, int *inv, cud
 
 cudaError_t launch_grid_qupdate(long long N, int K, float *Q, const float *P, const int *perm, int sample_num,
                                 int sm_count, cudaStream_t st, int fixed) {
-    grid_qupdate_kernel<<<sm_count * 8, 256, 0, st>>>(N, K, Q, P, perm, sample_num, fixed);
+    if (N * K < (1LL << 31) - (long long)sm_count * 8 * 256) grid_qupdate_kernel<unsigned><<<sm_count * 8, 256, 0, st>>>(N, K, Q, P, perm, sample_num, fixed);
+    else grid_qupdate_kernel<long long><<<sm_count * 8, 256, 0, st>>>(N, K, Q, P, perm, sample_num, fixed);
     g_launches++;
     return cudaGetLastError();
 }
@@ -410,7 +417,8 @@ cudaError_t launch_grid_clamp(long long n, float *p, int sm_count, cudaStream_t 
 
 cudaError_t launch_grid_qmean(long long N, int K, int M, const float *cube, const int *perm, float *Q, int sm_count,
                               cudaStream_t st) {
-    grid_qmean_kernel<<<sm_count * 8, 256, 0, st>>>(N, K, M, cube, perm, Q);
+    if (N * K < (1LL << 31) - (long long)sm_count * 8 * 256) grid_qmean_kernel<unsigned><<<sm_count * 8, 256, 0, st>>>(N, K, M, cube, perm, Q);
+    else grid_qmean_kernel<long long><<<sm_count * 8, 256, 0, st>>>(N, K, M, cube, perm, Q);
     g_launches++;
     return cudaGetLastError();
 }

@@ -960,14 +960,15 @@ def test_posterior_means_collapsed_and_stickbreaking(oracle, datasets):
         assert (np.abs(gm - om) < 4 * se).all(), ("stickbreaking", idx, gm, om)
 
 
-@pytest.mark.parametrize("relabel", [False, True])
-def test_grid_posterior_summaries(datasets, relabel):
+@pytest.mark.parametrize("relabel,precision", [(False, "fp64"), (True, "fp64"), (True, "fp32")])
+def test_grid_posterior_summaries(datasets, relabel, precision):
     """z_freq / z_last (what a large-N caller keeps instead of the S x N history) equal the same summaries
-    computed from the full history; and they are available with no_z_history."""
+    computed from the full history; and they are available with no_z_history.  fp32 = the tensor path, whose
+    relabelling runs its assignment on a side stream: the summary must wait for it."""
     _need_gpu()
     X = datasets["K3_N1000_P5"]
     K, ns, burnin = 3, 60, 20
-    kw = dict(burnin=burnin, relabel=relabel, burnrelabel=5, seed=6, grid_path=True)
+    kw = dict(burnin=burnin, relabel=relabel, burnrelabel=5, seed=6, grid_path=True, precision=precision)
     g = B.gibbs_full(X, ns, K, probes=("z_freq", "z_last"), **kw)
     freq = np.stack([(g["z"] == k + 1).sum(0) for k in range(K)], 1)
     assert np.array_equal(g["z_freq"], freq)
