@@ -1044,8 +1044,10 @@ int bmm_plan_create(int32_t sampler, const bmm_args *args, const bmm_init *init,
             int nseg = senv ? atoi(senv) : (pl->S >= 1024 ? 4 : pl->S / 256);
             if (pl->thin != 1 || nseg < 1) nseg = 1;
             pl->seg_slot.assign(1, 0);
+            // a short first segment (half a share) lets the host start while as much of the run as possible is still ahead
             for (int g = 1; g < nseg; ++g) {
-                const int b = (int)(((long long)pl->S * g / nseg) & ~63LL);
+                const long long num = 2LL * g - 1, den = 2LL * nseg - 1;
+                const int b = (int)((((long long)pl->S * num) / den) & ~63LL);
                 if (b > pl->seg_slot.back() && b < pl->S) pl->seg_slot.push_back(b);
             }
             pl->seg_slot.push_back(pl->S);
@@ -1216,9 +1218,10 @@ int bmm_plan_fetch(bmm_plan *pl, bmm_out *out) {
         for (size_t g = 0; g < nseg; ++g) {
             const int s0 = pl->seg_slot[g], L = pl->seg_slot[g + 1] - s0;
             CU(cudaStreamWaitEvent(pl->copy_stream, nseg > 1 ? pl->seg_ev[g] : pl->ev1, 0));
-            if (perm) {   // this segment's permutations are final: the whole (small) array again, rows < s0 + L are valid
-                CU(cudaMemcpyAsync(perm, pl->perm_out.p, C * S * K * 4, cudaMemcpyDeviceToHost, pl->copy_stream));
-                g_fetch_bytes += C * S * K * 4;
+            if (perm) {   // this segment's permutations: columns [s0, s0 + L) of every (chain, label) row of S entries
+                CU(cudaMemcpy2DAsync(perm + s0, S * 4, pl->perm_out.as<int>() + s0, S * 4, (size_t)L * 4, C * K, cudaMemcpyDeviceToHost,
+                                     pl->copy_stream));
+                g_fetch_bytes += C * K * (size_t)L * 4;
                 CU(cudaStreamSynchronize(pl->copy_stream));
             }
             const size_t off = C * N * (size_t)s0, n = C * N * (size_t)L;
