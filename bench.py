@@ -455,17 +455,24 @@ def run_grid(a):
     dur_s = kern[0] / a.steps / (ns - 1) / 1e3
     achieved = n_local * bytes_per_update / dur_s / 1e9
     traffic = None   # dram bytes of the dominant kernel's launch from the committed ncu --set full capture (same rows per GPU)
+    ncu_pipes = None  # ... and its issue-slot / MUFU / tensor-pipe utilisation from the same capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f).get(tkey, {})
+        if not tr:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f).get(tkey, {})
         if tr.get("n") == n_local and tr.get("dram_bytes_read") is not None:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            ncu_pipes = tr.get("ncu")
     except Exception:
         pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
             "kernel": "%s (%d rows, %d B/update)" % (kname, n_local, bytes_per_update),
             "kernel_ms": dur_s * 1e3, "kernel_share_of_step": float(kern[0] / max(kern[:3].sum() + kern[3], 1e-9))}
+    if ncu_pipes:
+        roof["ncu"] = ncu_pipes
     if relabel and kern[2] > 0:
         # with relabelling the dominant kernel is the single-pass relabelling kernel: Q once in, once out (fp32) plus the
         # packed row per update (2*K*4 + ceil(P/8) bytes), HBM-bound
@@ -478,6 +485,7 @@ def run_grid(a):
                 tr = json.load(f).get("big_relabel_ws_kernel", {})
             if tr.get("n") == n_local:
                 rtraffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                ncu_pipes = tr.get("ncu")
         except Exception:
             pass
         roof = {"bound": "hbm", "achieved": racc, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": racc / pk["hbm_gbs"],
@@ -485,6 +493,8 @@ def run_grid(a):
                 "kernel": "big_relabel_ws_kernel (%d rows, %d B/update: Q read + Q written in fp32, packed row)" % (n_local, rb),
                 "kernel_ms": rdur * 1e3, "kernel_share_of_step": float(kern[2] / max(kern[:3].sum() + kern[3], 1e-9)),
                 "sweep_kernel_ms": dur_s * 1e3}
+        if ncu_pipes:
+            roof["ncu"] = ncu_pipes
     elif 2 * K * P / bytes_per_update > 1e3 * pk["bf16_tflops_sustained"] / pk["hbm_gbs"]:
         # arithmetic intensity above the ridge (C5: 2044 flop/B vs 216): the tensor pipe bounds it
         flops = 2.0 * K * P * n_local          # algorithmic: one K x P contraction per update
@@ -536,6 +546,19 @@ def _max_over_ranks(x, dist):
     t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def ncu_record(key, n_rows):
+    """Issue-slot / MUFU / tensor-pipe utilisation and DRAM bytes of one launch of `key` from the committed ncu --set full
+    capture (profiles/r02_traffic.json), when it was taken at this many rows per GPU; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tr = json.load(f).get(key, {})
+        if tr.get("n") == n_rows and tr.get("ncu"):
+            return dict(tr["ncu"], dram_bytes=tr["dram_bytes_read"] + tr["dram_bytes_write"], source=tr.get("source"))
+    except Exception:
+        pass
+    return None
 
 
 def sharded_leg(rank, world, local, dist, steps=3, warmup=2):
@@ -604,6 +627,9 @@ def sharded_leg(rank, world, local, dist, steps=3, warmup=2):
             "hbm_bytes_per_update": bytes_upd,
             "tensor_frac": 2.0 * K * P * n_local / (sweep_us * 1e-6) / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
             "gpu_launches": launches, "clocks": clk}
+        rec = ncu_record("big_relabel_ws_kernel" if relabel else "big_sweep_ws_kernel", n_local)
+        if rec:
+            out[name]["ncu_dominant_kernel"] = rec
     bdist.finalize()
     return out
 
