@@ -278,27 +278,31 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lp_sweep_kernel(const BigParams
       }
       __syncwarp();
     } else {
-      if (tid == MW * 32) {
+      {
         // ================= MMA issuer: per step 4 x K16 for each of the two tiles against the same B stage =================
+        // (all 32 lanes walk the loop, one elected lane issues: umma.cuh::elect_one)
         constexpr uint32_t IDESC = umma_idesc_f16(128, LP_NCOL, 0, 0);
         long long g = 0;
         for (long long it = 0; it < mine && ok; ++it) {
-            if (it > 0) ok = mbar_wait(accempty, (uint32_t)((it - 1) & 1));
+            if (it > 0) ok = __all_sync(0xffffffffu, mbar_wait(accempty, (uint32_t)((it - 1) & 1)));
             tc_fence_after();
             for (int c = 0; c < nsteps && ok; ++c, ++g) {
                 const int s = (int)(g % LP_NS);
-                ok = mbar_wait(full0 + 8 * s, (uint32_t)((g / LP_NS) & 1));
+                ok = __all_sync(0xffffffffu, mbar_wait(full0 + 8 * s, (uint32_t)((g / LP_NS) & 1)));
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
+                if (elect_one()) {
+                    const uint32_t a0 = smem_u32(smem + s * LP_STAGE), b0 = a0 + LP_A_STAGE;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                    for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-                    for (int h = 0; h < LP_TM; ++h)
-                        umma_f16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + h * LP_A_TILE + kk * 2 * 2048, 2048, 128),
-                                  umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
-                umma_commit(empty0 + 8 * s);
-                if (c == nsteps - 1) umma_commit(accfull);
+                        for (int h = 0; h < LP_TM; ++h)
+                            umma_f16(acc + (uint32_t)(h * LP_NCOL), umma_desc(a0 + h * LP_A_TILE + kk * 2 * 2048, 2048, 128),
+                                      umma_desc(b0 + kk * 2 * (LP_NCOL * 16), LP_NCOL * 16, 128), IDESC, (c | kk) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);
+                    if (c == nsteps - 1) umma_commit(accfull);
+                }
+                __syncwarp();
             }
         }
       }

@@ -192,22 +192,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         // ================= GEMM1 issuer =================
         // (one thread per GEMM: a single thread issuing both was the bottleneck -- ~300 dependent
         //  instructions per tile; descriptors are base + constant offset in the 16-byte address field)
-        if (tid == 128) {
+        // all 32 lanes walk the loop (uniform control flow), one elected lane issues
+        {
             constexpr uint32_t IDESC1 = umma_idesc_f16(128, WS_PARTS * WS_KC, 0, 0);
             const uint64_t da0 = umma_desc(smem_u32(smem), WS_CHUNK, 128), db0 = umma_desc(smem_u32(B1), WS_B1_ROW, 128);
             int s = 0, a = 0;
             uint32_t ph_s = 0, ph_a = 0;
-            for (int k = 0; k < T && ok; ++k) {
+            for (int k = 0; k < T; ++k) {
                 ok = mbar_wait(full_a + 8 * s, ph_s);
                 if (ok && k >= WS_NA) ok = mbar_wait(acc_free + 8 * a, ph_a ^ 1u);
+                ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
                 tc_fence_after();
-                const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
 #pragma unroll
-                for (int kk = 0; kk < NCH / 2; ++kk)
-                    umma_f16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
-                              db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
-                umma_commit(acc_full + 8 * a);
+                    for (int kk = 0; kk < NCH / 2; ++kk)
+                        umma_f16(tmem_base + (uint32_t)(a * WS_PARTS * WS_KC), da + (uint64_t)((kk * 2 * WS_CHUNK) >> 4),
+                                  db0 + (uint64_t)((kk * 2 * WS_B1_ROW) >> 4), IDESC1, kk ? 1u : 0u);
+                    umma_commit(acc_full + 8 * a);
+                }
+                __syncwarp();
                 if (++s == WS_NS) { s = 0; ph_s ^= 1u; }
                 if (++a == WS_NA) { a = 0; ph_a ^= 1u; }
             }
@@ -215,25 +220,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) big_sweep_ws_kernel(const BigPa
         __syncwarp();
     } else if (warp == 5) {
         // ================= GEMM2 issuer =================
-        if (tid == 160) {
+        {
             constexpr uint32_t IDESC2 = umma_idesc_f16(128, WS_KC, 1, 1);
             const uint64_t da0 = umma_desc(smem_u32(smem), 128, WS_CHUNK), db0 = umma_desc(smem_u32(smem + L::B2_OFF), 128, WS_CHUNK);
             int s = 0, b = 0;
             uint32_t ph_b = 0;
-            for (int q = 0; q < T && ok; ++q) {
-                ok = mbar_wait(b2_full + 8 * b, ph_b);
+            for (int q = 0; q < T; ++q) {
+                ok = __all_sync(0xffffffffu, mbar_wait(b2_full + 8 * b, ph_b));
                 if (!ok) break;
                 tc_fence_after();
-                const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4), db = db0 + (uint64_t)((b * WS_B2_BYTES) >> 4);
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4), db = db0 + (uint64_t)((b * WS_B2_BYTES) >> 4);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    umma_f16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(free_a + 8 * s);
-                umma_commit(b2_free + 8 * b);
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_f16(acc2, da + (uint64_t)((kk * 256) >> 4), db + (uint64_t)((kk * 256) >> 4), IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(free_a + 8 * s);
+                    umma_commit(b2_free + 8 * b);
+                }
+                __syncwarp();
                 if (++s == WS_NS) s = 0;
                 if (++b == WS_NB) { b = 0; ph_b ^= 1u; }
             }
-            umma_commit(all_done);
+            if (elect_one()) umma_commit(all_done);
         }
         __syncwarp();
     } else if (warp >= 8) {

@@ -272,26 +272,31 @@ __global__ void __launch_bounds__(WsrLayout<NCH>::THREADS, 1) big_relabel_ws_ker
         }
     } else if (warp == 4) {
         // ================= GEMM1 issuer =================
-        if (tid == 128) {
+        // all 32 lanes walk the loop, one elected lane issues (umma.cuh::elect_one)
+        {
             constexpr uint32_t IDESC1 = umma_idesc_f16(128, 2 * WS_KC, 0, 0);
             const uint64_t da0 = umma_desc(smem_u32(smem), WSR_CHUNK, 128), db0 = umma_desc(smem_u32(B1), WSR_B_ROW, 128);
             int s = 0, a = 0;
             uint32_t ph_s = 0, ph_a = 0;
-            for (int k = 0; k < T && ok; ++k) {
+            for (int k = 0; k < T; ++k) {
                 ok = mbar_wait(full_a + 8 * s, ph_s);
                 if (ok && k >= WSR_NA) ok = mbar_wait(acc_free + 8 * a, ph_a ^ 1u);
+                ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
                 tc_fence_after();
-                const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
-                // X . hi^T + X . lo^T into one accumulator: the A stage is read twice, the two terms never meet in registers
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)((s * L::A_STAGE) >> 4);
+                    // X . hi^T + X . lo^T into one accumulator: the A stage is read twice, the two terms never meet in registers
 #pragma unroll
-                for (int kk = 0; kk < NCH; ++kk) {
-                    const int ka = kk % (NCH / 2);
-                    umma_f16(tmem_base + (uint32_t)(a * 2 * WS_KC), da + (uint64_t)((ka * 2 * WSR_CHUNK) >> 4),
-                              db0 + (uint64_t)(((kk / (NCH / 2)) * NCH * WSR_B_ROW + ka * 2 * WSR_B_ROW) >> 4), IDESC1, kk ? 1u : 0u);
+                    for (int kk = 0; kk < NCH; ++kk) {
+                        const int ka = kk % (NCH / 2);
+                        umma_f16(tmem_base + (uint32_t)(a * 2 * WS_KC), da + (uint64_t)((ka * 2 * WSR_CHUNK) >> 4),
+                                  db0 + (uint64_t)(((kk / (NCH / 2)) * NCH * WSR_B_ROW + ka * 2 * WSR_B_ROW) >> 4), IDESC1, kk ? 1u : 0u);
+                    }
+                    umma_commit(acc_full + 8 * a);
+                    umma_commit(free_a + 8 * s);        // the A stage is only read by this contraction
                 }
-                umma_commit(acc_full + 8 * a);
-                umma_commit(free_a + 8 * s);        // the A stage is only read by this contraction
+                __syncwarp();
                 if (++s == NS) { s = 0; ph_s ^= 1u; }
                 if (++a == WSR_NA) { a = 0; ph_a ^= 1u; }
             }
@@ -299,29 +304,32 @@ __global__ void __launch_bounds__(WsrLayout<NCH>::THREADS, 1) big_relabel_ws_ker
         __syncwarp();
     } else if (warp == 5) {
         // ================= cost-MMA issuer =================
-        if (tid == 160 && do_cost) {
+        if (do_cost) {
             constexpr uint32_t IDESC2 = umma_idesc_f16(128, 128, 1, 1);
             int b = 0;
             uint32_t ph_b = 0;
-            for (int q = 0; q < T && ok; ++q) {
-                ok = mbar_wait(st_full + 8 * b, ph_b);
+            for (int q = 0; q < T; ++q) {
+                ok = __all_sync(0xffffffffu, mbar_wait(st_full + 8 * b, ph_b));
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t sb = smem_u32(smem + L::ST_OFF + b * WSR_STAGE);
+                if (elect_one()) {
+                    const uint32_t sb = smem_u32(smem + L::ST_OFF + b * WSR_STAGE);
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const uint64_t ah = umma_desc(sb + 0 * WSR_MAT + kk * 256, 128, 512);
-                    const uint64_t al = umma_desc(sb + 1 * WSR_MAT + kk * 256, 128, 512);
-                    const uint64_t bh = umma_desc(sb + 2 * WSR_MAT + kk * 256, 128, 512);
-                    const uint64_t bl = umma_desc(sb + 3 * WSR_MAT + kk * 256, 128, 512);
-                    umma_f16(acc_cost, ah, bh, IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
-                    umma_f16(acc_cost, ah, bl, IDESC2, 1u);
-                    umma_f16(acc_cost, al, bh, IDESC2, 1u);
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint64_t ah = umma_desc(sb + 0 * WSR_MAT + kk * 256, 128, 512);
+                        const uint64_t al = umma_desc(sb + 1 * WSR_MAT + kk * 256, 128, 512);
+                        const uint64_t bh = umma_desc(sb + 2 * WSR_MAT + kk * 256, 128, 512);
+                        const uint64_t bl = umma_desc(sb + 3 * WSR_MAT + kk * 256, 128, 512);
+                        umma_f16(acc_cost, ah, bh, IDESC2, (q > 0 || kk > 0) ? 1u : 0u);
+                        umma_f16(acc_cost, ah, bl, IDESC2, 1u);
+                        umma_f16(acc_cost, al, bh, IDESC2, 1u);
+                    }
+                    umma_commit(st_free + 8 * b);
                 }
-                umma_commit(st_free + 8 * b);
+                __syncwarp();
                 if (++b == WSR_NB) { b = 0; ph_b ^= 1u; }
             }
-            umma_commit(all_done);
+            if (elect_one()) umma_commit(all_done);
         }
         __syncwarp();
     } else if (warp == 6) {

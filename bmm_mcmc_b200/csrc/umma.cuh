@@ -33,6 +33,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// One lane of a converged warp (the lowest), the same one every time.  The MMA-issuing warps run their loops with all 32
+// lanes and issue under this predicate: with `if (tid == X)` around the loop the descriptors reach the uniform registers
+// through a per-instruction ELECT / BRA.U.ANY loop, ~108 cycles of issuer time per tcgen05.mma (ncu source view of the
+// tensor sweep, round 2) -- eight of them per tile made the count contraction's issuer the slowest stage of the pipeline.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
