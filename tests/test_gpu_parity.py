@@ -645,6 +645,19 @@ def test_fetch_derived_z_odd_shapes(datasets, monkeypatch, sampler):
     assert np.array_equal(a["z_freq"], np.stack([(a["z"] == k + 1).sum(1) for k in range(K)], axis=2))
 
 
+def test_fetch_widening_above_16_labels(datasets, monkeypatch):
+    """More than 16 labels: the relabelled matrix is not derived on the host (the byte table covers K <= 16), both matrices
+    travel as bytes, still sweep segment by sweep segment."""
+    _need_gpu()
+    X = datasets["K2_N1000_P5"]
+    kw = dict(burnin=20, relabel=True, burnrelabel=5, maxK=20, chains=40, seed=12)
+    a = B.gibbs_dp(X, 20 + 300, **kw)                    # 40 * 300 * 1000 = 12M allocations, S = 300: one 256-slot segment + rest
+    monkeypatch.setenv("BMM_FETCH_WIDEN", "0")
+    b = B.gibbs_dp(X, 20 + 300, **kw)
+    for k in ("z", "z_original", "permutations"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("name,K", [("K3_N1000_P5", 3), ("K2_N1000_P5", 2)])
 def test_grid_path_relabel_replay(oracle, datasets, name, K):
     """Stephens batch + online relabelling with the streaming grid kernels (float P / Q, warp Jonker-Volgenant /
