@@ -123,6 +123,13 @@ inline void rmultinom(int n, double *prob, int K, int *rN) {
     rN[K - 1] = n;
 }
 
+// options() look-ups of r-package/src/host.cpp: the stand-in has no options, every look-up is NULL (defaults apply)
+inline SEXP Rf_install(const char *) { return nullptr; }
+inline SEXP Rf_GetOption1(SEXP) { return nullptr; }
+inline bool Rf_isNull(SEXP s) { return s == nullptr; }
+inline double Rf_asReal(SEXP) { return 0.0; }
+inline int Rf_asInteger(SEXP) { return 0; }
+
 namespace R {
 inline double rgamma(double shape, double scale) { return bmm_shim::rng().rgamma(shape, scale); }
 inline double rbeta(double a, double b) { return bmm_shim::rng().rbeta(a, b); }
@@ -698,18 +705,49 @@ inline std::vector<T> sexp_values(const SEXPREC *s) {  // with R's int <-> doubl
     return out;
 }
 
+// Rcpp::Dimension(K, P, S): the dim attribute of an array-valued Vector (used by r-package/src/host.cpp)
+class Dimension {
+   public:
+    std::vector<int> v;
+    Dimension(int a) : v{a} {}
+    Dimension(int a, int b) : v{a, b} {}
+    Dimension(int a, int b, int c) : v{a, b, c} {}
+    size_t prod() const {
+        size_t n = 1;
+        for (int x : v) n *= (size_t)x;
+        return n;
+    }
+};
+
 template <typename T>
 class Vector {
    public:
     std::vector<T> d;
+    std::vector<int> dimv;  // dim attribute, empty for a plain vector
     Vector() {}
     Vector(int n) : d((size_t)n, T(0)) {}
-    Vector(const RObject &o) : d(sexp_values<T>(o.p.get())) {}
-    Vector(SEXP s) : d(sexp_values<T>(s)) {}
+    Vector(const Dimension &dm) : d(dm.prod(), T(0)), dimv(dm.v) {}
+    Vector(const RObject &o) : d(sexp_values<T>(o.p.get())), dimv(o.p.get() ? o.p->dim : std::vector<int>()) {}
+    Vector(SEXP s) : d(sexp_values<T>(s)), dimv(s ? s->dim : std::vector<int>()) {}
     Vector &operator=(const RObject &o) {
         d = sexp_values<T>(o.p.get());
+        dimv = o.p.get() ? o.p->dim : std::vector<int>();
         return *this;
     }
+    // x.attr("dim") read as an IntegerVector (the only attribute the host reads)
+    class AttrProxy {
+       public:
+        const Vector &v;
+        std::string name;
+        AttrProxy(const Vector &v_, const std::string &n) : v(v_), name(n) {}
+        operator Vector<int>() const {
+            if (name != "dim") throw Rcpp::exception("Rcpp shim: only the dim attribute is modelled");
+            Vector<int> out((int)v.dimv.size());
+            for (size_t i = 0; i < v.dimv.size(); ++i) out.d[i] = v.dimv[i];
+            return out;
+        }
+    };
+    AttrProxy attr(const std::string &name) const { return AttrProxy(*this, name); }
     inline T &operator[](int i) { return d[(size_t)i]; }
     inline const T &operator[](int i) const { return d[(size_t)i]; }
     inline T &operator()(int i) {
@@ -789,6 +827,11 @@ class Matrix {
     }
     int nrow() const { return nr; }
     int ncol() const { return nc; }
+    typedef T *iterator;  // column-major payload, as in Rcpp
+    iterator begin() { return d.data(); }
+    iterator end() { return d.data() + d.size(); }
+    const T *begin() const { return d.data(); }
+    const T *end() const { return d.data() + d.size(); }
     inline T &operator()(int i, int j) { return d[(size_t)i + (size_t)nr * j]; }
     inline const T &operator()(int i, int j) const { return d[(size_t)i + (size_t)nr * j]; }
     MatrixRow<T> operator()(int i, const Underscore &) { return MatrixRow<T>(*this, i); }
@@ -810,7 +853,7 @@ RObject wrap_array(const T *src, size_t n, std::vector<int> dim) {
 }
 inline RObject wrap(const RObject &o) { return o; }
 template <typename T>
-RObject wrap(const Vector<T> &v) { return wrap_array(v.d.data(), v.d.size(), {}); }
+RObject wrap(const Vector<T> &v) { return wrap_array(v.d.data(), v.d.size(), v.dimv); }
 template <typename T>
 RObject wrap(const Matrix<T> &m) { return wrap_array(m.d.data(), m.d.size(), {m.nr, m.nc}); }
 template <typename T>
@@ -848,6 +891,23 @@ class List {
         }
     };
     Proxy operator[](const std::string &name) { return Proxy(*this, name); }
+    // List::create(Named("a") = x, Named("b") = y, ...)
+    struct NamedValue {
+        std::string name;
+        RObject value;
+    };
+    static void fill(List &) {}
+    template <typename... Rest>
+    static void fill(List &l, const NamedValue &nv, const Rest &...rest) {
+        l.set(nv.name, nv.value);
+        fill(l, rest...);
+    }
+    template <typename... Args>
+    static List create(const Args &...args) {
+        List l;
+        fill(l, args...);
+        return l;
+    }
     void set(const std::string &name, const RObject &v) {
         for (size_t i = 0; i < p->names.size(); ++i)
             if (p->names[i] == name) {
@@ -859,6 +919,13 @@ class List {
     }
 };
 inline RObject wrap(const List &l) { return RObject(l.p); }
+class Named {
+   public:
+    std::string name;
+    explicit Named(const std::string &n) : name(n) {}
+    template <typename T>
+    List::NamedValue operator=(const T &v) const { return List::NamedValue{name, wrap(v)}; }
+};
 
 // ---- as -----------------------------------------------------------------------------------------
 template <typename T> struct as_tag {};

@@ -4,8 +4,9 @@
 // storage modes as full_gibbs.cpp:233-248, stickbreaking.cpp:238-254, collapsed_gibbs.cpp:229-243,
 // collapsed_gibbs_dp.cpp:285-299) and turns a non-zero return code into an R error.
 //
-// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no R / Rcpp.  Everything below the C ABI
-// is exercised through the same entry points by tests/test_gpu_parity.py (ctypes).
+// The build image has no R / Rcpp: tests/test_rhost.py compiles this file, unmodified, against the Rcpp stand-in of
+// oracle/shim/ and checks on the GPU that every element of the returned lists equals the ctypes path's.  Everything
+// below the C ABI is exercised through the same entry points by tests/test_gpu_parity.py.
 #include <Rcpp.h>
 
 #include "bmm_capi.h"
