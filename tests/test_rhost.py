@@ -5,7 +5,6 @@ is how the host's argument forwarding, the names / shapes / storage modes of the
 CPU: it builds, links and fails loudly without a device.  GPU: every element equals the ctypes path's for the same key."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -15,21 +14,13 @@ from bmm_mcmc_b200 import _lib
 from bmm_mcmc_b200.rcompat import RRng
 from conftest import ROOT, gpu_available
 
-HERE = os.path.join(ROOT, "tests", "rhost")
-SO = os.path.join(HERE, "_build", "librhost.so")
-
-
 def _build():
-    src = [os.path.join(HERE, "driver.cpp"), os.path.join(ROOT, "r-package", "src", "host.cpp"),
-           os.path.join(ROOT, "oracle", "shim", "RcppArmadillo.h"), os.path.join(ROOT, "include", "bmm_capi.h")]
-    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
-        os.makedirs(os.path.dirname(SO), exist_ok=True)
-        _lib.lib()      # libbmm_b200.so must exist
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", os.path.join(ROOT, "oracle", "shim"),
-                               "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "include"), src[0], "-o", SO,
-                               "-L", os.path.join(ROOT, "bmm_mcmc_b200"), "-l:libbmm_b200.so",
-                               "-Wl,-rpath," + os.path.join(ROOT, "bmm_mcmc_b200")])
-    L = C.CDLL(SO)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rhost_build", os.path.join(ROOT, "tests", "rhost", "build.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    _lib.lib()      # libbmm_b200.so must exist
+    L = C.CDLL(m.build())
     L.rhost_last_error.restype = C.c_char_p
     return L
 
