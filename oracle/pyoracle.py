@@ -287,3 +287,17 @@ def opt_cpu_full_gibbs(X, K, nsamples, burnin, chains, threads):
     if s < 0:
         raise RuntimeError("opt_cpu_full_gibbs: unsupported shape")
     return s
+
+
+def opt_cpu_collapsed_gibbs(X, K, nsamples, chains, threads):
+    """Bench baseline (oracle/opt_cpu.cpp): count-maintaining collapsed sampler in product form; returns wall seconds."""
+    import ctypes as C
+    build()
+    L = C.CDLL(os.path.join(_HERE, "libopt_cpu.so"))
+    L.opt_cpu_collapsed_gibbs.restype = C.c_double
+    L.opt_cpu_collapsed_gibbs.argtypes = [C.c_void_p] + [C.c_int] * 6
+    Xf = np.asfortranarray(X, dtype=np.int32)
+    s = L.opt_cpu_collapsed_gibbs(Xf.ctypes.data, Xf.shape[0], Xf.shape[1], int(K), int(nsamples), int(chains), int(threads))
+    if s < 0:
+        raise RuntimeError("opt_cpu_collapsed_gibbs: unsupported shape")
+    return s

@@ -192,3 +192,4 @@ def test_optimised_cpu_baseline_runs(datasets):
     assert O.opt_cpu_full_gibbs(X, 3, 60, 10, 4, 2) > 0.0
     with pytest.raises(RuntimeError):
         O.opt_cpu_full_gibbs(np.zeros((10, 70), dtype=np.int32), 3, 10, 2, 1, 1)
+    assert O.opt_cpu_collapsed_gibbs(X, 3, 40, 4, 2) > 0.0
